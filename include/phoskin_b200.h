@@ -1,0 +1,123 @@
+/*
+ * phoskin_b200.h — C ABI of the B200-native ensemble ODE engine for PhosKinTime's hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / numpy types),
+ * and replaces a *loop of single calls* of one reference function (reference = Python, so the
+ * binding a maintainer adds is a ctypes stub — see INTEGRATION.md):
+ *
+ *   pk_local_solve_batch   <- models/distmod.py:93-134, models/succmod.py:114-152,
+ *                             models/randmod.py:249-305   solve_ode(params, init_cond, num_psites, t)
+ *                             selected by models/__init__.py:6-12 (ODE_MODEL plugin point)
+ *   loss fields of the job <- config/config.py:176-226 score_fit; paramest/normest.py:403-423
+ *                             (regularised curve_fit residual, sigma-weighted)
+ *   Y fields of the job    <- sensitivity/analysis.py:89-176 _compute_Y (5 metrics)
+ *   pk_morris_ee           <- SALib.analyze.morris.analyze as called at sensitivity/analysis.py:264
+ *   pk_allgather_f64       <- the per-sample result gather the reference does by pickling futures
+ *                             (sensitivity/analysis.py:241-259), here one NCCL all-gather.
+ *
+ * Conventions
+ *   - return value: 0 = ok, <0 = API misuse or CUDA error (message via pk_last_error()).
+ *     A failing *system* never fails the call: its int32 status is 1 (max steps), 2 (step size
+ *     underflow) or 3 (non-finite), and its outputs are NaN (the reference only warns and returns
+ *     garbage: models/distmod.py:112; consumers treat non-finite as a bad sample).
+ *   - all arrays are C-order doubles unless noted; `memspace` says where *all* data pointers of a
+ *     job live (host: the library stages through its own device workspace; device: used in place).
+ *   - the library never frees caller memory; a handle owns one stream + workspaces; one handle
+ *     per GPU; not fork-safe.
+ */
+#ifndef PHOSKIN_B200_H
+#define PHOSKIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PK_ABI_VERSION 1
+
+typedef struct pk_handle_s* pk_handle_t;
+
+enum pk_model { PK_DISTMOD = 0, PK_SUCCMOD = 1, PK_RANDMOD = 2 };
+enum pk_memspace { PK_HOST = 0, PK_DEVICE = 1 };
+/* sensitivity/analysis.py:114-176 */
+enum pk_y_metric { PK_Y_NONE = -1, PK_Y_TOTAL_SIGNAL = 0, PK_Y_MEAN_ACTIVITY = 1, PK_Y_VARIANCE = 2,
+                   PK_Y_DYNAMICS = 3, PK_Y_L2_NORM = 4 };
+enum pk_status { PK_OK = 0, PK_MAX_STEPS = 1, PK_STEP_UNDERFLOW = 2, PK_NON_FINITE = 3 };
+
+/* One batched call of solve_ode(params[b], init_cond, num_psites, t) for b in [0,B). */
+typedef struct pk_local_job {
+    int32_t model;          /* pk_model                                                          */
+    int32_t n_sites;        /* num_psites                                                        */
+    int64_t B;              /* number of independent systems                                     */
+    int32_t T;              /* number of output times (t[0] is the initial time)                 */
+    int32_t memspace;       /* pk_memspace of every pointer below                                */
+    const double* params;   /* [B,P]  P = 4+2ns (dist/succ) or 4+ns+2^ns-1 (rand), reference order */
+    const double* y0;       /* [n] if y0_stride==0 else [B,n] with row stride y0_stride doubles  */
+    int64_t y0_stride;
+    const double* t;        /* [T] strictly increasing                                           */
+    double rtol, atol;      /* <=0 -> defaults 1e-8 / 1e-11                                      */
+    int32_t max_steps;      /* per system, <=0 -> 100000                                         */
+    int32_t normalize;      /* NORMALIZE_MODEL_OUTPUT (models/distmod.py:115-122)                */
+    int32_t log_params;     /* 1: params hold log-values, model uses exp(params) (normest.py:54) */
+    int32_t y_metric;       /* pk_y_metric, PK_Y_NONE to skip                                    */
+    /* outputs, each may be NULL */
+    double* out_sol;        /* [B,T,n]  clipped at 0                                             */
+    double* out_flat;       /* [B,L]    L = (T-5)+T+ns*T  (needs T>5)                            */
+    double* out_Y;          /* [B]      Morris scalar                                            */
+    double* out_ssr;        /* [B]      sum(((model-target)/sigma)^2) incl. lam/P*params^2 terms */
+    double* out_score;      /* [B]      score_fit(params, target, flat)                          */
+    int32_t* out_status;    /* [B]                                                               */
+    int32_t* out_nsteps;    /* [B]      accepted steps                                           */
+    int32_t* out_nrej;      /* [B]      rejected steps                                           */
+    /* fused loss inputs (needed iff out_ssr or out_score) */
+    const double* target;   /* [G,L]                                                             */
+    const double* sigma;    /* NULL (ones) or [G,sigma_len], sigma_len in {L, L+P}               */
+    const int32_t* group;   /* NULL (all group 0) or [B] values in [0,G)                         */
+    int32_t n_groups;       /* G >= 1                                                            */
+    int32_t sigma_len;
+    double lam;             /* regularisation lambda (normest.py:56, 421)                        */
+    double score_w[5];      /* alpha(rmse) beta(mae) gamma(var) delta(mse) mu(l2); config.toml:212-217 */
+} pk_local_job;
+
+int pk_abi_version(void);
+const char* pk_last_error(void);
+
+int pk_create(int device, pk_handle_t* out);
+int pk_destroy(pk_handle_t h);
+int pk_device_count(int* out);
+/* multiprocessor count / SM clock (kHz) / name of the handle's device */
+int pk_device_info(pk_handle_t h, int* sm_count, int* clock_khz, char* name, int name_len);
+
+/* sizes implied by (model, n_sites, T): number of states, parameters, flat length */
+int pk_local_dims(int model, int n_sites, int T, int* n_states, int* n_params, int* flat_len);
+
+void pk_local_job_init(pk_local_job* job);        /* zero + defaults (score_w = 1, y_metric none)   */
+int pk_local_solve_batch(pk_handle_t h, const pk_local_job* job);
+/* number of kernel launches the last pk_* call on this handle issued, and its device time (ms,
+ * CUDA events on the handle's stream around the kernels only, copies excluded) */
+int pk_last_launch_info(pk_handle_t h, int* n_launches, float* kernel_ms);
+
+/* Morris elementary effects on device data already gathered: X[N*(D+1),D], Y[N*(D+1)].
+ * scaled!=0 -> sigma-scaled EE (analysis.py:264 `scaled=True`). Outputs [D] each (may be NULL). */
+int pk_morris_ee(pk_handle_t h, int memspace, const double* X, const double* Y, int64_t N, int32_t D,
+                 int32_t num_levels, int32_t scaled, double* out_mu, double* out_mu_star,
+                 double* out_sigma, double* out_ee /* [N,D] or NULL */);
+
+/* pinned host buffers for fast staging */
+int pk_host_alloc(void** ptr, int64_t bytes);
+int pk_host_free(void* ptr);
+
+/* FP64 FMA peak of the handle's device, measured with a register-resident DFMA kernel (TFLOP/s). */
+int pk_measure_fp64_peak(pk_handle_t h, double* tflops, float* ms);
+
+/* NCCL all-gather of per-sample doubles (device pointers). `comm` is an ncclComm_t created by the
+ * caller (or NULL with world==1 -> plain copy). */
+int pk_nccl_unique_id(char* out128);
+int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank);
+int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,95 @@
+"""ctypes binding of libphoskin_b200.so (include/phoskin_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call is made
+without a CUDA device, it raises.  The library itself links cudart statically, so it *loads*
+on a CPU-only host (used by the `-m "not gpu"` symbol tests) but every compute call fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphoskin_b200.so")
+
+PK_HOST, PK_DEVICE = 0, 1
+MODEL_IDS = {"distmod": 0, "succmod": 1, "randmod": 2}
+Y_METRIC_IDS = {"total_signal": 0, "mean_activity": 1, "variance": 2, "dynamics": 3, "l2_norm": 4}
+STATUS_NAMES = {0: "ok", 1: "max_steps", 2: "step_underflow", 3: "non_finite"}
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class PkLocalJob(C.Structure):
+    """Mirror of `struct pk_local_job` (include/phoskin_b200.h) — pointers as void* so that
+    host (numpy) and device (torch) addresses go through the same fields."""
+    _fields_ = [
+        ("model", C.c_int32), ("n_sites", C.c_int32), ("B", C.c_int64), ("T", C.c_int32),
+        ("memspace", C.c_int32),
+        ("params", C.c_void_p), ("y0", C.c_void_p), ("y0_stride", C.c_int64), ("t", C.c_void_p),
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("max_steps", C.c_int32), ("normalize", C.c_int32), ("log_params", C.c_int32),
+        ("y_metric", C.c_int32),
+        ("out_sol", C.c_void_p), ("out_flat", C.c_void_p), ("out_Y", C.c_void_p),
+        ("out_ssr", C.c_void_p), ("out_score", C.c_void_p), ("out_status", C.c_void_p),
+        ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p),
+        ("target", C.c_void_p), ("sigma", C.c_void_p), ("group", C.c_void_p),
+        ("n_groups", C.c_int32), ("sigma_len", C.c_int32), ("lam", C.c_double),
+        ("score_w", C.c_double * 5),
+    ]
+
+
+# every symbol include/phoskin_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pk_abi_version": (C.c_int, []),
+    "pk_last_error": (C.c_char_p, []),
+    "pk_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "pk_destroy": (C.c_int, [C.c_void_p]),
+    "pk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pk_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "pk_local_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)]),
+    "pk_local_job_init": (None, [C.POINTER(PkLocalJob)]),
+    "pk_local_solve_batch": (C.c_int, [C.c_void_p, C.POINTER(PkLocalJob)]),
+    "pk_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
+    "pk_morris_ee": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pk_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
+    "pk_host_free": (C.c_int, [C.c_void_p]),
+    "pk_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+}
+
+_lib = None
+
+
+class PhoskinError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and declare every prototype. Raises if it is missing:
+    there is deliberately no pure-Python / CPU substitute on the product path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PhoskinError(
+            f"{LIB_PATH} not found — build it with `make` (or __graft_entry__.build()); "
+            "phoskintime_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pk_abi_version() != 1:
+        raise PhoskinError("libphoskin_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pk_last_error()
+        raise PhoskinError(msg.decode() if msg else f"pk call failed with {rc}")

@@ -1,0 +1,596 @@
+// C ABI of libphoskin_b200.so (see include/phoskin_b200.h).  Host side: handle, workspaces,
+// staging copies, kernel dispatch by (model, n_sites), Morris elementary-effects reduction,
+// FP64 peak probe and the NCCL all-gather (NCCL resolved with dlopen so that the library loads on
+// hosts without it and reuses the copy PyTorch already mapped).
+#include "../../include/phoskin_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "local_dense.cuh"
+#include "local_tps.cuh"
+#include "pk_common.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) {
+    g_err = m;
+    return -1;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// NCCL through dlopen
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
+
+}  // namespace
+
+struct pk_handle_s {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch;
+    unsigned long long* counter = nullptr;
+    int last_launches = 0;
+    float last_ms = 0.f;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+// ---------------------------------------------------------------------------------- kernels
+namespace pk {
+
+// FP64 FMA peak probe: 8 independent register chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+}
+
+// ---- Morris elementary effects (SALib.analyze.morris as called at sensitivity/analysis.py:264)
+// column statistics: block c < D reduces X[:,c]; block D reduces Y.  out[c] = population std.
+__global__ void __launch_bounds__(256) morris_std_kernel(const double* X, const double* Y, long long rows, int D,
+                                                         double* out_std) {
+    __shared__ double sh[256];
+    __shared__ double mean_s;
+    const int c = blockIdx.x;
+    const double* base = c < D ? X + c : Y;
+    const long long stride = c < D ? D : 1;
+    double s = 0.0;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x) s += base[r * stride];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) mean_s = sh[0] / (double)rows;
+    __syncthreads();
+    const double m = mean_s;
+    s = 0.0;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x) { double d = base[r * stride] - m; s = fma(d, d, s); }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out_std[c] = sqrt(sh[0] / (double)rows);
+}
+
+// one thread per (trajectory r, move k): ee[r, moved coordinate]
+__global__ void morris_ee_kernel(const double* X, const double* Y, long long N, int D, double inv_delta,
+                                 int scaled, const double* stds, double* ee) {
+    long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (id >= N * D) return;
+    long long r = id / D;
+    int k = (int)(id % D);
+    const double* x0 = X + (r * (D + 1) + k) * D;
+    const double* x1 = x0 + D;
+    int which = 0;
+    double best = -1.0, step = 0.0;
+    for (int c = 0; c < D; ++c) {
+        double d = x1[c] - x0[c];
+        if (fabs(d) > best) { best = fabs(d); which = c; step = d; }
+    }
+    double dY = Y[r * (D + 1) + k + 1] - Y[r * (D + 1) + k];
+    double v;
+    if (scaled) v = dY / step * (stds[which] / stds[D]);
+    else v = (step > 0.0 ? dY : -dY) * inv_delta;
+    ee[r * D + which] = v;
+}
+
+// block c: statistics of ee[:, c] over N trajectories
+__global__ void __launch_bounds__(256) morris_stats_kernel(const double* ee, long long N, int D, double* mu,
+                                                           double* mu_star, double* sigma) {
+    __shared__ double sh[256], sh2[256];
+    __shared__ double mean_s;
+    const int c = blockIdx.x;
+    double s = 0.0, sa = 0.0;
+    for (long long r = threadIdx.x; r < N; r += blockDim.x) { double v = ee[r * D + c]; s += v; sa += fabs(v); }
+    sh[threadIdx.x] = s;
+    sh2[threadIdx.x] = sa;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; sh2[threadIdx.x] += sh2[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        mean_s = sh[0] / (double)N;
+        if (mu) mu[c] = mean_s;
+        if (mu_star) mu_star[c] = sh2[0] / (double)N;
+    }
+    __syncthreads();
+    const double m = mean_s;
+    s = 0.0;
+    for (long long r = threadIdx.x; r < N; r += blockDim.x) { double d = ee[r * D + c] - m; s = fma(d, d, s); }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0 && sigma) sigma[c] = N > 1 ? sqrt(sh[0] / (double)(N - 1)) : 0.0;
+}
+
+}  // namespace pk
+
+// --------------------------------------------------------------------------------- dispatch
+namespace {
+
+// Register-resident kernel limits: the largest site counts that compile with ZERO local-memory
+// spill (nvcc -Xptxas -v: dist-6 246 regs, succ-5 238 regs); larger systems take the dense path.
+constexpr int TPS_MAX_NS_DIST = 6;
+constexpr int TPS_MAX_NS_SUCC = 5;
+constexpr int TPS_BLOCK = 128;
+
+template <class M>
+cudaError_t launch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
+    size_t smem = (size_t)(a.T + M::N * TPS_BLOCK) * sizeof(double);
+    auto kern = pk::local_tps_kernel<M>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPS_BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long need = (a.B + TPS_BLOCK - 1) / TPS_BLOCK;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, TPS_BLOCK, smem, h->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <template <int> class M, int MAXNS>
+cudaError_t dispatch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
+    switch (a.ns) {
+        case 1: return launch_tps<M<1>>(h, a);
+        case 2: return launch_tps<M<2>>(h, a);
+        case 3: return launch_tps<M<3>>(h, a);
+        case 4: return launch_tps<M<4>>(h, a);
+        case 5: return launch_tps<M<5>>(h, a);
+        case 6:
+            if constexpr (MAXNS >= 6) return launch_tps<M<6>>(h, a);
+            else return cudaErrorInvalidValue;
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int MODEL>
+cudaError_t launch_dense(pk_handle_s* h, const pk::LocalArgs& a) {
+    pk::DenseLayout lay;
+    lay.n = a.n;
+    lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
+    lay.P = a.P;
+    lay.nobs = 2 + a.ns;
+    size_t smem = (size_t)lay.total() * sizeof(double);
+    auto kern = pk::local_dense_kernel<MODEL>;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 32, smem, h->stream>>>(a, lay);
+    return cudaGetLastError();
+}
+
+int dims(int model, int ns, int T, int* n, int* P, int* L) {
+    if (ns < 1) return fail("n_sites must be >= 1");
+    if (model == PK_DISTMOD || model == PK_SUCCMOD) {
+        if (ns > 60) return fail("n_sites too large");
+        *n = 2 + ns;
+        *P = 4 + 2 * ns;
+    } else if (model == PK_RANDMOD) {
+        if (ns > 7) return fail("randmod supports n_sites <= 7 (2^ns states in shared memory)");
+        *n = 2 + (1 << ns) - 1;
+        *P = 4 + ns + (1 << ns) - 1;
+    } else {
+        return fail("unknown model id");
+    }
+    *L = (T > pk::RNA_OFFSET ? T - pk::RNA_OFFSET : 0) + T + ns * T;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int pk_abi_version(void) { return PK_ABI_VERSION; }
+const char* pk_last_error(void) { return g_err.c_str(); }
+
+int pk_device_count(int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return fail(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *out = n;
+    return 0;
+}
+
+int pk_create(int device, pk_handle_t* out) {
+    if (!out) return fail("pk_create: out is NULL");
+    *out = nullptr;
+    CK(cudaSetDevice(device));
+    pk_handle_s* h = new pk_handle_s();
+    h->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    h->clock_khz = khz;
+    snprintf(h->name, sizeof(h->name), "%.127s", prop.name);
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    CK(cudaMalloc(&h->counter, sizeof(unsigned long long)));
+    *out = h;
+    return 0;
+}
+
+int pk_destroy(pk_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch};
+    for (DevBuf* b : bufs) b->release();
+    if (h->counter) cudaFree(h->counter);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int pk_device_info(pk_handle_t h, int* sm_count, int* clock_khz, char* name, int name_len) {
+    if (!h) return fail("null handle");
+    if (sm_count) *sm_count = h->sm_count;
+    if (clock_khz) *clock_khz = h->clock_khz;
+    if (name && name_len > 0) snprintf(name, name_len, "%s", h->name);
+    return 0;
+}
+
+int pk_local_dims(int model, int n_sites, int T, int* n_states, int* n_params, int* flat_len) {
+    int n, P, L;
+    if (dims(model, n_sites, T, &n, &P, &L)) return -1;
+    if (n_states) *n_states = n;
+    if (n_params) *n_params = P;
+    if (flat_len) *flat_len = L;
+    return 0;
+}
+
+void pk_local_job_init(pk_local_job* job) {
+    memset(job, 0, sizeof(*job));
+    job->y_metric = PK_Y_NONE;
+    job->n_groups = 1;
+    for (int i = 0; i < 5; ++i) job->score_w[i] = 1.0;
+}
+
+int pk_last_launch_info(pk_handle_t h, int* n_launches, float* kernel_ms) {
+    if (!h) return fail("null handle");
+    if (n_launches) *n_launches = h->last_launches;
+    if (kernel_ms) *kernel_ms = h->last_ms;
+    return 0;
+}
+
+int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
+    if (!h || !j) return fail("null handle or job");
+    int n, P, L;
+    if (dims(j->model, j->n_sites, j->T, &n, &P, &L)) return -1;
+    if (j->B < 0) return fail("B < 0");
+    if (j->T < 1) return fail("T < 1");
+    if (!j->params || !j->y0 || !j->t) return fail("params, y0 and t are required");
+    const bool want_loss = j->out_ssr || j->out_score;
+    if (want_loss && !j->target) return fail("out_ssr/out_score need target");
+    if (want_loss && j->n_groups < 1) return fail("n_groups < 1");
+    if (want_loss && j->sigma && j->sigma_len != L && j->sigma_len != L + P)
+        return fail("sigma_len must be L or L+P");
+    if (j->out_Y && (j->y_metric < 0 || j->y_metric > 4)) return fail("out_Y needs a valid y_metric");
+    h->last_launches = 0;
+    h->last_ms = 0.f;
+    if (j->B == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const size_t B = (size_t)j->B;
+    const bool host = j->memspace == PK_HOST;
+    cudaStream_t st = h->stream;
+
+    pk::LocalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = j->B; a.T = j->T; a.ns = j->n_sites; a.n = n; a.P = P; a.L = L;
+    a.rtol = j->rtol > 0 ? j->rtol : 1e-8;
+    a.atol = j->atol > 0 ? j->atol : 1e-11;
+    a.max_steps = j->max_steps > 0 ? j->max_steps : 100000;
+    a.normalize = j->normalize; a.log_params = j->log_params;
+    a.y_metric = j->out_Y ? j->y_metric : -1;
+    a.sigma_len = j->sigma ? j->sigma_len : 0;
+    a.lam = j->lam;
+    a.w_alpha = j->score_w[0]; a.w_beta = j->score_w[1]; a.w_gamma = j->score_w[2];
+    a.w_delta = j->score_w[3]; a.w_mu = j->score_w[4];
+    a.y0_stride = j->y0_stride;
+    a.counter = h->counter;
+
+    const size_t y0_elems = j->y0_stride ? (B - 1) * (size_t)j->y0_stride + n : (size_t)n;
+    const size_t G = want_loss ? (size_t)j->n_groups : 0;
+    if (host) {
+#define STAGE_IN(buf, src, bytes, dstfield)                                                   \
+        do {                                                                                  \
+            CK(h->buf.ensure(bytes));                                                         \
+            CK(cudaMemcpyAsync(h->buf.p, src, bytes, cudaMemcpyHostToDevice, st));            \
+            dstfield = (decltype(dstfield))h->buf.p;                                          \
+        } while (0)
+        STAGE_IN(params, j->params, B * P * sizeof(double), a.params);
+        STAGE_IN(y0, j->y0, y0_elems * sizeof(double), a.y0);
+        STAGE_IN(t, j->t, (size_t)j->T * sizeof(double), a.t);
+        if (want_loss) {
+            STAGE_IN(target, j->target, G * L * sizeof(double), a.target);
+            if (j->sigma) STAGE_IN(sigma, j->sigma, G * (size_t)j->sigma_len * sizeof(double), a.sigma);
+            if (j->group) STAGE_IN(group, j->group, B * sizeof(int32_t), a.group);
+        }
+#undef STAGE_IN
+#define STAGE_OUT(buf, user, bytes, dstfield)                                                 \
+        do {                                                                                  \
+            if (user) { CK(h->buf.ensure(bytes)); dstfield = (decltype(dstfield))h->buf.p; }  \
+        } while (0)
+        STAGE_OUT(sol, j->out_sol, B * j->T * n * sizeof(double), a.out_sol);
+        STAGE_OUT(flat, j->out_flat, B * L * sizeof(double), a.out_flat);
+        STAGE_OUT(Y, j->out_Y, B * sizeof(double), a.out_Y);
+        STAGE_OUT(ssr, j->out_ssr, B * sizeof(double), a.out_ssr);
+        STAGE_OUT(score, j->out_score, B * sizeof(double), a.out_score);
+        STAGE_OUT(status, j->out_status, B * sizeof(int32_t), a.out_status);
+        STAGE_OUT(nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
+        STAGE_OUT(nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
+#undef STAGE_OUT
+    } else {
+        a.params = j->params; a.y0 = j->y0; a.t = j->t;
+        a.target = j->target; a.sigma = j->sigma; a.group = j->group;
+        a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
+        a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
+        a.out_nrej = j->out_nrej;
+    }
+
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+    CK(cudaEventRecord(h->ev0, st));
+    cudaError_t e;
+    const bool tps = (j->model == PK_DISTMOD && j->n_sites <= TPS_MAX_NS_DIST) ||
+                     (j->model == PK_SUCCMOD && j->n_sites <= TPS_MAX_NS_SUCC);
+    if (tps) e = (j->model == PK_DISTMOD) ? dispatch_tps<pk::DistModel, TPS_MAX_NS_DIST>(h, a)
+                                            : dispatch_tps<pk::SuccModel, TPS_MAX_NS_SUCC>(h, a);
+    else if (j->model == PK_DISTMOD) e = launch_dense<0>(h, a);
+    else if (j->model == PK_SUCCMOD) e = launch_dense<1>(h, a);
+    else e = launch_dense<2>(h, a);
+    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+    CK(cudaEventRecord(h->ev1, st));
+    h->last_launches = 1;
+
+    if (host) {
+#define COPY_OUT(buf, user, bytes)                                                            \
+        do {                                                                                  \
+            if (user) CK(cudaMemcpyAsync(user, h->buf.p, bytes, cudaMemcpyDeviceToHost, st)); \
+        } while (0)
+        COPY_OUT(sol, j->out_sol, B * j->T * n * sizeof(double));
+        COPY_OUT(flat, j->out_flat, B * L * sizeof(double));
+        COPY_OUT(Y, j->out_Y, B * sizeof(double));
+        COPY_OUT(ssr, j->out_ssr, B * sizeof(double));
+        COPY_OUT(score, j->out_score, B * sizeof(double));
+        COPY_OUT(status, j->out_status, B * sizeof(int32_t));
+        COPY_OUT(nsteps, j->out_nsteps, B * sizeof(int32_t));
+        COPY_OUT(nrej, j->out_nrej, B * sizeof(int32_t));
+#undef COPY_OUT
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int pk_morris_ee(pk_handle_t h, int memspace, const double* X, const double* Y, int64_t N, int32_t D,
+                 int32_t num_levels, int32_t scaled, double* out_mu, double* out_mu_star, double* out_sigma,
+                 double* out_ee) {
+    if (!h || !X || !Y) return fail("null argument");
+    if (N < 1 || D < 1 || num_levels < 2) return fail("bad N, D or num_levels");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t rows = (size_t)N * (D + 1);
+    const bool host = memspace == PK_HOST;
+    // scratch layout: [X | Y] (host mode) | ee[N*D] | stds[D+1] | mu[D] | mu*[D] | sigma[D]
+    size_t off_x = 0, off_y = host ? rows * D : 0, off_ee = host ? rows * (D + 1) : 0;
+    size_t off_std = off_ee + (size_t)N * D, off_mu = off_std + D + 1;
+    size_t total = off_mu + 3 * (size_t)D;
+    CK(h->scratch.ensure(total * sizeof(double)));
+    double* base = (double*)h->scratch.p;
+    const double* dX = X;
+    const double* dY = Y;
+    if (host) {
+        CK(cudaMemcpyAsync(base + off_x, X, rows * D * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(base + off_y, Y, rows * sizeof(double), cudaMemcpyHostToDevice, st));
+        dX = base + off_x;
+        dY = base + off_y;
+    }
+    double* ee = base + off_ee;
+    double* stds = base + off_std;
+    double* mu = base + off_mu;
+    double* mus = mu + D;
+    double* sig = mus + D;
+    CK(cudaMemsetAsync(ee, 0, (size_t)N * D * sizeof(double), st));
+    CK(cudaEventRecord(h->ev0, st));
+    h->last_launches = 0;
+    if (scaled) {
+        pk::morris_std_kernel<<<D + 1, 256, 0, st>>>(dX, dY, (long long)rows, D, stds);
+        h->last_launches++;
+    }
+    const double inv_delta = 2.0 * (num_levels - 1) / (double)num_levels;
+    long long nthreads = (long long)N * D;
+    pk::morris_ee_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(dX, dY, N, D, inv_delta, scaled, stds, ee);
+    pk::morris_stats_kernel<<<D, 256, 0, st>>>(ee, N, D, mu, mus, sig);
+    h->last_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (out_mu) CK(cudaMemcpyAsync(out_mu, mu, D * sizeof(double), kind, st));
+    if (out_mu_star) CK(cudaMemcpyAsync(out_mu_star, mus, D * sizeof(double), kind, st));
+    if (out_sigma) CK(cudaMemcpyAsync(out_sigma, sig, D * sizeof(double), kind, st));
+    if (out_ee) CK(cudaMemcpyAsync(out_ee, ee, (size_t)N * D * sizeof(double), kind, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int pk_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail("bad argument");
+    CK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+int pk_host_free(void* ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return 0;
+}
+
+int pk_measure_fp64_peak(pk_handle_t h, double* tflops, float* ms_out) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(h->scratch.ensure(64));
+    const int iters = 4096, block = 256;
+    const int grid = h->sm_count * 8;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(h->ev0, h->stream));
+        pk::dfma_peak_kernel<<<grid, block, 0, h->stream>>>((double*)h->scratch.p, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    double flops = 2.0 * 64.0 * (double)iters * (double)grid * block;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}
+
+int pk_nccl_unique_id(char* out128) {
+    if (!g_nccl.load()) return fail("libnccl.so.2 not found");
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank) {
+    if (!h) return fail("null handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad world/rank");
+    h->world = world;
+    h->rank = rank;
+    if (world == 1) return 0;
+    if (!g_nccl.load()) return fail("libnccl.so.2 not found");
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    int r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != 0) return fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    return 0;
+}
+
+int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev) {
+    if (!h || !send_dev || !recv_dev || count < 0) return fail("bad argument");
+    CK(cudaSetDevice(h->device));
+    if (h->world == 1) {
+        if (send_dev != recv_dev)
+            CK(cudaMemcpyAsync(recv_dev, send_dev, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (!h->comm) return fail("pk_nccl_init was not called");
+    int r = g_nccl.AllGather(send_dev, recv_dev, (size_t)count, NCCL_FLOAT64, h->comm, h->stream);
+    if (r != 0) return fail(std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+"""Host-side engine: one handle per GPU, batched solves through the C ABI.
+
+`Engine.solve_local_batch` is the batched form of the reference's
+`solve_ode(params, init_cond, num_psites, t)` (models/distmod.py:93-134 and siblings): B
+parameter sets in, any of {sol, flat, Y, ssr, score} out.  Inputs may be numpy arrays (host
+path: the library stages them to HBM) or torch CUDA tensors (device path: used in place,
+outputs come back as torch tensors on the same device).  PyTorch is only the owner of device
+buffers here; all arithmetic happens in libphoskin_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError, PkLocalJob
+
+DEFAULT_RTOL = 1e-8
+DEFAULT_ATOL = 1e-11
+
+_engines = {}
+
+
+def local_dims(model, num_psites, T):
+    """(n_states, n_params, flat_len) for a model — pure arithmetic, no device needed."""
+    lib = _lib.load()
+    n, P, L = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.pk_local_dims(MODEL_IDS[model], int(num_psites), int(T), C.byref(n), C.byref(P), C.byref(L)))
+    return n.value, P.value, L.value
+
+
+def _is_torch(x):
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class Engine:
+    """Owns one pk_handle (stream + device workspaces) on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        _lib.check(self.lib.pk_create(self.device, C.byref(h)))
+        self._h = h
+        sm, khz = C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        _lib.check(self.lib.pk_device_info(self._h, C.byref(sm), C.byref(khz), name, 128))
+        self.sm_count, self.clock_khz, self.device_name = sm.value, khz.value, name.value.decode()
+        self.world, self.rank = 1, 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------ info
+    def last_launch_info(self):
+        n, ms = C.c_int(), C.c_float()
+        _lib.check(self.lib.pk_last_launch_info(self._h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def measure_fp64_peak(self):
+        tf, ms = C.c_double(), C.c_float()
+        _lib.check(self.lib.pk_measure_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
+        return tf.value
+
+    # ----------------------------------------------------------------------------- solve
+    def solve_local_batch(self, model, params, init_cond, num_psites, t, want=("sol", "flat"), *,
+                          target=None, sigma=None, group=None, lam=0.0, y_metric="total_signal",
+                          rtol=None, atol=None, max_steps=0, normalize=False, log_params=False,
+                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None):
+        """Solve B systems.  Returns a dict with the requested keys among
+        sol[B,T,n], flat[B,L], Y[B], ssr[B], score[B] plus status/nsteps/nrej[B] (int32).
+
+        params : [B,P] (numpy or torch.cuda float64, C-contiguous)
+        init_cond : [n] shared, or [B,n] per system
+        target/sigma/group : fused-loss inputs — target [L] or [G,L]; sigma None, [L]/[L+P] or
+            [G,·]; group [B] int32 indices into G (None = all 0)
+        out : optional dict of preallocated outputs (same kind as params) to fill
+        """
+        want = tuple(want)
+        unknown = set(want) - {"sol", "flat", "Y", "ssr", "score"}
+        if unknown:
+            raise ValueError(f"unknown outputs {sorted(unknown)}")
+        dev = _is_torch(params)
+        xp = _TorchOps(params.device) if dev else _NumpyOps()
+        params = xp.f64(params)
+        if params.ndim == 1:
+            params = params.reshape(1, -1)
+        B = int(params.shape[0])
+        t_arr = xp.f64(t).reshape(-1)
+        T = int(t_arr.shape[0])
+        n, P, L = local_dims(model, num_psites, T)
+        if params.shape[1] != P:
+            raise ValueError(f"{model} with {num_psites} sites takes {P} parameters, got {params.shape[1]}")
+        y0 = xp.f64(init_cond)
+        if y0.ndim == 1:
+            if y0.shape[0] != n:
+                raise ValueError(f"init_cond must have {n} entries, got {y0.shape[0]}")
+            y0_stride = 0
+        else:
+            if tuple(y0.shape) != (B, n):
+                raise ValueError(f"init_cond must be [{n}] or [{B},{n}]")
+            y0_stride = n
+
+        job = PkLocalJob()
+        self.lib.pk_local_job_init(C.byref(job))
+        job.model, job.n_sites, job.B, job.T = MODEL_IDS[model], int(num_psites), B, T
+        job.memspace = PK_DEVICE if dev else PK_HOST
+        job.params, job.y0, job.y0_stride, job.t = xp.ptr(params), xp.ptr(y0), y0_stride, xp.ptr(t_arr)
+        job.rtol = DEFAULT_RTOL if rtol is None else float(rtol)
+        job.atol = DEFAULT_ATOL if atol is None else float(atol)
+        job.max_steps, job.normalize, job.log_params = int(max_steps), int(bool(normalize)), int(bool(log_params))
+        job.lam = float(lam)
+        for i, w in enumerate(score_weights):
+            job.score_w[i] = float(w)
+
+        keep = [params, y0, t_arr]
+        res = {}
+        out = out or {}
+
+        def alloc(key, shape, dtype="f64"):
+            buf = out.get(key)
+            if buf is None:
+                buf = xp.empty(shape, dtype)
+            res[key] = buf
+            return xp.ptr(buf)
+
+        if "sol" in want:
+            job.out_sol = alloc("sol", (B, T, n))
+        if "flat" in want:
+            job.out_flat = alloc("flat", (B, L))
+        if "Y" in want:
+            job.y_metric = Y_METRIC_IDS[y_metric]
+            job.out_Y = alloc("Y", (B,))
+        if "ssr" in want or "score" in want:
+            if target is None:
+                raise ValueError("ssr/score need target")
+            tg = xp.f64(target)
+            tg = tg.reshape(1, -1) if tg.ndim == 1 else tg
+            if tg.shape[1] != L:
+                raise ValueError(f"target must have {L} columns")
+            G = int(tg.shape[0])
+            job.target, job.n_groups = xp.ptr(tg), G
+            keep.append(tg)
+            if sigma is not None:
+                sg = xp.f64(sigma)
+                sg = sg.reshape(1, -1) if sg.ndim == 1 else sg
+                if sg.shape[0] != G or sg.shape[1] not in (L, L + P):
+                    raise ValueError(f"sigma must be [{G},{L}] or [{G},{L + P}]")
+                job.sigma, job.sigma_len = xp.ptr(sg), int(sg.shape[1])
+                keep.append(sg)
+            if group is not None:
+                gr = xp.i32(group).reshape(-1)
+                if gr.shape[0] != B:
+                    raise ValueError("group must have B entries")
+                job.group = xp.ptr(gr)
+                keep.append(gr)
+            elif G != 1:
+                raise ValueError("several target rows need `group`")
+            if "ssr" in want:
+                job.out_ssr = alloc("ssr", (B,))
+            if "score" in want:
+                job.out_score = alloc("score", (B,))
+        job.out_status = alloc("status", (B,), "i32")
+        job.out_nsteps = alloc("nsteps", (B,), "i32")
+        job.out_nrej = alloc("nrej", (B,), "i32")
+
+        if dev:
+            xp.sync()          # inputs produced on torch's stream must be visible to ours
+        _lib.check(self.lib.pk_local_solve_batch(self._h, C.byref(job)))
+        del keep
+        return res
+
+    # ---------------------------------------------------------------------------- morris
+    def morris_ee(self, X, Y, num_levels, scaled=False, want_ee=False):
+        """mu, mu*, sigma (and optionally the EE matrix) from trajectories X[N(D+1),D], Y[N(D+1)]
+        — SALib.analyze.morris as called at sensitivity/analysis.py:264-265 (without the
+        bootstrap confidence column)."""
+        dev = _is_torch(X)
+        xp = _TorchOps(X.device) if dev else _NumpyOps()
+        X = xp.f64(X)
+        Y = xp.f64(Y).reshape(-1)
+        D = int(X.shape[1])
+        rows = int(X.shape[0])
+        if rows % (D + 1) or Y.shape[0] != rows:
+            raise ValueError("X must hold N*(D+1) rows and Y one value per row")
+        N = rows // (D + 1)
+        mu, mus, sig = xp.empty((D,), "f64"), xp.empty((D,), "f64"), xp.empty((D,), "f64")
+        ee = xp.empty((N, D), "f64") if want_ee else None
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_morris_ee(self._h, PK_DEVICE if dev else PK_HOST, xp.ptr(X), xp.ptr(Y), N, D,
+                                         int(num_levels), int(bool(scaled)), xp.ptr(mu), xp.ptr(mus),
+                                         xp.ptr(sig), xp.ptr(ee) if want_ee else None))
+        res = {"mu": mu, "mu_star": mus, "sigma": sig}
+        if want_ee:
+            res["ee"] = ee
+        return res
+
+    # ------------------------------------------------------------------------- multi-GPU
+    def init_nccl(self, world, rank, id_bytes):
+        _lib.check(self.lib.pk_nccl_init(self._h, id_bytes, int(world), int(rank)))
+        self.world, self.rank = int(world), int(rank)
+
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        _lib.check(self.lib.pk_nccl_unique_id(buf))
+        return buf.raw
+
+    def allgather_f64(self, send, recv):
+        """NCCL all-gather of torch CUDA float64 tensors (recv.numel() == world * send.numel())."""
+        import torch
+        torch.cuda.current_stream(send.device).synchronize()
+        _lib.check(self.lib.pk_allgather_f64(self._h, send.data_ptr(), send.numel(), recv.data_ptr()))
+        return recv
+
+
+class _NumpyOps:
+    def f64(self, x):
+        return np.ascontiguousarray(x, dtype=np.float64)
+
+    def i32(self, x):
+        return np.ascontiguousarray(x, dtype=np.int32)
+
+    def empty(self, shape, dtype):
+        return np.empty(shape, dtype=np.float64 if dtype == "f64" else np.int32)
+
+    def ptr(self, a):
+        return None if a is None else a.ctypes.data
+
+
+class _TorchOps:
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.device = device
+        if device.type != "cuda":
+            raise PhoskinError("torch inputs must live on a CUDA device (no CPU path)")
+
+    def f64(self, x):
+        t = self.torch.as_tensor(x, dtype=self.torch.float64, device=self.device)
+        return t.contiguous()
+
+    def i32(self, x):
+        return self.torch.as_tensor(x, dtype=self.torch.int32, device=self.device).contiguous()
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=self.torch.float64 if dtype == "f64" else self.torch.int32,
+                                device=self.device)
+
+    def ptr(self, a):
+        return None if a is None else a.data_ptr()
+
+    def sync(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+
+def get_engine(device=None):
+    """Process-wide engine per device (created lazily; raises without a GPU)."""
+    if device is None:
+        import os
+        device = int(os.environ.get("LOCAL_RANK", "0")) if "PHOSKIN_DEVICE" not in os.environ \
+            else int(os.environ["PHOSKIN_DEVICE"])
+    device = int(device)
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]
