@@ -14,8 +14,8 @@ namespace pk {
 struct DenseLayout {       // per-warp shared-memory carve-up, in doubles
     int n, ld, P, nobs;
     __host__ __device__ int W() const { return 0; }
-    __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..8: y,U1..U5,w,E,inv0
-    __host__ __device__ int par() const { return n * ld + 9 * n; }
+    __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..3: y, v, y_new, err
+    __host__ __device__ int par() const { return n * ld + 4 * n; }
     __host__ __device__ int prev() const { return par() + P; }
     __host__ __device__ int total() const { return prev() + nobs; }
 };
@@ -83,52 +83,52 @@ __device__ __forceinline__ void dense_rhs(int ns, int n, const double* p, const 
     }
 }
 
-// W = g*I - J (row-major, leading dimension ld).  Each lane assembles whole rows.
+// W = I - c*J (row-major, leading dimension ld), c = h*gamma.  Each lane assembles whole rows.
 template <int MODEL>
-__device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double* p, double g, double* W, int lane) {
+__device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double* p, double c, double* W, int lane) {
     for (int idx = lane; idx < n * ld; idx += 32) W[idx] = 0.0;
     __syncwarp();
     const double* S = p + 4;
     for (int r = lane; r < n; r += 32) {
         double* row = W + r * ld;
-        if (r == 0) { row[0] = g + p[1]; continue; }
+        if (r == 0) { row[0] = fma(c, p[1], 1.0); continue; }
         if (MODEL == 2) {
             const double* Dd = p + 4 + ns;
             if (r == 1) {
                 double sS = 0.0;
-                for (int k = 0; k < ns; ++k) { sS += S[k]; row[1 + (1 << k)] = -1.0; }
-                row[0] = -p[2];
-                row[1] = g + p[3] + sS;
+                for (int k = 0; k < ns; ++k) { sS += S[k]; row[1 + (1 << k)] = -c; }
+                row[0] = -c * p[2];
+                row[1] = fma(c, p[3] + sS, 1.0);
             } else {
                 const int s = r - 1;
                 const double rate_in = S[__ffs(s) - 1];
                 double out = Dd[s - 1];
                 for (int j = 0; j < ns; ++j) {
                     const int bit = 1 << j;
-                    if (s & bit) { row[1 + (s & ~bit)] = -rate_in; out += 1.0; }
-                    else { const int up = s | bit; row[1 + up] = -1.0; out += S[__ffs(up) - 1]; }
+                    if (s & bit) { row[1 + (s & ~bit)] = -c * rate_in; out += 1.0; }
+                    else { const int up = s | bit; row[1 + up] = -c; out += S[__ffs(up) - 1]; }
                 }
-                row[r] = g + out;
+                row[r] = fma(c, out, 1.0);
             }
         } else {
             const double* Dr = p + 4 + ns;
             if (MODEL == 0) {
                 if (r == 1) {
                     double sS = 0.0;
-                    for (int k = 0; k < ns; ++k) { sS += S[k]; row[2 + k] = -1.0; }
-                    row[0] = -p[2];
-                    row[1] = g + p[3] + sS;
+                    for (int k = 0; k < ns; ++k) { sS += S[k]; row[2 + k] = -c; }
+                    row[0] = -c * p[2];
+                    row[1] = fma(c, p[3] + sS, 1.0);
                 } else {
-                    row[1] = -S[r - 2];
-                    row[r] = g + 1.0 + Dr[r - 2];
+                    row[1] = -c * S[r - 2];
+                    row[r] = fma(c, 1.0 + Dr[r - 2], 1.0);
                 }
             } else {
-                if (r == 1) { row[0] = -p[2]; row[1] = g + p[3] + S[0]; row[2] = -1.0; }
+                if (r == 1) { row[0] = -c * p[2]; row[1] = fma(c, p[3] + S[0], 1.0); row[2] = -c; }
                 else {
                     const int i = r - 2;
-                    row[r - 1] = -S[i];
-                    row[r] = g + 1.0 + Dr[i] + (i < ns - 1 ? S[i + 1] : 0.0);
-                    if (i < ns - 1) row[r + 1] = -1.0;
+                    row[r - 1] = -c * S[i];
+                    row[r] = fma(c, 1.0 + Dr[i] + (i < ns - 1 ? S[i + 1] : 0.0), 1.0);
+                    if (i < ns - 1) row[r + 1] = -c;
                 }
             }
         }
@@ -191,19 +191,13 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
     double* W = smem + lay.W();
     double* y = smem + lay.vec(0);
-    double* U1 = smem + lay.vec(1);
-    double* U2 = smem + lay.vec(2);
-    double* U3 = smem + lay.vec(3);
-    double* U4 = smem + lay.vec(4);
-    double* U5 = smem + lay.vec(5);
-    double* w = smem + lay.vec(6);
-    double* E = smem + lay.vec(7);
-    double* inv0 = smem + lay.vec(8);
+    double* v = smem + lay.vec(1);
+    double* w = smem + lay.vec(2);
+    double* E = smem + lay.vec(3);
     double* p = smem + lay.par();
     double* prev = smem + lay.prev();
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
-    const double invL = 1.0 / (double)a.L;
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
 
     for (;;) {
@@ -222,7 +216,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             p2l = fma(v, v, p2l);
         }
         const double* y0 = a.y0 + (a.y0_stride ? sys * (size_t)a.y0_stride : 0);
-        for (int i = lane; i < n; i += 32) { y[i] = y0[i]; inv0[i] = a.normalize ? 1.0 / y0[i] : 1.0; }
+        for (int i = lane; i < n; i += 32) y[i] = y0[i];
         __syncwarp();
         const int grp = a.group ? a.group[sys] : 0;
         const double* tg = a.target ? a.target + (size_t)grp * a.L : nullptr;
@@ -235,7 +229,8 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
         auto emit = [&](int k, const double* src) {
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
             for (int i = lane; i < n; i += 32) {
-                double v = src ? fmax(src[i], 0.0) * inv0[i] : qnan;
+                double v = src ? fmax(src[i], 0.0) : qnan;
+                if (a.normalize) v *= 1.0 / y0[i];
                 if (a.out_sol) a.out_sol[(sys * T + k) * n + i] = v;
                 if (i < nobs) {
                     int fi = (i == 0) ? (k >= RNA_OFFSET ? k - RNA_OFFSET : -1)
@@ -246,9 +241,8 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
                             double dlt = v - __ldg(tg + fi);
                             double ww = sg ? dlt / __ldg(sg + fi) : dlt;
                             e.ssr = fma(ww, ww, e.ssr);
-                            double r = fabs(dlt) * invL;
-                            e.sr += r;
-                            e.sr2 = fma(r, r, e.sr2);
+                            e.sr += fabs(dlt);
+                            e.sr2 = fma(dlt, dlt, e.sr2);
                         }
                     }
                     if (want_y) {
@@ -264,18 +258,18 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
         };
 
         // initial step from the error-weighted time scale |y|/|f|
-        dense_rhs<MODEL>(ns, n, p, y, U1, lane);
+        dense_rhs<MODEL>(ns, n, p, y, v, lane);
         __syncwarp();
         double d0 = 0.0, d1 = 0.0;
         for (int i = lane; i < n; i += 32) {
             double sc = 1.0 / fma(a.rtol, fabs(y[i]), a.atol);
             d0 = fmax(d0, fabs(y[i]) * sc);
-            d1 = fmax(d1, fabs(U1[i]) * sc);
+            d1 = fmax(d1, fabs(v[i]) * sc);
         }
         d0 = warp_max(d0);
         d1 = warp_max(d1);
         const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        StepCtl ctl{h0, h0, 1.0, 0, 0};
+        StepCtl ctl{h0, (float)h0, 1.0f, 0, 0};
         emit(0, y);
 
         // ---------------------------------------------------------------------- time loop
@@ -287,68 +281,41 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             bool land = false;
             if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
             else if (hh > 0.5 * rem) hh = 0.5 * rem;
-            const double ih = 1.0 / hh;
-            const double g = ih * (1.0 / GAMMA);
-
-            dense_fillW<MODEL>(ns, n, ld, p, g, W, lane);
+            dense_fillW<MODEL>(ns, n, ld, p, hh * GAMMA, W, lane);
             dense_lu(n, ld, W, lane);
 
-            dense_rhs<MODEL>(ns, n, p, y, U1, lane);
+            // v_0 = h f(y); v_k = A^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
+            dense_rhs<MODEL>(ns, n, p, y, v, lane);
+            for (int i = lane; i < n; i += 32) v[i] *= hh;
             __syncwarp();
-            dense_solve(n, ld, W, U1, lane);
-            for (int i = lane; i < n; i += 32) w[i] = fma(A21, U1[i], y[i]);
-            __syncwarp();
-            dense_rhs<MODEL>(ns, n, p, w, U2, lane);
-            for (int i = lane; i < n; i += 32) U2[i] = fma(C21 * ih, U1[i], U2[i]);
-            __syncwarp();
-            dense_solve(n, ld, W, U2, lane);
-            for (int i = lane; i < n; i += 32) w[i] = fma(A32, U2[i], fma(A31, U1[i], y[i]));
-            __syncwarp();
-            dense_rhs<MODEL>(ns, n, p, w, U3, lane);
-            for (int i = lane; i < n; i += 32) U3[i] = fma(C32 * ih, U2[i], fma(C31 * ih, U1[i], U3[i]));
-            __syncwarp();
-            dense_solve(n, ld, W, U3, lane);
-            for (int i = lane; i < n; i += 32) w[i] = fma(A43, U3[i], fma(A42, U2[i], fma(A41, U1[i], y[i])));
-            __syncwarp();
-            dense_rhs<MODEL>(ns, n, p, w, U4, lane);
-            for (int i = lane; i < n; i += 32)
-                U4[i] = fma(C43 * ih, U3[i], fma(C42 * ih, U2[i], fma(C41 * ih, U1[i], U4[i])));
-            __syncwarp();
-            dense_solve(n, ld, W, U4, lane);
-            for (int i = lane; i < n; i += 32)
-                w[i] = fma(A54, U4[i], fma(A53, U3[i], fma(A52, U2[i], fma(A51, U1[i], y[i]))));
-            __syncwarp();
-            dense_rhs<MODEL>(ns, n, p, w, U5, lane);
-            for (int i = lane; i < n; i += 32)
-                U5[i] = fma(C54 * ih, U4[i],
-                            fma(C53 * ih, U3[i], fma(C52 * ih, U2[i], fma(C51 * ih, U1[i], U5[i]))));
-            __syncwarp();
-            dense_solve(n, ld, W, U5, lane);
-            for (int i = lane; i < n; i += 32) w[i] += U5[i];
-            __syncwarp();
-            dense_rhs<MODEL>(ns, n, p, w, E, lane);
-            for (int i = lane; i < n; i += 32)
-                E[i] = fma(C65 * ih, U5[i],
-                           fma(C64 * ih, U4[i],
-                               fma(C63 * ih, U3[i], fma(C62 * ih, U2[i], fma(C61 * ih, U1[i], E[i])))));
-            __syncwarp();
-            dense_solve(n, ld, W, E, lane);
-            double err = 0.0;
+            dense_solve(n, ld, W, v, lane);
+            for (int i = lane; i < n; i += 32) w[i] = fma(MU1, v[i], y[i]);
+            dense_solve(n, ld, W, v, lane);
+            for (int i = lane; i < n; i += 32) { w[i] = fma(MU2, v[i], w[i]); E[i] = EPS2 * v[i]; }
+            dense_solve(n, ld, W, v, lane);
+            for (int i = lane; i < n; i += 32) { w[i] = fma(MU3, v[i], w[i]); E[i] = fma(EPS3, v[i], E[i]); }
+            dense_solve(n, ld, W, v, lane);
+            for (int i = lane; i < n; i += 32) { w[i] = fma(MU4, v[i], w[i]); E[i] = fma(EPS4, v[i], E[i]); }
+            dense_solve(n, ld, W, v, lane);
+            for (int i = lane; i < n; i += 32) { w[i] = fma(MU5, v[i], w[i]); E[i] = fma(EPS5, v[i], E[i]); }
+            dense_solve(n, ld, W, v, lane);
+            float err = 0.0f;
             bool bad = false;
             for (int i = lane; i < n; i += 32) {
-                double yn = w[i] + E[i];
+                const double yn = fma(MU6, v[i], w[i]);
+                const double ei = fma(EPS6, v[i], E[i]);
                 w[i] = yn;
-                double sc = fma(a.rtol, fmax(fabs(y[i]), fabs(yn)), a.atol);
-                double q = fabs(E[i]) / sc;
-                bad |= !(q < 1.0e300);
-                err = fmax(err, q);
+                const float q = err_ratio(ei, y[i], yn, a.rtol, a.atol);
+                bad |= !(q < 3.0e38f) || !(fabs(yn) < 1.0e300);
+                err = fmaxf(err, q);
             }
-            err = warp_max(err);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
             bad = __any_sync(0xffffffffu, bad);
             __syncwarp();
 
             if (bad) { status = 3; break; }
-            if (err <= 1.0) {
+            if (err <= 1.0f) {
                 ++nst;
                 const double hprop = ctl.h;
                 const double hnew = ctl_accept(ctl, hh, err);
@@ -387,9 +354,10 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             if (lane == 0) {
                 if (a.out_ssr) a.out_ssr[sys] = ssr;
                 if (a.out_score) {
-                    const double Ld = (double)a.L;
-                    const double mean_r2 = sr2 / Ld, mae = sr / Ld;
-                    a.out_score[sys] = a.w_delta * sr2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                    const double invL = 1.0 / (double)a.L;
+                    const double r1 = sr * invL, r2 = sr2 * invL * invL;      // sum r, sum r^2, r = |d|/L
+                    const double mean_r2 = r2 * invL, mae = r1 * invL;
+                    a.out_score[sys] = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
                                        a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
                 }
             }

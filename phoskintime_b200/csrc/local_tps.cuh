@@ -1,23 +1,44 @@
 // Thread-per-system RODAS4 kernel for the small local models (distributive, successive).
 //
-// One lane integrates one system with its whole state (y, five stage vectors, the factorised
-// W = I/(h*gamma) - J) in registers; the Jacobian structure is exploited analytically:
-//   distributive (models/distmod.py:57-63): arrow matrix  -> O(n) elimination via the P pivot
-//   successive   (models/succmod.py:33-90): tridiagonal in (P, site_1..site_ns) -> Thomas
-// mRNA (row 0) is decoupled in both and eliminated first.
-// Lanes pull systems from a global queue (warp-aggregated atomicAdd) as they finish, so a warp
-// never idles on its slowest member: per-system adaptivity costs no SIMT efficiency except in
-// the tail.  The epilogue (clip, flat layout, weighted residual / score_fit, Morris Y) is fused:
-// it runs at the step that lands on each requested output time.
+// One lane integrates one system with its whole working set (y, the Krylov vector v, y_new, err
+// and the factorised I - h*gamma*M) in registers; the Jacobian structure is exploited analytically:
+//   distributive (models/distmod.py:57-63): arrow matrix  -> Schur pivot on the protein row
+//   successive   (models/succmod.py:33-90): tridiagonal in (P, site_1..site_ns) -> Thomas, with the
+//                pivots obtained from the continuant recurrence so that they are independent
+// mRNA (row 0) is decoupled in both and eliminated first.  All reciprocals of one factorisation come
+// from ONE FP64 division (batch inversion by prefix products); the error ratio and the step-size
+// controller run in FP32.  Rarely touched per-system state (loss / Y accumulators) lives in shared
+// memory.  Lanes pull systems from a global queue (warp-aggregated atomicAdd) as they finish, so a
+// warp never idles on its slowest member.  The epilogue (clip, flat layout, weighted residual /
+// score_fit, Morris Y) is fused: it runs at the step that lands on each requested output time.
 #pragma once
 #include "pk_common.cuh"
 
 namespace pk {
 
+// a[i] <- 1/a[i] for i < M with one division (Montgomery's trick).
+template <int M>
+__device__ __forceinline__ void batch_invert(double (&a)[M]) {
+    double pre[M];
+    pre[0] = a[0];
+#pragma unroll
+    for (int i = 1; i < M; ++i) pre[i] = pre[i - 1] * a[i];
+    double inv = 1.0 / pre[M - 1];
+#pragma unroll
+    for (int i = M - 1; i > 0; --i) {
+        double ai = a[i];
+        a[i] = inv * pre[i - 1];
+        inv *= ai;
+    }
+    a[0] = inv;
+}
+
 // ------------------------------------------------------------------------------------ models
+// Each model provides rhs(y) = M y + b, factor(c) of A = I - c M (c = h*gamma) and an in-place
+// solve A x = r.
 template <int NS_>
 struct DistModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = NS_ + 2;
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4;
     double A, Bm, C, kP, S[NS], k[NS];
     __device__ __forceinline__ void load(const double* p) {
         A = p[0]; Bm = p[1]; C = p[2];
@@ -33,28 +54,49 @@ struct DistModel {
         for (int i = 0; i < NS; ++i) { acc += y[2 + i]; f[2 + i] = fma(S[i], y[1], -k[i] * y[2 + i]); }
         f[1] = acc;
     }
-    // F[0] = 1/(g+B); F[1] = 1/schur pivot of P; F[2+i] = 1/(g+k_i)
-    __device__ __forceinline__ void factor(double g, double (&F)[NF]) const {
-        F[0] = 1.0 / (g + Bm);
-        double piv = g + kP;
+    // rows: (1+cB) x0 = r0 ; -cC x0 + (1+c kP) x1 - c sum x_{2+i} = r1 ; -c S_i x1 + q_i x_{2+i} = r_{2+i}
+    // F = [1/q0, 1/pivot, cC, c, 1/q_i (NS), c S_i / q_i (NS)]
+    __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
+        double q[NS], pre[NS], suf[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { F[2 + i] = 1.0 / (g + k[i]); piv = fma(-S[i], F[2 + i], piv); }
-        F[1] = 1.0 / piv;
+        for (int i = 0; i < NS; ++i) q[i] = fma(c, k[i], 1.0);
+        pre[0] = 1.0;
+#pragma unroll
+        for (int i = 1; i < NS; ++i) pre[i] = pre[i - 1] * q[i - 1];
+        suf[NS - 1] = 1.0;
+#pragma unroll
+        for (int i = NS - 2; i >= 0; --i) suf[i] = suf[i + 1] * q[i + 1];
+        const double Q = pre[NS - 1] * q[NS - 1];
+        double sq = 0.0;                                   // sum_i S_i prod_{j != i} q_j
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { pre[i] *= suf[i]; sq = fma(S[i], pre[i], sq); }
+        double inv[3] = {fma(c, Bm, 1.0), Q, fma(fma(c, kP, 1.0), Q, -(c * c) * sq)};   // q0, Q, pivot*Q
+        batch_invert<3>(inv);
+        F[0] = inv[0];
+        F[1] = Q * inv[2];
+        F[2] = c * C;
+        F[3] = c;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            double iq = pre[i] * inv[1];
+            F[4 + i] = iq;
+            F[4 + NS + i] = c * S[i] * iq;
+        }
     }
     __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
         x[0] *= F[0];
-        double s = fma(C, x[0], x[1]);
+        double sz = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) s = fma(x[2 + i], F[2 + i], s);
-        x[1] = s * F[1];
+        for (int i = 0; i < NS; ++i) { x[2 + i] *= F[4 + i]; sz += x[2 + i]; }
+        x[1] = fma(F[3], sz, fma(F[2], x[0], x[1])) * F[1];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) x[2 + i] = fma(S[i], x[1], x[2 + i]) * F[2 + i];
+        for (int i = 0; i < NS; ++i) x[2 + i] = fma(F[4 + NS + i], x[1], x[2 + i]);
     }
 };
 
 template <int NS_>
 struct SuccModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 2;
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 3 * NS_ + 3;
     // d[0] = D + S_0 (protein), d[1+i] = 1 + Dr_i + S_{i+1} (site i; no S term for the last site)
     double A, Bm, C, S[NS], d[NS + 1];
     __device__ __forceinline__ void load(const double* p) {
@@ -63,7 +105,7 @@ struct SuccModel {
         for (int i = 0; i < NS; ++i) S[i] = p[4 + i];
         d[0] = p[3] + S[0];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) d[1 + i] = 1.0 + p[4 + NS + i] + (i < NS - 1 ? S[i + 1] : 0.0);
+        for (int i = 0; i < NS; ++i) d[1 + i] = 1.0 + p[4 + NS + i] + (i < NS - 1 ? S[i < NS - 1 ? i + 1 : i] : 0.0);
     }
     __device__ __forceinline__ void rhs(const double (&y)[N], double (&f)[N]) const {
         f[0] = fma(-Bm, y[0], A);
@@ -71,57 +113,63 @@ struct SuccModel {
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             double v = fma(S[i], y[1 + i], -d[1 + i] * y[2 + i]);
-            if (i < NS - 1) v += y[3 + i];
+            if (i < NS - 1) v += y[i < NS - 1 ? 3 + i : 2 + i];
             f[2 + i] = v;
         }
     }
-    // Tridiagonal (x_1..x_{n-1}): diag g+d[j], sub -S[j-1], super -1.  Thomas without pivoting
-    // (column diagonally dominant for non-negative rates).  F[0] = 1/(g+B); F[1+j] = 1/pivot_j;
-    // F[NS+2+j] unused slot kept for alignment of indices (only first NS+2 are pivots).
-    __device__ __forceinline__ void factor(double g, double (&F)[NF]) const {
-        F[0] = 1.0 / (g + Bm);
-        double piv = g + d[0];
-        F[1] = 1.0 / piv;
+    // Tridiagonal block over x_1..x_{1+NS}: diag a_j = 1 + c d_j, sub -c S_{j-1}, super -c.
+    // Continuants theta_j = a_j theta_{j-1} - (c S_{j-1}) c theta_{j-2} give the Thomas pivots
+    // p_j = theta_j / theta_{j-1} without a sequential chain of divisions (no pivoting needed: the
+    // block is strictly column diagonally dominant for non-negative rates).
+    // F = [1/q0, cC, 1/p_j (NS+1), l_j = c S_{j-1}/p_{j-1} (NS), c/p_j (NS)]
+    __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
+        double th[NS + 2];                       // th[0] = q0, th[1+j] = theta_j
+        th[0] = fma(c, Bm, 1.0);
+        th[1] = fma(c, d[0], 1.0);
+        double cs[NS];
 #pragma unroll
-        for (int j = 1; j <= NS; ++j) {
-            // eliminate sub-diagonal -S[j-1] with row j-1: l = -S[j-1]/piv_{j-1}; piv_j = diag_j - l*(-1)...
-            double l = S[j - 1] * F[j];          // multiplier magnitude
-            F[NS + 1 + j] = l;                   // store for the forward sweep
-            piv = (g + d[j]) - l;                // diag_j - (S[j-1]/piv_{j-1}) * 1
-            F[1 + j] = 1.0 / piv;
-        }
+        for (int j = 0; j < NS; ++j) cs[j] = c * S[j];
+        th[2] = fma(fma(c, d[1], 1.0), th[1], -(cs[0] * c));
+#pragma unroll
+        for (int j = 2; j <= NS; ++j) th[1 + j] = fma(fma(c, d[j], 1.0), th[j], -(cs[j - 1] * c) * th[j - 1]);
+        double inv[NS + 2];
+#pragma unroll
+        for (int j = 0; j < NS + 2; ++j) inv[j] = th[j];
+        batch_invert<NS + 2>(inv);
+        F[0] = inv[0];
+        F[1] = c * C;
+        F[2] = inv[1];                                          // 1/p_0 = 1/theta_0
+#pragma unroll
+        for (int j = 1; j <= NS; ++j) F[2 + j] = th[j] * inv[1 + j];   // theta_{j-1} / theta_j
+#pragma unroll
+        for (int j = 1; j <= NS; ++j) F[2 + NS + j] = cs[j - 1] * F[1 + j];       // l_j
+#pragma unroll
+        for (int j = 0; j < NS; ++j) F[3 + 2 * NS + j] = c * F[2 + j];            // c / p_j
     }
     __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
         x[0] *= F[0];
-        x[1] = fma(C, x[0], x[1]);
+        x[1] = fma(F[1], x[0], x[1]);
 #pragma unroll
-        for (int j = 1; j <= NS; ++j) x[1 + j] = fma(F[NS + 1 + j], x[j], x[1 + j]);   // forward
-        x[1 + NS] *= F[1 + NS];
+        for (int j = 1; j <= NS; ++j) x[1 + j] = fma(F[2 + NS + j], x[j], x[1 + j]);        // forward
+        x[1 + NS] *= F[2 + NS];
 #pragma unroll
-        for (int j = NS - 1; j >= 0; --j) x[1 + j] = (x[1 + j] + x[2 + j]) * F[1 + j];  // backward
+        for (int j = NS - 1; j >= 0; --j) x[1 + j] = fma(F[3 + 2 * NS + j], x[2 + j], x[1 + j] * F[2 + j]);
     }
 };
 
-// ---------------------------------------------------------------------------------- epilogue
-__device__ __forceinline__ void epi_loss_point(const LocalArgs& a, EpiAcc& e, const double* tg,
-                                               const double* sg, int fi, double v, double invL) {
-    double dlt = v - __ldg(tg + fi);
-    double w = sg ? dlt / __ldg(sg + fi) : dlt;
-    e.ssr = fma(w, w, e.ssr);
-    double r = fabs(dlt) * invL;
-    e.sr += r;
-    e.sr2 = fma(r, r, e.sr2);
-}
-
 // ------------------------------------------------------------------------------------ kernel
-template <class M>
-__global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
+constexpr int TPS_BLOCK = 128;
+constexpr int TPS_COLD = 7;      // per-lane shared-memory doubles: ssr, sr, sr2, s1, s2, dyn, |p|^2
+
+template <class M, int MIN_BLOCKS>
+__global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
     constexpr int N = M::N, NS = M::NS, NF = M::NF, P = M::P;
     using namespace rodas4;
     extern __shared__ double smem[];
     double* tgrid = smem;                                     // [T]
-    double* prev = smem + a.T;                                // [N][blockDim] (dynamics metric only)
-    for (int i = threadIdx.x; i < a.T; i += blockDim.x) tgrid[i] = a.t[i];
+    double* cold = smem + a.T + threadIdx.x;                  // [TPS_COLD][TPS_BLOCK]
+    double* prev = cold + TPS_COLD * TPS_BLOCK;               // [N][TPS_BLOCK] (dynamics metric only)
+    for (int i = threadIdx.x; i < a.T; i += TPS_BLOCK) tgrid[i] = a.t[i];
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
@@ -129,22 +177,27 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
     const int T = a.T;
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
-    const double invL = 1.0 / (double)a.L;
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
 
     bool active = false, exhausted = false;
     long long sys = -1;
     M mdl;
-    double y[N], inv0[N];
-    double t = 0.0, p2 = 0.0;
+    double y[N];
+    double t = 0.0;
     StepCtl ctl;
     int kout = 0, nst = 0, nrej = 0, status = 0;
-    EpiAcc e;
-    const double* tg = nullptr;
-    const double* sg = nullptr;
 
-    // write outputs of time index k for state vector v (already clipped / normalised)
-    auto emit = [&](int k, const double (&v)[N]) {
+    // outputs of time index k for state y (or NaN for a failed system)
+    auto emit = [&](int k, bool failed) {
+        double v[N];
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = failed ? qnan : fmax(y[i], 0.0);      // np.clip(sol, 0, None)
+        if (a.normalize) {                                                       // NORMALIZE_MODEL_OUTPUT
+            const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] *= 1.0 / y0[i];       // sol *= 1/init (distmod.py:118-122)
+        }
         if (a.out_sol) {
             double* o = a.out_sol + ((size_t)sys * T + k) * N;
 #pragma unroll
@@ -158,76 +211,79 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
             for (int i = 0; i < NS; ++i) o[rna_len + T + i * T + k] = v[2 + i];
         }
         if (want_loss) {
-            if (k >= RNA_OFFSET) epi_loss_point(a, e, tg, sg, k - RNA_OFFSET, v[0], invL);
-            epi_loss_point(a, e, tg, sg, rna_len + k, v[1], invL);
+            const int g = a.group ? a.group[sys] : 0;
+            const double* tg = a.target + (size_t)g * a.L;
+            const double* sg = a.sigma ? a.sigma + (size_t)g * a.sigma_len : nullptr;
+            double ssr = cold[0 * TPS_BLOCK], sr = cold[1 * TPS_BLOCK], sr2 = cold[2 * TPS_BLOCK];
+            auto point = [&](int fi, double val) {
+                double dlt = val - __ldg(tg + fi);
+                double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                ssr = fma(w, w, ssr);
+                sr += fabs(dlt);
+                sr2 = fma(dlt, dlt, sr2);
+            };
+            if (k >= RNA_OFFSET) point(k - RNA_OFFSET, v[0]);
+            point(rna_len + k, v[1]);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) epi_loss_point(a, e, tg, sg, rna_len + T + i * T + k, v[2 + i], invL);
+            for (int i = 0; i < NS; ++i) point(rna_len + T + i * T + k, v[2 + i]);
+            cold[0 * TPS_BLOCK] = ssr; cold[1 * TPS_BLOCK] = sr; cold[2 * TPS_BLOCK] = sr2;
         }
         if (want_y) {
+            double s1 = cold[3 * TPS_BLOCK], s2 = cold[4 * TPS_BLOCK], dyn = cold[5 * TPS_BLOCK];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                e.s1 += v[i];
-                e.s2 = fma(v[i], v[i], e.s2);
+                s1 += v[i];
+                s2 = fma(v[i], v[i], s2);
                 if (a.y_metric == 3) {
-                    double* pv = prev + i * blockDim.x + threadIdx.x;
-                    if (k > 0) { double dd = v[i] - *pv; e.dyn = fma(dd, dd, e.dyn); }
-                    *pv = v[i];
+                    if (k > 0) { double dd = v[i] - prev[i * TPS_BLOCK]; dyn = fma(dd, dd, dyn); }
+                    prev[i * TPS_BLOCK] = v[i];
                 }
             }
+            cold[3 * TPS_BLOCK] = s1; cold[4 * TPS_BLOCK] = s2; cold[5 * TPS_BLOCK] = dyn;
         }
-    };
-    auto emit_state = [&](int k) {
-        double v[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            v[i] = fmax(y[i], 0.0);                       // np.clip(sol, 0, None)
-            if (a.normalize) v[i] *= inv0[i];             // NORMALIZE_MODEL_OUTPUT
-        }
-        emit(k, v);
     };
     auto finish = [&]() {
-        if (status != 0) {                                // failed system: NaN for what is missing
-            double v[N];
-            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-            for (int i = 0; i < N; ++i) v[i] = qnan;
-            for (int k = kout; k < T; ++k) emit(k, v);
-        }
+        if (status != 0)                                  // failed system: NaN for what is missing
+            for (int k = kout; k < T; ++k) emit(k, true);
         if (a.out_status) a.out_status[sys] = status;
         if (a.out_nsteps) a.out_nsteps[sys] = nst;
         if (a.out_nrej) a.out_nrej[sys] = nrej;
         if (want_loss) {
-            // regularisation rows of normest's model_func: lam/P * theta^2, target 0, sigma from tail
-            const double* pr = a.params + (size_t)sys * P;
-            double ssr = e.ssr;
+            double ssr = cold[0 * TPS_BLOCK];
             if (a.lam != 0.0) {
+                // regularisation rows of normest's model_func: lam/P * theta^2, target 0
+                const double* pr = a.params + (size_t)sys * P;
+                const int g = a.group ? a.group[sys] : 0;
+                const double* sg = (a.sigma && a.sigma_len > a.L) ? a.sigma + (size_t)g * a.sigma_len + a.L : nullptr;
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     double th = pr[i];
                     double w = a.lam / (double)P * th * th;
-                    if (sg && a.sigma_len > a.L) w /= __ldg(sg + a.L + i);
+                    if (sg) w /= __ldg(sg + i);
                     ssr = fma(w, w, ssr);
                 }
             }
             if (a.out_ssr) a.out_ssr[sys] = ssr;
             if (a.out_score) {
-                double Ld = (double)a.L;
-                double mse = e.sr2, mean_r2 = e.sr2 / Ld, mae = e.sr / Ld;
-                double var = mean_r2 - mae * mae;
-                double l2 = sqrt(p2) / (double)P;
-                a.out_score[sys] = a.w_delta * mse + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
-                                   a.w_gamma * var + a.w_mu * l2;
+                // score_fit (config/config.py:176-226) with r = |target - pred| / L
+                const double Ld = (double)a.L, invL = 1.0 / Ld;
+                const double sr = cold[1 * TPS_BLOCK] * invL, sr2 = cold[2 * TPS_BLOCK] * invL * invL;
+                const double mean_r2 = sr2 * invL, mae = sr * invL;
+                const double l2 = sqrt(cold[6 * TPS_BLOCK]) / (double)P;
+                a.out_score[sys] = a.w_delta * sr2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                                   a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * l2;
             }
         }
         if (want_y) {
-            double len = (double)(T * N), yv;
-            double mean = e.s1 / len;
+            const double s1 = cold[3 * TPS_BLOCK], s2 = cold[4 * TPS_BLOCK];
+            const double len = (double)(T * N), mean = s1 / len;
+            double yv;
             switch (a.y_metric) {
-                case 0: yv = e.s1; break;
+                case 0: yv = s1; break;
                 case 1: yv = mean; break;
-                case 2: yv = e.s2 / len - mean * mean; break;
-                case 3: yv = e.dyn; break;
-                default: yv = sqrt(e.s2); break;
+                case 2: yv = s2 / len - mean * mean; break;
+                case 3: yv = cold[5 * TPS_BLOCK]; break;
+                default: yv = sqrt(s2); break;
             }
             a.out_Y[sys] = yv;
         }
@@ -249,7 +305,7 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
                     active = true;
                     const double* pr = a.params + (size_t)sys * P;
                     double pv[P];
-                    p2 = 0.0;
+                    double p2 = 0.0;
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
                         double v = pr[i];
@@ -260,11 +316,10 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
                     mdl.load(pv);
                     const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { y[i] = y0[i]; inv0[i] = a.normalize ? 1.0 / y[i] : 1.0; }
-                    int g = a.group ? a.group[sys] : 0;
-                    tg = a.target ? a.target + (size_t)g * a.L : nullptr;
-                    sg = a.sigma ? a.sigma + (size_t)g * a.sigma_len : nullptr;
-                    e = EpiAcc{0, 0, 0, 0, 0, 0};
+                    for (int i = 0; i < N; ++i) y[i] = y0[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) cold[i * TPS_BLOCK] = 0.0;
+                    cold[6 * TPS_BLOCK] = p2;
                     t = tgrid[0];
                     nst = nrej = status = 0;
                     // initial step: 1% of the time scale |y|/|f| in the error-weighted norm
@@ -278,8 +333,8 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
                         d1 = fmax(d1, fabs(f0[i]) * sc);
                     }
                     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-                    ctl = StepCtl{h0, h0, 1.0, 0, 0};
-                    emit_state(0);
+                    ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
+                    emit(0, false);
                     kout = 1;
                     if (T <= 1) finish();
                 } else {
@@ -294,7 +349,7 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
         const double tout = tgrid[kout];
         const double rem = tout - t;
         if (!(rem > 0.0)) {            // repeated output time
-            emit_state(kout);
+            emit(kout, false);
             if (++kout >= T) finish();
             continue;
         }
@@ -302,70 +357,53 @@ __global__ void __launch_bounds__(128) local_tps_kernel(const LocalArgs a) {
         bool land = false;
         if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
         else if (hh > 0.5 * rem) hh = 0.5 * rem;
-        const double ih = 1.0 / hh;
-        const double g = ih * (1.0 / GAMMA);
 
         double F[NF];
-        mdl.factor(g, F);
-        double U1[N], U2[N], U3[N], U4[N], U5[N], w[N], E[N];
-        mdl.rhs(y, U1);
-        mdl.solve(F, U1);
+        mdl.factor(hh * GAMMA, F);
+        double v[N], yn[N], er[N];
+        mdl.rhs(y, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = fma(A21, U1[i], y[i]);
-        mdl.rhs(w, U2);
+        for (int i = 0; i < N; ++i) v[i] *= hh;
+        mdl.solve(F, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) U2[i] = fma(C21 * ih, U1[i], U2[i]);
-        mdl.solve(F, U2);
+        for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
+        mdl.solve(F, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = fma(A32, U2[i], fma(A31, U1[i], y[i]));
-        mdl.rhs(w, U3);
+        for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
+        mdl.solve(F, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) U3[i] = fma(C32 * ih, U2[i], fma(C31 * ih, U1[i], U3[i]));
-        mdl.solve(F, U3);
+        for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
+        mdl.solve(F, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) w[i] = fma(A43, U3[i], fma(A42, U2[i], fma(A41, U1[i], y[i])));
-        mdl.rhs(w, U4);
+        for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
+        mdl.solve(F, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-            U4[i] = fma(C43 * ih, U3[i], fma(C42 * ih, U2[i], fma(C41 * ih, U1[i], U4[i])));
-        mdl.solve(F, U4);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            w[i] = fma(A54, U4[i], fma(A53, U3[i], fma(A52, U2[i], fma(A51, U1[i], y[i]))));
-        mdl.rhs(w, U5);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            U5[i] = fma(C54 * ih, U4[i], fma(C53 * ih, U3[i], fma(C52 * ih, U2[i], fma(C51 * ih, U1[i], U5[i]))));
-        mdl.solve(F, U5);
-#pragma unroll
-        for (int i = 0; i < N; ++i) w[i] += U5[i];
-        mdl.rhs(w, E);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            E[i] = fma(C65 * ih, U5[i],
-                       fma(C64 * ih, U4[i], fma(C63 * ih, U3[i], fma(C62 * ih, U2[i], fma(C61 * ih, U1[i], E[i])))));
-        mdl.solve(F, E);
-        double err = 0.0;
+        for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
+        mdl.solve(F, v);
+        float err = 0.0f;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            w[i] += E[i];
-            double sc = fma(a.rtol, fmax(fabs(y[i]), fabs(w[i])), a.atol);
-            err = fmax(err, fabs(E[i]) / sc);
+            yn[i] = fma(MU6, v[i], yn[i]);
+            er[i] = fma(EPS6, v[i], er[i]);
+            err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
         }
+        double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
+#pragma unroll
+        for (int i = 0; i < N; ++i) chk += yn[i];
 
-        if (!(err < 1.0e300)) {                     // NaN or inf
+        if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
             status = 3;
             finish();
-        } else if (err <= 1.0) {
+        } else if (err <= 1.0f) {
             ++nst;
-            double hprop = ctl.h;
-            double hnew = ctl_accept(ctl, hh, err);
+            const double hprop = ctl.h;
+            const double hnew = ctl_accept(ctl, hh, err);
             ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
 #pragma unroll
-            for (int i = 0; i < N; ++i) y[i] = w[i];
+            for (int i = 0; i < N; ++i) y[i] = yn[i];
             if (land) {
                 t = tout;
-                emit_state(kout);
+                emit(kout, false);
                 if (++kout >= T) finish();
             } else {
                 t += hh;

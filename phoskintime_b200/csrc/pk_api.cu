@@ -197,15 +197,18 @@ __global__ void __launch_bounds__(256) morris_stats_kernel(const double* ee, lon
 namespace {
 
 // Register-resident kernel limits: the largest site counts that compile with ZERO local-memory
-// spill (nvcc -Xptxas -v: dist-6 246 regs, succ-5 238 regs); larger systems take the dense path.
-constexpr int TPS_MAX_NS_DIST = 6;
-constexpr int TPS_MAX_NS_SUCC = 5;
-constexpr int TPS_BLOCK = 128;
+// spill (csrc/ptxas.log); larger systems take the shared-memory dense path.
+constexpr int TPS_MAX_NS_DIST = 8;
+constexpr int TPS_MAX_NS_SUCC = 8;
+// Resident CTAs per SM the register allocator must allow with ZERO spill (checked in ptxas.log):
+// n <= 5 states fit 128 registers (4 CTAs x 128 lanes), mid sizes get 168 (3 CTAs), the rest 255.
+template <class M> constexpr int tps_min_blocks() { return M::N <= 5 ? 4 : (M::N + M::NF <= 26 ? 3 : 2); }
+using pk::TPS_BLOCK;
 
 template <class M>
 cudaError_t launch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
-    size_t smem = (size_t)(a.T + M::N * TPS_BLOCK) * sizeof(double);
-    auto kern = pk::local_tps_kernel<M>;
+    size_t smem = (size_t)(a.T + (pk::TPS_COLD + M::N) * TPS_BLOCK) * sizeof(double);
+    auto kern = pk::local_tps_kernel<M, tps_min_blocks<M>()>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -230,9 +233,9 @@ cudaError_t dispatch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
         case 3: return launch_tps<M<3>>(h, a);
         case 4: return launch_tps<M<4>>(h, a);
         case 5: return launch_tps<M<5>>(h, a);
-        case 6:
-            if constexpr (MAXNS >= 6) return launch_tps<M<6>>(h, a);
-            else return cudaErrorInvalidValue;
+        case 6: return launch_tps<M<6>>(h, a);
+        case 7: return launch_tps<M<7>>(h, a);
+        case 8: return launch_tps<M<8>>(h, a);
         default: return cudaErrorInvalidValue;
     }
 }
