@@ -93,10 +93,17 @@ int pk_device_info(pk_handle_t h, int* sm_count, int* clock_khz, char* name, int
 int pk_local_dims(int model, int n_sites, int T, int* n_states, int* n_params, int* flat_len);
 
 void pk_local_job_init(pk_local_job* job);        /* zero + defaults (score_w = 1, y_metric none)   */
+int pk_sizeof_local_job(void);                    /* sizeof(pk_local_job), for binding self-checks  */
 int pk_local_solve_batch(pk_handle_t h, const pk_local_job* job);
 /* number of kernel launches the last pk_* call on this handle issued, and its device time (ms,
  * CUDA events on the handle's stream around the kernels only, copies excluded) */
 int pk_last_launch_info(pk_handle_t h, int* n_launches, float* kernel_ms);
+
+/* Region timing on the handle's stream (the stream every pk_* kernel and copy is issued on):
+ * pk_region_begin records a CUDA event, pk_region_end records a second one, synchronises and
+ * returns the device time between them in ms. */
+int pk_region_begin(pk_handle_t h);
+int pk_region_end(pk_handle_t h, float* ms);
 
 /* Morris elementary effects on device data already gathered: X[N*(D+1),D], Y[N*(D+1)].
  * scaled!=0 -> sigma-scaled EE (analysis.py:264 `scaled=True`). Outputs [D] each (may be NULL). */

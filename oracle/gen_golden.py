@@ -33,6 +33,10 @@ def load_compute_Y(metric):
     """sensitivity/analysis.py closes over Y_METRIC at jit time: one module per metric,
     with SALib / plotting (absent here, not on the path being pinned) stubbed out."""
     ref_shim.install_stubs(y_metric=metric)
+    # numba's on-disk cache is keyed by source file, not by the global it closed over: give every
+    # metric its own cache directory or the first compiled metric would be returned for all.
+    import numba
+    numba.config.CACHE_DIR = f"/tmp/phoskin_numba_cache_{metric}"
     const = sys.modules["config.constants"]
     const.NUM_TRAJECTORIES, const.PARAMETER_SPACE = 1000, 400
     const.TIME_POINTS_RNA = np.array([4.0, 8.0, 15.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])

@@ -49,6 +49,9 @@ SYMBOLS = {
     "pk_local_dims": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                 C.POINTER(C.c_int)]),
     "pk_local_job_init": (None, [C.POINTER(PkLocalJob)]),
+    "pk_sizeof_local_job": (C.c_int, []),
+    "pk_region_begin": (C.c_int, [C.c_void_p]),
+    "pk_region_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pk_local_solve_batch": (C.c_int, [C.c_void_p, C.POINTER(PkLocalJob)]),
     "pk_last_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     "pk_morris_ee": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
@@ -85,6 +88,8 @@ def load():
         fn.argtypes = args
     if lib.pk_abi_version() != 1:
         raise PhoskinError("libphoskin_b200.so ABI version mismatch")
+    if lib.pk_sizeof_local_job() != C.sizeof(PkLocalJob):
+        raise PhoskinError("pk_local_job layout mismatch between header and ctypes mirror")
     _lib = lib
     return lib
 

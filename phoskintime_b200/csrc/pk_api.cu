@@ -87,7 +87,7 @@ struct pk_handle_s {
     int clock_khz = 0;
     char name[128] = {0};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
     DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch;
     unsigned long long* counter = nullptr;
     int last_launches = 0;
@@ -312,6 +312,8 @@ int pk_create(int device, pk_handle_t* out) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->evr0));
+    CK(cudaEventCreate(&h->evr1));
     CK(cudaMalloc(&h->counter, sizeof(unsigned long long)));
     *out = h;
     return 0;
@@ -327,6 +329,8 @@ int pk_destroy(pk_handle_t h) {
     if (h->counter) cudaFree(h->counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evr0) cudaEventDestroy(h->evr0);
+    if (h->evr1) cudaEventDestroy(h->evr1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -354,6 +358,26 @@ void pk_local_job_init(pk_local_job* job) {
     job->y_metric = PK_Y_NONE;
     job->n_groups = 1;
     for (int i = 0; i < 5; ++i) job->score_w[i] = 1.0;
+}
+
+int pk_sizeof_local_job(void) { return (int)sizeof(pk_local_job); }
+
+int pk_region_begin(pk_handle_t h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->evr0, h->stream));
+    return 0;
+}
+
+int pk_region_end(pk_handle_t h, float* ms) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->evr1, h->stream));
+    CK(cudaEventSynchronize(h->evr1));
+    float v = 0.f;
+    CK(cudaEventElapsedTime(&v, h->evr0, h->evr1));
+    if (ms) *ms = v;
+    return 0;
 }
 
 int pk_last_launch_info(pk_handle_t h, int* n_launches, float* kernel_ms) {

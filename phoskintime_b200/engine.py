@@ -64,6 +64,14 @@ class Engine:
         _lib.check(self.lib.pk_last_launch_info(self._h, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    def region_begin(self):
+        _lib.check(self.lib.pk_region_begin(self._h))
+
+    def region_end(self):
+        ms = C.c_float()
+        _lib.check(self.lib.pk_region_end(self._h, C.byref(ms)))
+        return ms.value
+
     def measure_fp64_peak(self):
         tf, ms = C.c_double(), C.c_float()
         _lib.check(self.lib.pk_measure_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
@@ -73,7 +81,7 @@ class Engine:
     def solve_local_batch(self, model, params, init_cond, num_psites, t, want=("sol", "flat"), *,
                           target=None, sigma=None, group=None, lam=0.0, y_metric="total_signal",
                           rtol=None, atol=None, max_steps=0, normalize=False, log_params=False,
-                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None):
+                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True):
         """Solve B systems.  Returns a dict with the requested keys among
         sol[B,T,n], flat[B,L], Y[B], ssr[B], score[B] plus status/nsteps/nrej[B] (int32).
 
@@ -82,6 +90,7 @@ class Engine:
         target/sigma/group : fused-loss inputs — target [L] or [G,L]; sigma None, [L]/[L+P] or
             [G,·]; group [B] int32 indices into G (None = all 0)
         out : optional dict of preallocated outputs (same kind as params) to fill
+        counters : also return accepted/rejected step counts per system (nsteps, nrej)
         """
         want = tuple(want)
         unknown = set(want) - {"sol", "flat", "Y", "ssr", "score"}
@@ -168,8 +177,9 @@ class Engine:
             if "score" in want:
                 job.out_score = alloc("score", (B,))
         job.out_status = alloc("status", (B,), "i32")
-        job.out_nsteps = alloc("nsteps", (B,), "i32")
-        job.out_nrej = alloc("nrej", (B,), "i32")
+        if counters:
+            job.out_nsteps = alloc("nsteps", (B,), "i32")
+            job.out_nrej = alloc("nrej", (B,), "i32")
 
         if dev:
             xp.sync()          # inputs produced on torch's stream must be visible to ours

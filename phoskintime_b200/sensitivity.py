@@ -1,0 +1,120 @@
+"""Morris sensitivity on the batched engine — mirrors the reference's `sensitivity/analysis.py`.
+
+Reference flow (sensitivity/analysis.py:197-331): build the ±50 % box around the fitted
+parameters, draw N Morris trajectories, run ONE `solve_ode` per row in a process pool, reduce
+each solution to a scalar Y (`_compute_Y`), run SALib's `analyze`, then rank the trajectories
+by RMSE against the data and keep the K closest.  Here the N·(D+1) solves are one kernel launch
+with Y fused into its epilogue, and the elementary-effects statistics are a second small launch
+(`pk_morris_ee`).  Trajectory generation stays on the host (it is O(N·D) integers).
+
+SALib itself is not available in this image and is not part of the reference tree; sampling and
+analysis follow the published method (Morris 1991, Campolongo 2007, Sin & Gernaey 2009 scaling) —
+see oracle/morris.py for the restated checker.
+"""
+import math
+
+import numpy as np
+
+from .engine import get_engine
+
+PERTURBATIONS_VALUE = 0.5      # config.toml:222
+NUM_TRAJECTORIES = 1000        # config/constants.py:47
+PARAMETER_SPACE = 400          # config/constants.py:48 (num_levels)
+Y_METRIC = "total_signal"      # config/constants.py:104
+
+
+def compute_bound(value, perturbation=PERTURBATIONS_VALUE):
+    """[lb, ub] for one parameter (sensitivity/analysis.py:20-35)."""
+    if abs(value) < 1e-6:
+        return [0.0, 0.1]
+    return [max(0.0, value * (1 - perturbation)), value * (1 + perturbation)]
+
+
+def get_param_names_rand(num_psites):
+    """config/helpers/__init__.py:5-22 — labels only; Ddeg values are positional (bitmask-1)."""
+    from itertools import combinations
+    names = ["A", "B", "C", "D"] + [f"S{i}" for i in range(1, num_psites + 1)]
+    for i in range(1, num_psites + 1):
+        for combo in combinations(range(1, num_psites + 1), i):
+            names.append("D" + "".join(map(str, combo)))
+    return names
+
+
+def define_sensitivity_problem_rand(num_psites, values):
+    names = get_param_names_rand(num_psites)
+    assert len(values) == len(names), "Length mismatch with values"
+    return {"num_vars": len(names), "names": names, "bounds": [compute_bound(v) for v in values]}
+
+
+def define_sensitivity_problem_ds(num_psites, values):
+    num_vars = 4 + 2 * num_psites
+    names = ["A", "B", "C", "D"] + [f"S{i + 1}" for i in range(num_psites)] + \
+            [f"D{i + 1}" for i in range(num_psites)]
+    assert len(values) == num_vars, "Length mismatch with values"
+    return {"num_vars": num_vars, "names": names, "bounds": [compute_bound(v) for v in values]}
+
+
+def morris_sample(problem, N, num_levels=4, seed=None):
+    """N trajectories of D+1 points on a `num_levels` grid, scaled to problem['bounds'].
+    Returns X[N*(D+1), D].  One coordinate moves by delta = p/(2(p-1)) per step, in random
+    order and direction."""
+    bounds = np.asarray(problem["bounds"], dtype=np.float64)
+    D = bounds.shape[0]
+    rng = np.random.default_rng(seed)
+    delta = num_levels / (2.0 * (num_levels - 1))
+    grid = np.linspace(0.0, 1.0 - delta, num_levels // 2)
+    base = rng.choice(grid, (N, D))
+    rank = np.argsort(rng.random((N, D)), axis=1)            # rank[r, c]: move index of coordinate c
+    up = rng.random((N, D)) < 0.5
+    step = np.arange(D + 1)[None, :, None]                   # [1, D+1, 1]
+    moved = step > rank[:, None, :]                          # [N, D+1, D]
+    x01 = base[:, None, :] + delta * np.where(up[:, None, :], moved, ~moved)
+    return bounds[:, 0] + x01.reshape(-1, D) * (bounds[:, 1] - bounds[:, 0])
+
+
+def sensitivity_analysis(popt, time_points, num_psites, init_cond, model, *, pr_data=None, p_data=None,
+                         rna_data=None, N=NUM_TRAJECTORIES, num_levels=PARAMETER_SPACE,
+                         y_metric=Y_METRIC, scaled=True, seed=None, X=None, engine=None,
+                         keep_trajectories=True):
+    """Batched equivalent of `_sensitivity_analysis` (without plotting).
+
+    Returns (Si, best_trajectories): Si has names, mu, mu_star, sigma (numpy, length D) and Y;
+    best_trajectories is the reference's top-K list (params, solution, rmse) when data are given.
+    """
+    eng = engine or get_engine()
+    popt = np.asarray(popt, dtype=np.float64)
+    problem = (define_sensitivity_problem_rand if model == "randmod" else define_sensitivity_problem_ds)(
+        num_psites, popt)
+    if X is None:
+        X = morris_sample(problem, N, num_levels, seed)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    D = problem["num_vars"]
+    need_sol = keep_trajectories and pr_data is not None
+    want = ("Y", "sol") if need_sol else ("Y",)
+    res = eng.solve_local_batch(model, X, init_cond, num_psites, time_points, want=want, y_metric=y_metric)
+    Y = np.nan_to_num(res["Y"], nan=0.0, posinf=0.0, neginf=0.0)          # analysis.py:261
+    stats = eng.morris_ee(X, Y, num_levels, scaled=scaled)
+    Si = {"names": problem["names"], "mu": stats["mu"], "mu_star": stats["mu_star"], "sigma": stats["sigma"],
+          "Y": Y, "X": X, "status": res["status"]}
+    best = []
+    if need_sol:
+        best = select_closest(res["sol"], X, pr_data, p_data, rna_data, num_psites, N, num_levels)
+    return Si, best
+
+
+def select_closest(sol, X, pr_data, p_data, rna_data, num_psites, N=NUM_TRAJECTORIES, num_levels=PARAMETER_SPACE):
+    """RMSE of every trajectory against the data and the K = ceil(10 N / levels) closest
+    (sensitivity/analysis.py:267-305)."""
+    protein_ref = np.asarray(pr_data, dtype=np.float64).reshape(-1)
+    psite_ref = np.asarray(p_data, dtype=np.float64)
+    rna_ref = np.asarray(rna_data, dtype=np.float64).reshape(-1)
+    rna_pred = sol[:, -rna_ref.size:, 0]
+    prot_pred = sol[:, :, 1]
+    psite_pred = sol[:, :, 2:2 + num_psites]
+    rna_mse = np.mean((np.abs(rna_pred - rna_ref[None, :]) / rna_ref.size) ** 2, axis=1)
+    psite_mse = np.mean((np.abs(psite_pred - psite_ref.T[None, :, :]) / psite_ref.size) ** 2, axis=(1, 2))
+    prot_mse = np.mean((np.abs(prot_pred - protein_ref[None, :]) / protein_ref.size) ** 2, axis=1)
+    rmse = np.sqrt((rna_mse + psite_mse + prot_mse) / 2.0)
+    K = int(math.ceil(N * 10 / num_levels))
+    idx = np.argsort(rmse)[:K]
+    return [{"params": X[i], "solution": sol[i], "rmse": float(rmse[i])} for i in idx]
