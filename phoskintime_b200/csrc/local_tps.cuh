@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             cold[3 * TPS_BLOCK] = s1; cold[4 * TPS_BLOCK] = s2; cold[5 * TPS_BLOCK] = dyn;
         }
     };
+    // final scalars of a system; called from exactly one site to keep the kernel inside the
+    // instruction cache (every extra inlined copy of emit/finish costs ~10 KB of SASS)
     auto finish = [&]() {
-        if (status != 0)                                  // failed system: NaN for what is missing
-            for (int k = kout; k < T; ++k) emit(k, true);
         if (a.out_status) a.out_status[sys] = status;
         if (a.out_nsteps) a.out_nsteps[sys] = nst;
         if (a.out_nrej) a.out_nrej[sys] = nrej;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 const double* pr = a.params + (size_t)sys * P;
                 const int g = a.group ? a.group[sys] : 0;
                 const double* sg = (a.sigma && a.sigma_len > a.L) ? a.sigma + (size_t)g * a.sigma_len + a.L : nullptr;
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < P; ++i) {
                     double th = pr[i];
                     double w = a.lam / (double)P * th * th;
@@ -334,9 +334,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     }
                     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
                     ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
-                    emit(0, false);
-                    kout = 1;
-                    if (T <= 1) finish();
+                    kout = 0;                 // output index 0 (the initial state) is emitted below
                 } else {
                     exhausted = true;
                 }
@@ -345,75 +343,73 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
         if (__all_sync(FULL, !active)) break;
         if (!active) continue;
 
-        // ------------------------------------------------------------------ one step attempt
+        // ------------------------------------------------------------- one step attempt, or an
+        // emission without a step (initial state, repeated output time, NaN tail of a failed system)
+        bool do_emit = false;
         const double tout = tgrid[kout];
         const double rem = tout - t;
-        if (!(rem > 0.0)) {            // repeated output time
-            emit(kout, false);
-            if (++kout >= T) finish();
-            continue;
-        }
-        double hh = ctl.h;
-        bool land = false;
-        if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
-        else if (hh > 0.5 * rem) hh = 0.5 * rem;
-
-        double F[NF];
-        mdl.factor(hh * GAMMA, F);
-        double v[N], yn[N], er[N];
-        mdl.rhs(y, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] *= hh;
-        mdl.solve(F, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
-        mdl.solve(F, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
-        mdl.solve(F, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
-        mdl.solve(F, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
-        mdl.solve(F, v);
-#pragma unroll
-        for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
-        mdl.solve(F, v);
-        float err = 0.0f;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            yn[i] = fma(MU6, v[i], yn[i]);
-            er[i] = fma(EPS6, v[i], er[i]);
-            err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
-        }
-        double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
-#pragma unroll
-        for (int i = 0; i < N; ++i) chk += yn[i];
-
-        if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
-            status = 3;
-            finish();
-        } else if (err <= 1.0f) {
-            ++nst;
-            const double hprop = ctl.h;
-            const double hnew = ctl_accept(ctl, hh, err);
-            ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
-#pragma unroll
-            for (int i = 0; i < N; ++i) y[i] = yn[i];
-            if (land) {
-                t = tout;
-                emit(kout, false);
-                if (++kout >= T) finish();
-            } else {
-                t += hh;
-            }
-            if (active && nst + nrej >= a.max_steps) { status = 1; finish(); }
+        if (status != 0 || kout == 0 || !(rem > 0.0)) {
+            do_emit = true;
         } else {
-            ++nrej;
-            ctl.h = ctl_reject(ctl, hh, err);
-            if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) { status = 2; finish(); }
-            else if (nst + nrej >= a.max_steps) { status = 1; finish(); }
+            double hh = ctl.h;
+            bool land = false;
+            if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
+            else if (hh > 0.5 * rem) hh = 0.5 * rem;
+
+            double F[NF];
+            mdl.factor(hh * GAMMA, F);
+            double v[N], yn[N], er[N];
+            mdl.rhs(y, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] *= hh;
+            mdl.solve(F, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
+            mdl.solve(F, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
+            mdl.solve(F, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
+            mdl.solve(F, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
+            mdl.solve(F, v);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
+            mdl.solve(F, v);
+            float err = 0.0f;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                yn[i] = fma(MU6, v[i], yn[i]);
+                er[i] = fma(EPS6, v[i], er[i]);
+                err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
+            }
+            double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
+#pragma unroll
+            for (int i = 0; i < N; ++i) chk += yn[i];
+
+            if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
+                status = 3;
+            } else if (err <= 1.0f) {
+                ++nst;
+                const double hprop = ctl.h;
+                const double hnew = ctl_accept(ctl, hh, err);
+                ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
+#pragma unroll
+                for (int i = 0; i < N; ++i) y[i] = yn[i];
+                if (land) { t = tout; do_emit = true; }
+                else t += hh;
+            } else {
+                ++nrej;
+                ctl.h = ctl_reject(ctl, hh, err);
+                if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
+            }
+            if (status == 0 && !do_emit && nst + nrej >= a.max_steps) status = 1;
+        }
+        if (do_emit) {
+            emit(kout, status != 0);
+            if (++kout >= T) finish();
         }
     }
 }
