@@ -7,10 +7,9 @@
 //                pivots obtained from the continuant recurrence so that they are independent
 // mRNA (row 0) is decoupled in both and eliminated first.  All reciprocals of one factorisation come
 // from ONE FP64 division (batch inversion by prefix products); the error ratio and the step-size
-// controller run in FP32.  Rarely touched per-system state (loss / Y accumulators) lives in shared
-// memory.  Lanes pull systems from a global queue (warp-aggregated atomicAdd) as they finish, so a
+// controller run in FP32.  Lanes pull systems from a global queue (warp-aggregated atomicAdd) as they finish, so a
 // warp never idles on its slowest member.  The epilogue (clip, flat layout, weighted residual /
-// score_fit, Morris Y) is fused: it runs at the step that lands on each requested output time.
+// score_fit, Morris Y) is fused and runs warp-cooperatively when a system completes.
 #pragma once
 #include "pk_common.cuh"
 
@@ -159,25 +158,38 @@ struct SuccModel {
 
 // ------------------------------------------------------------------------------------ kernel
 constexpr int TPS_BLOCK = 128;
-constexpr int TPS_COLD = 7;      // per-lane shared-memory doubles: ssr, sr, sr2, s1, s2, dyn, |p|^2
 
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Step loop: every lane owns one system.  A lane that lands on an output time only stores its raw
+// state (N doubles) into its private trajectory slot `traj` (one [T][N] slot per resident lane,
+// ~45 MB in total, L2-resident and reused for every system the lane integrates).  When a lane has
+// produced its last output the WHOLE WARP runs the epilogue for it: 32 lanes walk the T*N stored
+// values coalesced, clip / normalise, write sol and flat rows coalesced, and reduce the weighted
+// residual, score_fit and Morris-Y sums with shuffles.  The divergent part of the loop is thus a
+// handful of stores; the expensive epilogue runs at full warp width once per system.
 template <class M, int MIN_BLOCKS>
 __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
-    constexpr int N = M::N, NS = M::NS, NF = M::NF, P = M::P;
+    constexpr int N = M::N, NF = M::NF, P = M::P;
     using namespace rodas4;
     extern __shared__ double smem[];
     double* tgrid = smem;                                     // [T]
-    double* cold = smem + a.T + threadIdx.x;                  // [TPS_COLD][TPS_BLOCK]
-    double* prev = cold + TPS_COLD * TPS_BLOCK;               // [N][TPS_BLOCK] (dynamics metric only)
     for (int i = threadIdx.x; i < a.T; i += TPS_BLOCK) tgrid[i] = a.t[i];
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int T = a.T;
+    const int TN = T * N;
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
+    double* const warp_traj = a.traj + ((size_t)blockIdx.x * TPS_BLOCK + (threadIdx.x & ~31)) * TN;
+    double* const my_traj = warp_traj + (size_t)lane * TN;
 
     bool active = false, exhausted = false;
     long long sys = -1;
@@ -186,109 +198,6 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     double t = 0.0;
     StepCtl ctl;
     int kout = 0, nst = 0, nrej = 0, status = 0;
-
-    // outputs of time index k for state y (or NaN for a failed system)
-    auto emit = [&](int k, bool failed) {
-        double v[N];
-        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = failed ? qnan : fmax(y[i], 0.0);      // np.clip(sol, 0, None)
-        if (a.normalize) {                                                       // NORMALIZE_MODEL_OUTPUT
-            const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
-#pragma unroll
-            for (int i = 0; i < N; ++i) v[i] *= 1.0 / y0[i];       // sol *= 1/init (distmod.py:118-122)
-        }
-        if (a.out_sol) {
-            double* o = a.out_sol + ((size_t)sys * T + k) * N;
-#pragma unroll
-            for (int i = 0; i < N; ++i) o[i] = v[i];
-        }
-        if (a.out_flat) {
-            double* o = a.out_flat + (size_t)sys * a.L;
-            if (k >= RNA_OFFSET) o[k - RNA_OFFSET] = v[0];
-            o[rna_len + k] = v[1];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) o[rna_len + T + i * T + k] = v[2 + i];
-        }
-        if (want_loss) {
-            const int g = a.group ? a.group[sys] : 0;
-            const double* tg = a.target + (size_t)g * a.L;
-            const double* sg = a.sigma ? a.sigma + (size_t)g * a.sigma_len : nullptr;
-            double ssr = cold[0 * TPS_BLOCK], sr = cold[1 * TPS_BLOCK], sr2 = cold[2 * TPS_BLOCK];
-            auto point = [&](int fi, double val) {
-                double dlt = val - __ldg(tg + fi);
-                double w = sg ? dlt / __ldg(sg + fi) : dlt;
-                ssr = fma(w, w, ssr);
-                sr += fabs(dlt);
-                sr2 = fma(dlt, dlt, sr2);
-            };
-            if (k >= RNA_OFFSET) point(k - RNA_OFFSET, v[0]);
-            point(rna_len + k, v[1]);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) point(rna_len + T + i * T + k, v[2 + i]);
-            cold[0 * TPS_BLOCK] = ssr; cold[1 * TPS_BLOCK] = sr; cold[2 * TPS_BLOCK] = sr2;
-        }
-        if (want_y) {
-            double s1 = cold[3 * TPS_BLOCK], s2 = cold[4 * TPS_BLOCK], dyn = cold[5 * TPS_BLOCK];
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                s1 += v[i];
-                s2 = fma(v[i], v[i], s2);
-                if (a.y_metric == 3) {
-                    if (k > 0) { double dd = v[i] - prev[i * TPS_BLOCK]; dyn = fma(dd, dd, dyn); }
-                    prev[i * TPS_BLOCK] = v[i];
-                }
-            }
-            cold[3 * TPS_BLOCK] = s1; cold[4 * TPS_BLOCK] = s2; cold[5 * TPS_BLOCK] = dyn;
-        }
-    };
-    // final scalars of a system; called from exactly one site to keep the kernel inside the
-    // instruction cache (every extra inlined copy of emit/finish costs ~10 KB of SASS)
-    auto finish = [&]() {
-        if (a.out_status) a.out_status[sys] = status;
-        if (a.out_nsteps) a.out_nsteps[sys] = nst;
-        if (a.out_nrej) a.out_nrej[sys] = nrej;
-        if (want_loss) {
-            double ssr = cold[0 * TPS_BLOCK];
-            if (a.lam != 0.0) {
-                // regularisation rows of normest's model_func: lam/P * theta^2, target 0
-                const double* pr = a.params + (size_t)sys * P;
-                const int g = a.group ? a.group[sys] : 0;
-                const double* sg = (a.sigma && a.sigma_len > a.L) ? a.sigma + (size_t)g * a.sigma_len + a.L : nullptr;
-#pragma unroll 1
-                for (int i = 0; i < P; ++i) {
-                    double th = pr[i];
-                    double w = a.lam / (double)P * th * th;
-                    if (sg) w /= __ldg(sg + i);
-                    ssr = fma(w, w, ssr);
-                }
-            }
-            if (a.out_ssr) a.out_ssr[sys] = ssr;
-            if (a.out_score) {
-                // score_fit (config/config.py:176-226) with r = |target - pred| / L
-                const double Ld = (double)a.L, invL = 1.0 / Ld;
-                const double sr = cold[1 * TPS_BLOCK] * invL, sr2 = cold[2 * TPS_BLOCK] * invL * invL;
-                const double mean_r2 = sr2 * invL, mae = sr * invL;
-                const double l2 = sqrt(cold[6 * TPS_BLOCK]) / (double)P;
-                a.out_score[sys] = a.w_delta * sr2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
-                                   a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * l2;
-            }
-        }
-        if (want_y) {
-            const double s1 = cold[3 * TPS_BLOCK], s2 = cold[4 * TPS_BLOCK];
-            const double len = (double)(T * N), mean = s1 / len;
-            double yv;
-            switch (a.y_metric) {
-                case 0: yv = s1; break;
-                case 1: yv = mean; break;
-                case 2: yv = s2 / len - mean * mean; break;
-                case 3: yv = cold[5 * TPS_BLOCK]; break;
-                default: yv = sqrt(s2); break;
-            }
-            a.out_Y[sys] = yv;
-        }
-        active = false;
-    };
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -305,112 +214,201 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     active = true;
                     const double* pr = a.params + (size_t)sys * P;
                     double pv[P];
-                    double p2 = 0.0;
 #pragma unroll
-                    for (int i = 0; i < P; ++i) {
-                        double v = pr[i];
-                        if (a.log_params) v = exp(v);
-                        pv[i] = v;
-                        p2 = fma(v, v, p2);
+                    for (int i = 0; i < P; ++i) pv[i] = pr[i];
+                    if (a.log_params) {
+#pragma unroll 1
+                        for (int i = 0; i < P; ++i) pv[i] = exp(pv[i]);
                     }
                     mdl.load(pv);
                     const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) y[i] = y0[i];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) cold[i * TPS_BLOCK] = 0.0;
-                    cold[6 * TPS_BLOCK] = p2;
+                    for (int i = 0; i < N; ++i) { y[i] = y0[i]; my_traj[i] = y[i]; }
                     t = tgrid[0];
                     nst = nrej = status = 0;
+                    kout = 1;
                     // initial step: 1% of the time scale |y|/|f| in the error-weighted norm
                     double f0[N];
                     mdl.rhs(y, f0);
-                    double d0 = 0.0, d1 = 0.0;
+                    float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        double sc = 1.0 / fma(a.rtol, fabs(y[i]), a.atol);
-                        d0 = fmax(d0, fabs(y[i]) * sc);
-                        d1 = fmax(d1, fabs(f0[i]) * sc);
+                        float sc = (float)fma(a.rtol, fabs(y[i]), a.atol);
+                        d0 = fmaxf(d0, __fdividef((float)fabs(y[i]), sc));
+                        d1 = fmaxf(d1, __fdividef((float)fabs(f0[i]), sc));
                     }
-                    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+                    double h0 = (d0 < 1e-5f || d1 < 1e-5f || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
                     ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
-                    kout = 0;                 // output index 0 (the initial state) is emitted below
                 } else {
                     exhausted = true;
                 }
             }
         }
         if (__all_sync(FULL, !active)) break;
-        if (!active) continue;
 
-        // ------------------------------------------------------------- one step attempt, or an
-        // emission without a step (initial state, repeated output time, NaN tail of a failed system)
-        bool do_emit = false;
-        const double tout = tgrid[kout];
-        const double rem = tout - t;
-        if (status != 0 || kout == 0 || !(rem > 0.0)) {
-            do_emit = true;
-        } else {
-            double hh = ctl.h;
-            bool land = false;
-            if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
-            else if (hh > 0.5 * rem) hh = 0.5 * rem;
+        // ------------------------------------------------------------------ one step attempt
+        bool finished = false;
+        if (active) {
+            if (kout < T) {
+                const double tout = tgrid[kout];
+                const double rem = tout - t;
+                bool store = false;
+                if (!(rem > 0.0)) {
+                    store = true;                                  // repeated output time
+                } else {
+                    double hh = ctl.h;
+                    bool land = false;
+                    if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
+                    else if (hh > 0.5 * rem) hh = 0.5 * rem;
 
-            double F[NF];
-            mdl.factor(hh * GAMMA, F);
-            double v[N], yn[N], er[N];
-            mdl.rhs(y, v);
+                    double F[NF];
+                    mdl.factor(hh * GAMMA, F);
+                    double v[N], yn[N], er[N];
+                    mdl.rhs(y, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i] *= hh;
-            mdl.solve(F, v);
+                    for (int i = 0; i < N; ++i) v[i] *= hh;
+                    mdl.solve(F, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
-            mdl.solve(F, v);
+                    for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
+                    mdl.solve(F, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
-            mdl.solve(F, v);
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
+                    mdl.solve(F, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
-            mdl.solve(F, v);
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
+                    mdl.solve(F, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
-            mdl.solve(F, v);
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
+                    mdl.solve(F, v);
 #pragma unroll
-            for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
-            mdl.solve(F, v);
-            float err = 0.0f;
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
+                    mdl.solve(F, v);
+                    float err = 0.0f;
+                    double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                yn[i] = fma(MU6, v[i], yn[i]);
-                er[i] = fma(EPS6, v[i], er[i]);
-                err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
+                    for (int i = 0; i < N; ++i) {
+                        yn[i] = fma(MU6, v[i], yn[i]);
+                        er[i] = fma(EPS6, v[i], er[i]);
+                        err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
+                        chk += yn[i];
+                    }
+                    if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
+                        status = 3;
+                    } else if (err <= 1.0f) {
+                        ++nst;
+                        const double hprop = ctl.h;
+                        const double hnew = ctl_accept(ctl, hh, err);
+                        ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) y[i] = yn[i];
+                        if (land) { t = tout; store = true; }
+                        else t += hh;
+                    } else {
+                        ++nrej;
+                        ctl.h = ctl_reject(ctl, hh, err);
+                        if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
+                    }
+                    if (status == 0 && !store && nst + nrej >= a.max_steps) status = 1;
+                }
+                if (store) {
+                    double* o = my_traj + kout * N;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) o[i] = y[i];
+                    ++kout;
+                }
             }
-            double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
-#pragma unroll
-            for (int i = 0; i < N; ++i) chk += yn[i];
+            finished = (kout >= T) || (status != 0);
+        }
 
-            if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
-                status = 3;
-            } else if (err <= 1.0f) {
-                ++nst;
-                const double hprop = ctl.h;
-                const double hnew = ctl_accept(ctl, hh, err);
-                ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
-#pragma unroll
-                for (int i = 0; i < N; ++i) y[i] = yn[i];
-                if (land) { t = tout; do_emit = true; }
-                else t += hh;
-            } else {
-                ++nrej;
-                ctl.h = ctl_reject(ctl, hh, err);
-                if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
+        // ------------------------------------------ warp-cooperative epilogue of finished systems
+        unsigned fin = __ballot_sync(FULL, finished);
+        while (fin) {
+            const int f = __ffs(fin) - 1;
+            fin &= fin - 1;
+            const size_t fsys = (size_t)__shfl_sync(FULL, sys, f);
+            const int fstatus = __shfl_sync(FULL, status, f);
+            const int fvalid = __shfl_sync(FULL, kout, f);          // outputs 0..fvalid-1 were produced
+            const int fnst = __shfl_sync(FULL, nst, f), fnrej = __shfl_sync(FULL, nrej, f);
+            __syncwarp();                                           // the owner's trajectory stores are visible
+            const double* tr = warp_traj + (size_t)f * TN;
+            const double* y0 = a.y0 + (a.y0_stride ? fsys * (size_t)a.y0_stride : 0);
+            const int g = (want_loss && a.group) ? a.group[fsys] : 0;
+            const double* tg = want_loss ? a.target + (size_t)g * a.L : nullptr;
+            const double* sg = (want_loss && a.sigma) ? a.sigma + (size_t)g * a.sigma_len : nullptr;
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            double ssr = 0.0, sr = 0.0, sr2 = 0.0, s1 = 0.0, s2 = 0.0, dyn = 0.0;
+            for (int idx = lane; idx < TN; idx += 32) {
+                const int k = idx / N, i = idx - k * N;
+                double v = (k < fvalid) ? fmax(tr[idx], 0.0) : qnan;            // np.clip(sol, 0, None)
+                const double nrm = a.normalize ? 1.0 / y0[i] : 1.0;             // NORMALIZE_MODEL_OUTPUT
+                v *= nrm;
+                if (a.out_sol) a.out_sol[fsys * TN + idx] = v;
+                const int fi = (i == 0) ? (k >= RNA_OFFSET ? k - RNA_OFFSET : -1)
+                                        : (i == 1 ? rna_len + k : rna_len + T + (i - 2) * T + k);
+                if (fi >= 0) {
+                    if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
+                    if (want_loss) {
+                        const double dlt = v - __ldg(tg + fi);
+                        const double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                        ssr = fma(w, w, ssr);
+                        sr += fabs(dlt);
+                        sr2 = fma(dlt, dlt, sr2);
+                    }
+                }
+                if (want_y) {
+                    s1 += v;
+                    s2 = fma(v, v, s2);
+                    if (a.y_metric == 3 && k > 0) {
+                        const double pv = (k - 1 < fvalid) ? fmax(tr[idx - N], 0.0) * nrm : qnan;
+                        dyn = fma(v - pv, v - pv, dyn);
+                    }
+                }
             }
-            if (status == 0 && !do_emit && nst + nrej >= a.max_steps) status = 1;
+            double p2 = 0.0;
+            if (want_loss) {
+                // |params|^2 for score_fit's l2 term and the lam/P*theta^2 rows of normest's model_func
+                const double* sgr = (sg && a.sigma_len > a.L) ? sg + a.L : nullptr;
+                for (int i = lane; i < P; i += 32) {
+                    const double th = a.params[fsys * P + i];
+                    const double ph = a.log_params ? exp(th) : th;
+                    p2 = fma(ph, ph, p2);
+                    if (a.lam != 0.0) {
+                        double w = a.lam / (double)P * th * th;
+                        if (sgr) w /= __ldg(sgr + i);
+                        ssr = fma(w, w, ssr);
+                    }
+                }
+                ssr = warp_sum_d(ssr); sr = warp_sum_d(sr); sr2 = warp_sum_d(sr2); p2 = warp_sum_d(p2);
+            }
+            if (want_y) { s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); dyn = warp_sum_d(dyn); }
+            if (lane == 0) {
+                if (a.out_status) a.out_status[fsys] = fstatus;
+                if (a.out_nsteps) a.out_nsteps[fsys] = fnst;
+                if (a.out_nrej) a.out_nrej[fsys] = fnrej;
+                if (a.out_ssr) a.out_ssr[fsys] = ssr;
+                if (a.out_score) {
+                    // score_fit (config/config.py:176-226) with r = |target - pred| / L
+                    const double invL = 1.0 / (double)a.L;
+                    const double r1 = sr * invL, r2 = sr2 * invL * invL;
+                    const double mean_r2 = r2 * invL, mae = r1 * invL;
+                    a.out_score[fsys] = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                                        a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
+                }
+                if (want_y) {
+                    const double len = (double)TN, mean = s1 / len;
+                    double yv;
+                    switch (a.y_metric) {
+                        case 0: yv = s1; break;
+                        case 1: yv = mean; break;
+                        case 2: yv = s2 / len - mean * mean; break;
+                        case 3: yv = dyn; break;
+                        default: yv = sqrt(s2); break;
+                    }
+                    a.out_Y[fsys] = yv;
+                }
+            }
         }
-        if (do_emit) {
-            emit(kout, status != 0);
-            if (++kout >= T) finish();
-        }
+        if (finished) active = false;
     }
 }
 

@@ -88,7 +88,7 @@ struct pk_handle_s {
     char name[128] = {0};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-    DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch;
+    DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
     unsigned long long* counter = nullptr;
     int last_launches = 0;
     float last_ms = 0.f;
@@ -206,8 +206,8 @@ template <class M> constexpr int tps_min_blocks() { return M::N <= 5 ? 4 : (M::N
 using pk::TPS_BLOCK;
 
 template <class M>
-cudaError_t launch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
-    size_t smem = (size_t)(a.T + (pk::TPS_COLD + M::N) * TPS_BLOCK) * sizeof(double);
+cudaError_t launch_tps(pk_handle_s* h, pk::LocalArgs a) {
+    size_t smem = (size_t)a.T * sizeof(double);
     auto kern = pk::local_tps_kernel<M, tps_min_blocks<M>()>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -221,6 +221,10 @@ cudaError_t launch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
     long long grid = (long long)h->sm_count * per_sm;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    // one [T][n] trajectory slot per resident lane (L2-resident, reused for every system of the lane)
+    e = h->traj.ensure((size_t)grid * TPS_BLOCK * a.T * M::N * sizeof(double));
+    if (e != cudaSuccess) return e;
+    a.traj = (double*)h->traj.p;
     kern<<<(unsigned)grid, TPS_BLOCK, smem, h->stream>>>(a);
     return cudaGetLastError();
 }
@@ -324,7 +328,7 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj};
     for (DevBuf* b : bufs) b->release();
     if (h->counter) cudaFree(h->counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
