@@ -43,6 +43,9 @@ enum pk_memspace { PK_HOST = 0, PK_DEVICE = 1 };
 /* sensitivity/analysis.py:114-176 */
 enum pk_y_metric { PK_Y_NONE = -1, PK_Y_TOTAL_SIGNAL = 0, PK_Y_MEAN_ACTIVITY = 1, PK_Y_VARIANCE = 2,
                    PK_Y_DYNAMICS = 3, PK_Y_L2_NORM = 4 };
+/* integrator coefficient set: ROS5L = 6-solve order-5(4) Rosenbrock for linear systems (default),
+ * RODAS4 = Hairer-Wanner order-4(3); see DESIGN.md section 2 */
+enum pk_method { PK_METHOD_DEFAULT = 0, PK_METHOD_RODAS4 = 1, PK_METHOD_ROS5L = 2 };
 enum pk_status { PK_OK = 0, PK_MAX_STEPS = 1, PK_STEP_UNDERFLOW = 2, PK_NON_FINITE = 3 };
 
 /* One batched call of solve_ode(params[b], init_cond, num_psites, t) for b in [0,B). */
@@ -56,11 +59,13 @@ typedef struct pk_local_job {
     const double* y0;       /* [n] if y0_stride==0 else [B,n] with row stride y0_stride doubles  */
     int64_t y0_stride;
     const double* t;        /* [T] strictly increasing                                           */
-    double rtol, atol;      /* <=0 -> defaults 1e-8 / 1e-11                                      */
+    double rtol, atol;      /* <=0 -> defaults 1e-7 / 1e-10                                      */
     int32_t max_steps;      /* per system, <=0 -> 100000                                         */
     int32_t normalize;      /* NORMALIZE_MODEL_OUTPUT (models/distmod.py:115-122)                */
     int32_t log_params;     /* 1: params hold log-values, model uses exp(params) (normest.py:54) */
     int32_t y_metric;       /* pk_y_metric, PK_Y_NONE to skip                                    */
+    int32_t method;         /* pk_method                                                         */
+    int32_t reserved0;
     /* outputs, each may be NULL */
     double* out_sol;        /* [B,T,n]  clipped at 0                                             */
     double* out_flat;       /* [B,L]    L = (T-5)+T+ns*T  (needs T>5)                            */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libphoskin_b200.so")
 PK_HOST, PK_DEVICE = 0, 1
 MODEL_IDS = {"distmod": 0, "succmod": 1, "randmod": 2}
 Y_METRIC_IDS = {"total_signal": 0, "mean_activity": 1, "variance": 2, "dynamics": 3, "l2_norm": 4}
+METHOD_IDS = {None: 0, "default": 0, "rodas4": 1, "ros5l": 2}
 STATUS_NAMES = {0: "ok", 1: "max_steps", 2: "step_underflow", 3: "non_finite"}
 
 c_double_p = C.POINTER(C.c_double)
@@ -28,7 +29,7 @@ class PkLocalJob(C.Structure):
         ("params", C.c_void_p), ("y0", C.c_void_p), ("y0_stride", C.c_int64), ("t", C.c_void_p),
         ("rtol", C.c_double), ("atol", C.c_double),
         ("max_steps", C.c_int32), ("normalize", C.c_int32), ("log_params", C.c_int32),
-        ("y_metric", C.c_int32),
+        ("y_metric", C.c_int32), ("method", C.c_int32), ("reserved0", C.c_int32),
         ("out_sol", C.c_void_p), ("out_flat", C.c_void_p), ("out_Y", C.c_void_p),
         ("out_ssr", C.c_void_p), ("out_score", C.c_void_p), ("out_status", C.c_void_p),
         ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p),

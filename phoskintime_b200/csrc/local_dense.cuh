@@ -185,7 +185,6 @@ __device__ __forceinline__ double warp_max(double v) {
 
 template <int MODEL>
 __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
-    using namespace rodas4;
     extern __shared__ double smem[];
     const int lane = threadIdx.x;
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             bool land = false;
             if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
             else if (hh > 0.5 * rem) hh = 0.5 * rem;
-            dense_fillW<MODEL>(ns, n, ld, p, hh * GAMMA, W, lane);
+            dense_fillW<MODEL>(ns, n, ld, p, hh * a.m.gamma, W, lane);
             dense_lu(n, ld, W, lane);
 
             // v_0 = h f(y); v_k = A^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
@@ -289,21 +288,21 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             for (int i = lane; i < n; i += 32) v[i] *= hh;
             __syncwarp();
             dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) w[i] = fma(MU1, v[i], y[i]);
+            for (int i = lane; i < n; i += 32) w[i] = fma(a.m.mu[0], v[i], y[i]);
             dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(MU2, v[i], w[i]); E[i] = EPS2 * v[i]; }
+            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[1], v[i], w[i]); E[i] = a.m.eps[1] * v[i]; }
             dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(MU3, v[i], w[i]); E[i] = fma(EPS3, v[i], E[i]); }
+            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[2], v[i], w[i]); E[i] = fma(a.m.eps[2], v[i], E[i]); }
             dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(MU4, v[i], w[i]); E[i] = fma(EPS4, v[i], E[i]); }
+            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[3], v[i], w[i]); E[i] = fma(a.m.eps[3], v[i], E[i]); }
             dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(MU5, v[i], w[i]); E[i] = fma(EPS5, v[i], E[i]); }
+            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[4], v[i], w[i]); E[i] = fma(a.m.eps[4], v[i], E[i]); }
             dense_solve(n, ld, W, v, lane);
             float err = 0.0f;
             bool bad = false;
             for (int i = lane; i < n; i += 32) {
-                const double yn = fma(MU6, v[i], w[i]);
-                const double ei = fma(EPS6, v[i], E[i]);
+                const double yn = fma(a.m.mu[5], v[i], w[i]);
+                const double ei = fma(a.m.eps[5], v[i], E[i]);
                 w[i] = yn;
                 const float q = err_ratio(ei, y[i], yn, a.rtol, a.atol);
                 bad |= !(q < 3.0e38f) || !(fabs(yn) < 1.0e300);
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             if (err <= 1.0f) {
                 ++nst;
                 const double hprop = ctl.h;
-                const double hnew = ctl_accept(ctl, hh, err);
+                const double hnew = ctl_accept(ctl, hh, err, a.m.expo);
                 ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
                 for (int i = lane; i < n; i += 32) y[i] = w[i];
                 __syncwarp();
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
                 else t += hh;
             } else {
                 ++nrej;
-                ctl.h = ctl_reject(ctl, hh, err);
+                ctl.h = ctl_reject(ctl, hh, err, a.m.expo);
                 if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
             }
             if (status == 0 && kout < T && nst + nrej >= a.max_steps) status = 1;

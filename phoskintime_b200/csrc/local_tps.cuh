@@ -175,7 +175,6 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 template <class M, int MIN_BLOCKS>
 __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
     constexpr int N = M::N, NF = M::NF, P = M::P;
-    using namespace rodas4;
     extern __shared__ double smem[];
     double* tgrid = smem;                                     // [T]
     for (int i = threadIdx.x; i < a.T; i += TPS_BLOCK) tgrid[i] = a.t[i];
@@ -262,33 +261,33 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     else if (hh > 0.5 * rem) hh = 0.5 * rem;
 
                     double F[NF];
-                    mdl.factor(hh * GAMMA, F);
+                    mdl.factor(hh * a.m.gamma, F);
                     double v[N], yn[N], er[N];
                     mdl.rhs(y, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) v[i] *= hh;
                     mdl.solve(F, v);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) yn[i] = fma(MU1, v[i], y[i]);
+                    for (int i = 0; i < N; ++i) yn[i] = fma(a.m.mu[0], v[i], y[i]);
                     mdl.solve(F, v);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU2, v[i], yn[i]); er[i] = EPS2 * v[i]; }
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[1], v[i], yn[i]); er[i] = a.m.eps[1] * v[i]; }
                     mdl.solve(F, v);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU3, v[i], yn[i]); er[i] = fma(EPS3, v[i], er[i]); }
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[2], v[i], yn[i]); er[i] = fma(a.m.eps[2], v[i], er[i]); }
                     mdl.solve(F, v);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU4, v[i], yn[i]); er[i] = fma(EPS4, v[i], er[i]); }
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[3], v[i], yn[i]); er[i] = fma(a.m.eps[3], v[i], er[i]); }
                     mdl.solve(F, v);
 #pragma unroll
-                    for (int i = 0; i < N; ++i) { yn[i] = fma(MU5, v[i], yn[i]); er[i] = fma(EPS5, v[i], er[i]); }
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[4], v[i], yn[i]); er[i] = fma(a.m.eps[4], v[i], er[i]); }
                     mdl.solve(F, v);
                     float err = 0.0f;
                     double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        yn[i] = fma(MU6, v[i], yn[i]);
-                        er[i] = fma(EPS6, v[i], er[i]);
+                        yn[i] = fma(a.m.mu[5], v[i], yn[i]);
+                        er[i] = fma(a.m.eps[5], v[i], er[i]);
                         err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
                         chk += yn[i];
                     }
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     } else if (err <= 1.0f) {
                         ++nst;
                         const double hprop = ctl.h;
-                        const double hnew = ctl_accept(ctl, hh, err);
+                        const double hnew = ctl_accept(ctl, hh, err, a.m.expo);
                         ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
 #pragma unroll
                         for (int i = 0; i < N; ++i) y[i] = yn[i];
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         else t += hh;
                     } else {
                         ++nrej;
-                        ctl.h = ctl_reject(ctl, hh, err);
+                        ctl.h = ctl_reject(ctl, hh, err, a.m.expo);
                         if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
                     }
                     if (status == 0 && !store && nst + nrej >= a.max_steps) status = 1;

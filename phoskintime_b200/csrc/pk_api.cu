@@ -415,8 +415,10 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     pk::LocalArgs a;
     memset(&a, 0, sizeof(a));
     a.B = j->B; a.T = j->T; a.ns = j->n_sites; a.n = n; a.P = P; a.L = L;
-    a.rtol = j->rtol > 0 ? j->rtol : 1e-8;
-    a.atol = j->atol > 0 ? j->atol : 1e-11;
+    a.rtol = j->rtol > 0 ? j->rtol : 1e-7;
+    a.atol = j->atol > 0 ? j->atol : 1e-10;
+    if (j->method < 0 || j->method > 2) return fail("unknown method");
+    a.m = (j->method == PK_METHOD_RODAS4) ? pk::METHOD_RODAS4 : pk::METHOD_ROS5L;
     a.max_steps = j->max_steps > 0 ? j->max_steps : 100000;
     a.normalize = j->normalize; a.log_params = j->log_params;
     a.y_metric = j->out_Y ? j->y_metric : -1;

@@ -12,10 +12,10 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError, PkLocalJob
+from ._lib import METHOD_IDS, MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError, PkLocalJob
 
-DEFAULT_RTOL = 1e-8
-DEFAULT_ATOL = 1e-11
+DEFAULT_RTOL = 1e-7
+DEFAULT_ATOL = 1e-10
 
 _engines = {}
 
@@ -81,7 +81,7 @@ class Engine:
     def solve_local_batch(self, model, params, init_cond, num_psites, t, want=("sol", "flat"), *,
                           target=None, sigma=None, group=None, lam=0.0, y_metric="total_signal",
                           rtol=None, atol=None, max_steps=0, normalize=False, log_params=False,
-                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True):
+                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True, method=None):
         """Solve B systems.  Returns a dict with the requested keys among
         sol[B,T,n], flat[B,L], Y[B], ssr[B], score[B] plus status/nsteps/nrej[B] (int32).
 
@@ -91,6 +91,7 @@ class Engine:
             [G,·]; group [B] int32 indices into G (None = all 0)
         out : optional dict of preallocated outputs (same kind as params) to fill
         counters : also return accepted/rejected step counts per system (nsteps, nrej)
+        method : None/'ros5l' (order 5(4), default) or 'rodas4' (order 4(3)) — DESIGN.md §2
         """
         want = tuple(want)
         unknown = set(want) - {"sol", "flat", "Y", "ssr", "score"}
@@ -126,6 +127,7 @@ class Engine:
         job.atol = DEFAULT_ATOL if atol is None else float(atol)
         job.max_steps, job.normalize, job.log_params = int(max_steps), int(bool(normalize)), int(bool(log_params))
         job.lam = float(lam)
+        job.method = METHOD_IDS[method]
         for i, w in enumerate(score_weights):
             job.score_w[i] = float(w)
 

@@ -201,6 +201,21 @@ def test_per_system_initial_conditions_normalize_and_log_params(engine):
         assert np.allclose(rl["sol"], r["sol"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("method,rtol,atol", [("rodas4", 1e-8, 1e-11), ("ros5l", 1e-7, 1e-10), ("ros5l", 1e-9, 1e-12)])
+def test_both_integrators_meet_the_parity_bound(engine, method, rtol, atol):
+    """RODAS4 (order 4(3)) and ROS5L (order 5(4), the default) against O2 on every golden case; the
+    tighter ROS5L run must also be closer to O2 than the default one (the error is tolerance driven)."""
+    worst = 0.0
+    for path in FILES:
+        model, ns, g = _case(path)
+        r = engine.solve_local_batch(model, g["params"], g["y0"], ns, g["t"], want=("sol",), method=method,
+                                     rtol=rtol, atol=atol)
+        assert (r["status"] == 0).all()
+        e = (np.abs(r["sol"] - g["sol_tight"]) / (1e-6 * np.abs(g["sol_tight"]) + 1e-9)).max()
+        worst = max(worst, float(e))
+    assert worst < (0.05 if rtol > 5e-9 else 0.005), worst
+
+
 def test_host_and_device_paths_agree_and_are_deterministic(engine):
     import torch
     rng = np.random.default_rng(5)
