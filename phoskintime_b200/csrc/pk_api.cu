@@ -86,7 +86,8 @@ struct pk_handle_s {
     int sm_count = 0;
     int clock_khz = 0;
     char name[128] = {0};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
     DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
     unsigned long long* counter = nullptr;
@@ -204,6 +205,8 @@ constexpr int TPS_MAX_NS_SUCC = 8;
 // n <= 5 states fit 128 registers (4 CTAs x 128 lanes), mid sizes get 168 (3 CTAs), the rest 255.
 template <class M> constexpr int tps_min_blocks() { return M::N <= 5 ? 4 : (M::N + M::NF <= 26 ? 3 : 2); }
 using pk::TPS_BLOCK;
+constexpr int PIPE_MAX_CHUNKS = 4;
+constexpr size_t PIPE_MIN_CHUNK = 100000;   // host-path batches >= 2x/4x this are pipelined in 2/4 chunks
 
 template <class M>
 cudaError_t launch_tps(pk_handle_s* h, pk::LocalArgs a) {
@@ -314,6 +317,12 @@ int pk_create(int device, pk_handle_t* out) {
     h->clock_khz = khz;
     snprintf(h->name, sizeof(h->name), "%.127s", prop.name);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) {
+        CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+    }
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->evr0));
@@ -335,6 +344,12 @@ int pk_destroy(pk_handle_t h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evr0) cudaEventDestroy(h->evr0);
     if (h->evr1) cudaEventDestroy(h->evr1);
+    for (int i = 0; i < 4; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -431,73 +446,122 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
 
     const size_t y0_elems = j->y0_stride ? (B - 1) * (size_t)j->y0_stride + n : (size_t)n;
     const size_t G = want_loss ? (size_t)j->n_groups : 0;
-    if (host) {
-#define STAGE_IN(buf, src, bytes, dstfield)                                                   \
-        do {                                                                                  \
-            CK(h->buf.ensure(bytes));                                                         \
-            CK(cudaMemcpyAsync(h->buf.p, src, bytes, cudaMemcpyHostToDevice, st));            \
-            dstfield = (decltype(dstfield))h->buf.p;                                          \
-        } while (0)
-        STAGE_IN(params, j->params, B * P * sizeof(double), a.params);
-        STAGE_IN(y0, j->y0, y0_elems * sizeof(double), a.y0);
-        STAGE_IN(t, j->t, (size_t)j->T * sizeof(double), a.t);
-        if (want_loss) {
-            STAGE_IN(target, j->target, G * L * sizeof(double), a.target);
-            if (j->sigma) STAGE_IN(sigma, j->sigma, G * (size_t)j->sigma_len * sizeof(double), a.sigma);
-            if (j->group) STAGE_IN(group, j->group, B * sizeof(int32_t), a.group);
-        }
-#undef STAGE_IN
-#define STAGE_OUT(buf, user, bytes, dstfield)                                                 \
-        do {                                                                                  \
-            if (user) { CK(h->buf.ensure(bytes)); dstfield = (decltype(dstfield))h->buf.p; }  \
-        } while (0)
-        STAGE_OUT(sol, j->out_sol, B * j->T * n * sizeof(double), a.out_sol);
-        STAGE_OUT(flat, j->out_flat, B * L * sizeof(double), a.out_flat);
-        STAGE_OUT(Y, j->out_Y, B * sizeof(double), a.out_Y);
-        STAGE_OUT(ssr, j->out_ssr, B * sizeof(double), a.out_ssr);
-        STAGE_OUT(score, j->out_score, B * sizeof(double), a.out_score);
-        STAGE_OUT(status, j->out_status, B * sizeof(int32_t), a.out_status);
-        STAGE_OUT(nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
-        STAGE_OUT(nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
-#undef STAGE_OUT
-    } else {
+    const size_t TN = (size_t)j->T * n;
+
+    auto launch = [&](const pk::LocalArgs& ac) -> cudaError_t {
+        const bool tps = (j->model == PK_DISTMOD && j->n_sites <= TPS_MAX_NS_DIST) ||
+                         (j->model == PK_SUCCMOD && j->n_sites <= TPS_MAX_NS_SUCC);
+        if (tps) return (j->model == PK_DISTMOD) ? dispatch_tps<pk::DistModel, TPS_MAX_NS_DIST>(h, ac)
+                                                  : dispatch_tps<pk::SuccModel, TPS_MAX_NS_SUCC>(h, ac);
+        if (j->model == PK_DISTMOD) return launch_dense<0>(h, ac);
+        if (j->model == PK_SUCCMOD) return launch_dense<1>(h, ac);
+        return launch_dense<2>(h, ac);
+    };
+
+    if (!host) {
         a.params = j->params; a.y0 = j->y0; a.t = j->t;
         a.target = j->target; a.sigma = j->sigma; a.group = j->group;
         a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
         a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
         a.out_nrej = j->out_nrej;
+        CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+        CK(cudaEventRecord(h->ev0, st));
+        cudaError_t e = launch(a);
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        CK(cudaEventRecord(h->ev1, st));
+        h->last_launches = 1;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+        return 0;
     }
 
-    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+    // ---- host memory: stage through device workspaces.  Large batches are pipelined in chunks:
+    // H2D of chunk c+1 (copy-in stream) overlaps the kernel of chunk c (compute stream), whose
+    // results leave on the copy-out stream while chunk c+1 computes.
+#define WS(buf, need, bytes, dstfield)                                                        \
+    do {                                                                                      \
+        if (need) { CK(h->buf.ensure(bytes)); dstfield = (decltype(dstfield))h->buf.p; }      \
+    } while (0)
+    WS(params, true, B * P * sizeof(double), a.params);
+    WS(y0, true, y0_elems * sizeof(double), a.y0);
+    WS(t, true, (size_t)j->T * sizeof(double), a.t);
+    WS(target, want_loss, G * L * sizeof(double), a.target);
+    WS(sigma, want_loss && j->sigma, G * (size_t)j->sigma_len * sizeof(double), a.sigma);
+    WS(group, want_loss && j->group, B * sizeof(int32_t), a.group);
+    WS(sol, j->out_sol, B * TN * sizeof(double), a.out_sol);
+    WS(flat, j->out_flat, B * L * sizeof(double), a.out_flat);
+    WS(Y, j->out_Y, B * sizeof(double), a.out_Y);
+    WS(ssr, j->out_ssr, B * sizeof(double), a.out_ssr);
+    WS(score, j->out_score, B * sizeof(double), a.out_score);
+    WS(status, j->out_status, B * sizeof(int32_t), a.out_status);
+    WS(nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
+    WS(nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
+#undef WS
+    const int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 4 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
+    cudaStream_t sin = h->s_in, sout = h->s_out;
+    // small shared inputs first, then the per-system inputs chunk by chunk on the copy-in stream
+    CK(cudaMemcpyAsync((void*)a.t, j->t, (size_t)j->T * sizeof(double), cudaMemcpyHostToDevice, sin));
+    if (!j->y0_stride) CK(cudaMemcpyAsync((void*)a.y0, j->y0, n * sizeof(double), cudaMemcpyHostToDevice, sin));
+    if (want_loss) {
+        CK(cudaMemcpyAsync((void*)a.target, j->target, G * L * sizeof(double), cudaMemcpyHostToDevice, sin));
+        if (j->sigma)
+            CK(cudaMemcpyAsync((void*)a.sigma, j->sigma, G * (size_t)j->sigma_len * sizeof(double),
+                               cudaMemcpyHostToDevice, sin));
+    }
+    size_t lo[PIPE_MAX_CHUNKS + 1];
+    for (int c = 0; c <= nchunks; ++c) lo[c] = B * (size_t)c / nchunks;
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t o = lo[c], cnt = lo[c + 1] - lo[c];
+        CK(cudaMemcpyAsync((double*)a.params + o * P, j->params + o * P, cnt * P * sizeof(double),
+                           cudaMemcpyHostToDevice, sin));
+        if (j->y0_stride)
+            CK(cudaMemcpyAsync((double*)a.y0 + o * j->y0_stride, j->y0 + o * j->y0_stride,
+                               ((cnt - 1) * (size_t)j->y0_stride + n) * sizeof(double), cudaMemcpyHostToDevice, sin));
+        if (a.group)
+            CK(cudaMemcpyAsync((int*)a.group + o, j->group + o, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, sin));
+        CK(cudaEventRecord(h->ev_in[c], sin));
+    }
     CK(cudaEventRecord(h->ev0, st));
-    cudaError_t e;
-    const bool tps = (j->model == PK_DISTMOD && j->n_sites <= TPS_MAX_NS_DIST) ||
-                     (j->model == PK_SUCCMOD && j->n_sites <= TPS_MAX_NS_SUCC);
-    if (tps) e = (j->model == PK_DISTMOD) ? dispatch_tps<pk::DistModel, TPS_MAX_NS_DIST>(h, a)
-                                            : dispatch_tps<pk::SuccModel, TPS_MAX_NS_SUCC>(h, a);
-    else if (j->model == PK_DISTMOD) e = launch_dense<0>(h, a);
-    else if (j->model == PK_SUCCMOD) e = launch_dense<1>(h, a);
-    else e = launch_dense<2>(h, a);
-    if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
-    CK(cudaEventRecord(h->ev1, st));
-    h->last_launches = 1;
-
-    if (host) {
-#define COPY_OUT(buf, user, bytes)                                                            \
+    for (int c = 0; c < nchunks; ++c) {
+        const size_t o = lo[c], cnt = lo[c + 1] - lo[c];
+        pk::LocalArgs ac = a;
+        ac.B = (long long)cnt;
+        ac.params += o * P;
+        if (j->y0_stride) ac.y0 += o * j->y0_stride;
+        if (ac.group) ac.group += o;
+        if (ac.out_sol) ac.out_sol += o * TN;
+        if (ac.out_flat) ac.out_flat += o * L;
+        if (ac.out_Y) ac.out_Y += o;
+        if (ac.out_ssr) ac.out_ssr += o;
+        if (ac.out_score) ac.out_score += o;
+        if (ac.out_status) ac.out_status += o;
+        if (ac.out_nsteps) ac.out_nsteps += o;
+        if (ac.out_nrej) ac.out_nrej += o;
+        CK(cudaStreamWaitEvent(st, h->ev_in[c], 0));
+        CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+        cudaError_t e = launch(ac);
+        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        CK(cudaEventRecord(h->ev_k[c], st));
+        h->last_launches++;
+        CK(cudaStreamWaitEvent(sout, h->ev_k[c], 0));
+#define COPY_OUT(field, user, per)                                                            \
         do {                                                                                  \
-            if (user) CK(cudaMemcpyAsync(user, h->buf.p, bytes, cudaMemcpyDeviceToHost, st)); \
+            if (user) CK(cudaMemcpyAsync(user + o * (per), ac.field, cnt * (per) * sizeof(*user), \
+                                         cudaMemcpyDeviceToHost, sout));                      \
         } while (0)
-        COPY_OUT(sol, j->out_sol, B * j->T * n * sizeof(double));
-        COPY_OUT(flat, j->out_flat, B * L * sizeof(double));
-        COPY_OUT(Y, j->out_Y, B * sizeof(double));
-        COPY_OUT(ssr, j->out_ssr, B * sizeof(double));
-        COPY_OUT(score, j->out_score, B * sizeof(double));
-        COPY_OUT(status, j->out_status, B * sizeof(int32_t));
-        COPY_OUT(nsteps, j->out_nsteps, B * sizeof(int32_t));
-        COPY_OUT(nrej, j->out_nrej, B * sizeof(int32_t));
+        COPY_OUT(out_sol, j->out_sol, TN);
+        COPY_OUT(out_flat, j->out_flat, (size_t)L);
+        COPY_OUT(out_Y, j->out_Y, (size_t)1);
+        COPY_OUT(out_ssr, j->out_ssr, (size_t)1);
+        COPY_OUT(out_score, j->out_score, (size_t)1);
+        COPY_OUT(out_status, j->out_status, (size_t)1);
+        COPY_OUT(out_nsteps, j->out_nsteps, (size_t)1);
+        COPY_OUT(out_nrej, j->out_nrej, (size_t)1);
 #undef COPY_OUT
     }
+    CK(cudaEventRecord(h->ev1, st));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(sout));
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }

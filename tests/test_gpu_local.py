@@ -234,6 +234,26 @@ def test_host_and_device_paths_agree_and_are_deterministic(engine):
     assert np.array_equal(c["flat"], a["flat"][perm]) and np.array_equal(c["score"], a["score"][perm])
 
 
+def test_pipelined_host_path_equals_device_path(engine):
+    """Host batches >= 400k systems are staged in 4 chunks (H2D / kernel / D2H overlapped on three
+    streams); every output slice, per-system y0 and the group index must land where the one-launch
+    device path puts them."""
+    import torch
+    B = 420_001
+    rng = np.random.default_rng(8)
+    p = rng.uniform(0.05, 3.0, (B, 10))
+    y0 = rng.uniform(0.1, 1.0, (B, 5))
+    tg = rng.random((3, 65))
+    grp = rng.integers(0, 3, B).astype(np.int32)
+    a = engine.solve_local_batch("distmod", p, y0, 3, T14, want=("flat", "ssr", "score", "Y"), target=tg, group=grp)
+    b = engine.solve_local_batch("distmod", torch.from_numpy(p).cuda(), torch.from_numpy(y0).cuda(), 3,
+                                 torch.from_numpy(T14).cuda(), want=("flat", "ssr", "score", "Y"),
+                                 target=torch.from_numpy(tg).cuda(), group=torch.from_numpy(grp).cuda())
+    for k in ("flat", "ssr", "score", "Y", "status", "nsteps", "nrej"):
+        assert np.array_equal(a[k], b[k].cpu().numpy()), k
+    assert engine.last_launch_info()[0] == 1
+
+
 def test_large_batch_properties(engine):
     """Size-independent checks at bench scale (2^18 systems): steady states stay put, the flow is
     a semigroup (solve to t1 then on to t2 == solve to t2), and the map is affine in (A, y0)."""
