@@ -1,0 +1,77 @@
+"""CPU: the global-network oracle (oracle/global_models.py) against golden vectors produced by the
+UNMODIFIED reference (oracle/gen_golden_global.py ran /root/reference's `System`, `simulate_odeint`
+with the finite-difference Jacobian, `rhs_odeint` bucket by bucket at 1e-12 and `LOSS_FN` in all 8
+loss modes).  This pins the checker of the global path before any GPU result is compared with it."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import global_models as og  # noqa: E402
+from phoskintime_b200.global_model import synthetic_system  # noqa: E402
+
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "global_*.npz")))
+IDS = [os.path.basename(f)[7:-4] for f in FILES]
+
+
+def load_case(path):
+    g = np.load(path)
+    s = synthetic_system(seed=int(g["seed"]), N=int(g["N"]), K=int(g["K"]), max_sites=int(g["max_sites"]),
+                         model=int(g["model"]))
+    ld = {k[3:]: g[k] for k in g.files if k.startswith("ld_")}
+    for k in ("prot_base_idx", "rna_base_idx", "pho_base_idx"):
+        ld[k] = int(ld[k])
+    return g, s, ld
+
+
+def test_goldens_present():
+    assert len(FILES) == 4
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_stock_simulation_matches_reference(path):
+    """Restated RHS + FD Jacobian + LSODA vs the reference's simulate_odeint (rtol=atol=1e-8).  The
+    reference kernels are numba fastmath, the restatement is IEEE-ordered: agreement is at rounding
+    level in the RHS, amplified through the 1e-8 finite-difference Jacobian into LSODA's step and order
+    selection — i.e. bounded by the solve's own tolerance (rtol=atol=1e-8), hence the bound below."""
+    g, s, _ = load_case(path)
+    net = s.as_dict()
+    for b in (0, 2):
+        Y = og.simulate_odeint(int(g["model"]), net, g["t"], 1e-8, 1e-8, 200000, params=og.unpack_params(g["params"][b], net))
+        assert Y.shape == g["Y"][b].shape
+        assert np.all(np.abs(Y - g["Y"][b]) <= 1e-6 * np.abs(g["Y"][b]) + 2e-8)
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_tight_simulation_matches_reference(path):
+    g, s, _ = load_case(path)
+    net = s.as_dict()
+    Y = og.simulate_exact_buckets(int(g["model"]), net, g["t"], params=og.unpack_params(g["params"][1], net))
+    ref = g["Y_tight"][1]
+    assert np.all(np.abs(Y - ref) <= 1e-9 * np.abs(ref) + 1e-11)
+
+
+@pytest.mark.parametrize("path", [f for f in FILES if "loss_mode0" in np.load(f).files],
+                         ids=[i for f, i in zip(FILES, IDS) if "loss_mode0" in np.load(f).files])
+def test_losses_match_reference(path):
+    g, s, ld = load_case(path)
+    for mode in (0, 1, 2, 3, 4, 5, 6, -1):
+        ref = g[f"loss_mode{mode}"]
+        for b in range(ref.shape[0]):
+            mine = np.array(og.loss_noncomb(g["Y"][b], ld, mode))
+            both_nan = np.isnan(mine) & np.isnan(ref[b])       # mode 2 is NaN by design
+            assert np.all(both_nan | (np.abs(mine - ref[b]) <= 1e-10 * np.abs(ref[b]) + 1e-12)), (mode, b)
+
+
+def test_pack_unpack_roundtrip():
+    g, s, _ = load_case(FILES[0])
+    net = s.as_dict()
+    v = g["params"][3]
+    assert np.array_equal(og.pack_params(og.unpack_params(v, net)), v)
+    assert np.array_equal(s.pack_params(s.unpack_params(v)), v)
+    assert s.n_params == v.size
