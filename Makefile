@@ -3,10 +3,11 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 CSRC := phoskintime_b200/csrc
 LIB  := phoskintime_b200/libphoskin_b200.so
-HDRS := $(wildcard $(CSRC)/*.cuh) include/phoskin_b200.h
+SRCS := $(CSRC)/pk_api.cu $(CSRC)/pk_global.cu
+HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/pk_internal.hpp include/phoskin_b200.h
 
-$(LIB): $(CSRC)/pk_api.cu $(HDRS)
-	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -Xptxas -v -shared -Xcompiler -fPIC -o $@ $< -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
+$(LIB): $(SRCS) $(HDRS)
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -Xptxas -v -shared -Xcompiler -fPIC -o $@ $(SRCS) -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -c "0 bytes spill stores" $(CSRC)/ptxas.log >/dev/null
 
 clean:

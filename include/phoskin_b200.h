@@ -129,6 +129,99 @@ int pk_nccl_unique_id(char* out128);
 int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank);
 int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Global coupled kinase-TF-protein network (reference: global_model/)
+ *
+ *   pk_global_upload        <- the static array part of System.odeint_args()  global_model/network.py:508-526
+ *                              (kin_grid, kin_Kmat, W/TF CSR, offsets, n_sites, tf_deg, driver_map), copied once
+ *   pk_global_set_loss_data <- the argument list of LOSS_FN minus Y  global_model/lossfn.py:113-121
+ *                              (tables built by global_model/cache.py:19-155)
+ *   pk_global_set_prior     <- defaults of GlobalODE_MOO (global_model/optproblem.py:105-114)
+ *   pk_global_solve_batch   <- a loop of simulate_odeint(sys, t_eval, rtol, atol, mxstep)
+ *                              (global_model/simulate.py:34-80) after System.update(**params)
+ *                              (network.py:293-302), optionally followed by LOSS_FN, the objectives of
+ *                              GlobalODE_MOO._evaluate (optproblem.py:87-160) and the Morris scalar of
+ *                              global_model/sensitivity.py:106-140 over simulate_and_measure's fold changes
+ *                              (simulate.py:105-182).
+ * Kinetic models: 0 distributive, 1 sequential, 4 saturating (global_model/models.py); the combinatorial
+ * model 2 is not supported (pk_global_upload returns an error).
+ * -----------------------------------------------------------------------------------------------*/
+typedef struct pk_global_topology {
+    int32_t model;               /* 0, 1 or 4                                                      */
+    int32_t N;                   /* proteins                                                        */
+    int32_t K;                   /* kinases                                                         */
+    int32_t n_bins;              /* kinase-grid points                                              */
+    const int32_t* n_sites;      /* [N]; block of protein i = [mRNA, P0, site_1..site_ns]           */
+    const int32_t* W_indptr;     /* CSR [total_sites, K]: site <- kinase weights                    */
+    const int32_t* W_indices;
+    const double* W_data;
+    const int32_t* TF_indptr;    /* CSR [N, N]: gene <- TF weights                                  */
+    const int32_t* TF_indices;
+    const double* TF_data;
+    const double* kin_grid;      /* [n_bins]                                                        */
+    const double* kin_Kmat;      /* [K, n_bins] row-major                                           */
+    const double* tf_deg;        /* [N]                                                             */
+    const int32_t* driver_map;   /* [N] kinase index driving protein i's TF activity, or -1         */
+} pk_global_topology;
+
+typedef struct pk_global_loss_data {
+    int32_t n_prot, n_rna, n_pho;
+    const int32_t *p_prot, *t_prot;           /* protein index, time index into t_eval              */
+    const double *obs_prot, *w_prot;
+    const int32_t *p_rna, *t_rna;
+    const double *obs_rna, *w_rna;
+    const int32_t *p_pho, *s_pho, *t_pho;     /* protein, site-within-protein, time index           */
+    const double *obs_pho, *w_pho;
+    int32_t prot_base_idx, rna_base_idx, pho_base_idx;   /* runner.py:545-547                       */
+} pk_global_loss_data;
+
+enum pk_global_metric { PK_GM_NONE = -1, PK_GM_TOTAL_SIGNAL = 0, PK_GM_MEAN = 1, PK_GM_VARIANCE = 2, PK_GM_L2_NORM = 3 };
+
+typedef struct pk_global_job {
+    int32_t topo;                /* id returned by pk_global_upload                                 */
+    int32_t memspace;            /* of params, y0, out_*; t_eval and mt_* are always HOST pointers  */
+    int64_t B;
+    int32_t T;
+    int32_t theta_mode;          /* 1: params hold raw theta, physical = softplus(theta) (params.py:106-132) */
+    const double* params;        /* [B,P], P = K+5N+total_sites+1: c_k|A_i|B_i|C_i|D_i|Dp_i|E_i|tf_scale */
+    const double* y0;            /* [state_dim] (y0_stride 0) or [B, y0_stride]                     */
+    int64_t y0_stride;
+    const double* t_eval;        /* [T] strictly increasing, HOST                                   */
+    double rtol, atol;           /* <=0 -> 1e-6 / 1e-9                                              */
+    int32_t max_steps;           /* per system, <=0 -> 200000                                       */
+    int32_t loss_mode;           /* LOSS_MODE 0..7 (lossfn.py:150-246)                              */
+    int32_t metric;              /* pk_global_metric                                                */
+    int32_t n_mt_prot, n_mt_rna, n_mt_pho;        /* metric time indices per modality               */
+    const int32_t *mt_prot, *mt_rna, *mt_pho;     /* HOST                                           */
+    int32_t mb_prot, mb_rna, mb_pho;              /* base time indices (t=0 / t=4 / t=0)            */
+    int32_t reserved0;
+    double lambdas[3];           /* protein, rna, phospho (optproblem.py:146-148)                   */
+    double lambda_prior;
+    double* out_Y;               /* [B,T,state_dim] or NULL                                         */
+    double* out_loss;            /* [B,3] raw weighted sums (needs pk_global_set_loss_data) or NULL */
+    double* out_F;               /* [B,3] objectives incl. prior penalty or NULL                    */
+    double* out_metric;          /* [B] or NULL                                                     */
+    int32_t* out_status;         /* [B] pk_status                                                   */
+    int32_t* out_nsteps;
+    int32_t* out_nrej;
+} pk_global_job;
+
+int pk_global_upload(pk_handle_t h, const pk_global_topology* topo, int32_t* topo_id);
+int pk_global_set_loss_data(pk_handle_t h, int32_t topo_id, const pk_global_loss_data* ld);
+int pk_global_set_prior(pk_handle_t h, int32_t topo_id, const double* defaults /* [P] physical, HOST */);
+int pk_global_release(pk_handle_t h, int32_t topo_id);
+/* state_dim, number of parameters P, size of the regulator set (dense Schur block), shared memory bytes per CTA */
+int pk_global_dims(pk_handle_t h, int32_t topo_id, int32_t* state_dim, int32_t* n_params, int32_t* n_reg,
+                   int32_t* smem_bytes);
+void pk_global_job_init(pk_global_job* job);
+int pk_sizeof_global_job(void);
+int pk_global_solve_batch(pk_handle_t h, const pk_global_job* job);
+/* LOSS_FN(Y, tables...) (global_model/lossfn.py:113-121, dispatch :386) on B trajectories that already
+ * exist: Y [B,T,state_dim] -> out_loss [B,3] = (loss_p, loss_r, loss_ph) raw weighted sums. */
+int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const double* Y, int64_t B, int32_t T,
+                         int32_t loss_mode, double* out_loss);
+
 #ifdef __cplusplus
 }
 #endif

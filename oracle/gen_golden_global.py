@@ -22,7 +22,8 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tests", "golden")
 T_EVAL = np.array([0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 15.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])
-CASES = [(0, 10, 5, 3, 11), (0, 36, 12, 4, 12), (1, 14, 6, 4, 13), (4, 14, 6, 3, 14)]   # model, N, K, max_sites, seed
+CASES = [(0, 10, 5, 3, 11), (0, 36, 12, 4, 12), (1, 14, 6, 4, 13), (4, 14, 6, 3, 14),   # model, N, K, max_sites, seed
+         (0, 120, 40, 4, 5, 2)]     # BASELINE configs[4] shape (state_dim ~ 500), 2 parameter vectors
 
 
 def stub_modules(model, loss_mode):
@@ -44,7 +45,7 @@ def stub_modules(model, loss_mode):
     sys.modules["global_model.config"] = gc
 
 
-def run_case(model, N, K, max_sites, seed):
+def run_case(model, N, K, max_sites, seed, B=4):
     from scipy import sparse
     from scipy.integrate import odeint
     from phoskintime_b200.global_model import synthetic_system, synthetic_loss_data
@@ -76,7 +77,6 @@ def run_case(model, N, K, max_sites, seed):
         assert np.array_equal(np.asarray(a), np.asarray(b)), "odeint_args wire format mismatch"
 
     rng = np.random.default_rng(seed + 100)
-    B = 4
     P = np.empty((B, s.n_params))
     Ys, Yt = [], []
     for b in range(B):
@@ -124,7 +124,7 @@ def run_losses(model, N, loss_mode):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "case":
-        run_case(*[int(x) for x in sys.argv[2:7]])
+        run_case(*[int(x) for x in sys.argv[2:8]])
     elif len(sys.argv) > 1 and sys.argv[1] == "loss":
         run_losses(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     else:

@@ -39,6 +39,51 @@ class PkLocalJob(C.Structure):
     ]
 
 
+class PkGlobalTopology(C.Structure):
+    """Mirror of `struct pk_global_topology` — the static arrays of System.odeint_args()
+    (reference global_model/network.py:508-526)."""
+    _fields_ = [
+        ("model", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("n_bins", C.c_int32),
+        ("n_sites", C.c_void_p),
+        ("W_indptr", C.c_void_p), ("W_indices", C.c_void_p), ("W_data", C.c_void_p),
+        ("TF_indptr", C.c_void_p), ("TF_indices", C.c_void_p), ("TF_data", C.c_void_p),
+        ("kin_grid", C.c_void_p), ("kin_Kmat", C.c_void_p), ("tf_deg", C.c_void_p),
+        ("driver_map", C.c_void_p),
+    ]
+
+
+class PkGlobalLossData(C.Structure):
+    """Mirror of `struct pk_global_loss_data` — LOSS_FN's argument list minus Y
+    (reference global_model/lossfn.py:113-121)."""
+    _fields_ = [
+        ("n_prot", C.c_int32), ("n_rna", C.c_int32), ("n_pho", C.c_int32),
+        ("p_prot", C.c_void_p), ("t_prot", C.c_void_p), ("obs_prot", C.c_void_p), ("w_prot", C.c_void_p),
+        ("p_rna", C.c_void_p), ("t_rna", C.c_void_p), ("obs_rna", C.c_void_p), ("w_rna", C.c_void_p),
+        ("p_pho", C.c_void_p), ("s_pho", C.c_void_p), ("t_pho", C.c_void_p), ("obs_pho", C.c_void_p),
+        ("w_pho", C.c_void_p),
+        ("prot_base_idx", C.c_int32), ("rna_base_idx", C.c_int32), ("pho_base_idx", C.c_int32),
+    ]
+
+
+class PkGlobalJob(C.Structure):
+    """Mirror of `struct pk_global_job`."""
+    _fields_ = [
+        ("topo", C.c_int32), ("memspace", C.c_int32), ("B", C.c_int64), ("T", C.c_int32),
+        ("theta_mode", C.c_int32),
+        ("params", C.c_void_p), ("y0", C.c_void_p), ("y0_stride", C.c_int64), ("t_eval", C.c_void_p),
+        ("rtol", C.c_double), ("atol", C.c_double),
+        ("max_steps", C.c_int32), ("loss_mode", C.c_int32), ("metric", C.c_int32),
+        ("n_mt_prot", C.c_int32), ("n_mt_rna", C.c_int32), ("n_mt_pho", C.c_int32),
+        ("mt_prot", C.c_void_p), ("mt_rna", C.c_void_p), ("mt_pho", C.c_void_p),
+        ("mb_prot", C.c_int32), ("mb_rna", C.c_int32), ("mb_pho", C.c_int32), ("reserved0", C.c_int32),
+        ("lambdas", C.c_double * 3), ("lambda_prior", C.c_double),
+        ("out_Y", C.c_void_p), ("out_loss", C.c_void_p), ("out_F", C.c_void_p), ("out_metric", C.c_void_p),
+        ("out_status", C.c_void_p), ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p),
+    ]
+
+
+GLOBAL_METRIC_IDS = {"total_signal": 0, "mean": 1, "variance": 2, "l2_norm": 3}
+
 # every symbol include/phoskin_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pk_abi_version": (C.c_int, []),
@@ -63,6 +108,17 @@ SYMBOLS = {
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pk_global_upload": (C.c_int, [C.c_void_p, C.POINTER(PkGlobalTopology), C.POINTER(C.c_int32)]),
+    "pk_global_set_loss_data": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PkGlobalLossData)]),
+    "pk_global_set_prior": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "pk_global_release": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pk_global_dims": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pk_global_job_init": (None, [C.POINTER(PkGlobalJob)]),
+    "pk_sizeof_global_job": (C.c_int, []),
+    "pk_global_solve_batch": (C.c_int, [C.c_void_p, C.POINTER(PkGlobalJob)]),
+    "pk_global_loss_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p]),
 }
 
 _lib = None
@@ -91,6 +147,8 @@ def load():
         raise PhoskinError("libphoskin_b200.so ABI version mismatch")
     if lib.pk_sizeof_local_job() != C.sizeof(PkLocalJob):
         raise PhoskinError("pk_local_job layout mismatch between header and ctypes mirror")
+    if lib.pk_sizeof_global_job() != C.sizeof(PkGlobalJob):
+        raise PhoskinError("pk_global_job layout mismatch between header and ctypes mirror")
     _lib = lib
     return lib
 

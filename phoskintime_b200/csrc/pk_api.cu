@@ -2,56 +2,22 @@
 // staging copies, kernel dispatch by (model, n_sites), Morris elementary-effects reduction,
 // FP64 peak probe and the NCCL all-gather (NCCL resolved with dlopen so that the library loads on
 // hosts without it and reuses the copy PyTorch already mapped).
-#include "../../include/phoskin_b200.h"
-
-#include <cuda_runtime.h>
-#include <dlfcn.h>
-
-#include <cstdio>
-#include <cstring>
-#include <string>
+#include "pk_internal.hpp"
 
 #include "local_dense.cuh"
 #include "local_tps.cuh"
 #include "pk_common.cuh"
 
+namespace pkh {
+thread_local std::string g_err;
+}
+using pkh::fail;
+using pkh::DevBuf;
+using pkh::ncclComm_t;
+
 namespace {
 
-thread_local std::string g_err;
-
-int fail(const std::string& m) {
-    g_err = m;
-    return -1;
-}
-#define CK(call)                                                                              \
-    do {                                                                                      \
-        cudaError_t e_ = (call);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
-    } while (0)
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
 // NCCL through dlopen
-typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 struct NcclApi {
     void* lib = nullptr;
@@ -80,22 +46,6 @@ NcclApi g_nccl;
 constexpr int NCCL_FLOAT64 = 8;   // ncclDouble
 
 }  // namespace
-
-struct pk_handle_s {
-    int device = 0;
-    int sm_count = 0;
-    int clock_khz = 0;
-    char name[128] = {0};
-    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-    DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
-    unsigned long long* counter = nullptr;
-    int last_launches = 0;
-    float last_ms = 0.f;
-    ncclComm_t comm = nullptr;
-    int world = 1, rank = 0;
-};
 
 // ---------------------------------------------------------------------------------- kernels
 namespace pk {
@@ -293,7 +243,7 @@ int dims(int model, int ns, int T, int* n, int* P, int* L) {
 extern "C" {
 
 int pk_abi_version(void) { return PK_ABI_VERSION; }
-const char* pk_last_error(void) { return g_err.c_str(); }
+const char* pk_last_error(void) { return pkh::g_err.c_str(); }
 
 int pk_device_count(int* out) {
     int n = 0;
@@ -339,6 +289,10 @@ int pk_destroy(pk_handle_t h) {
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
                       &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj};
     for (DevBuf* b : bufs) b->release();
+    DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
+                       &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj};
+    for (DevBuf* b : gbufs) b->release();
+    pkh::release_global_topologies(h);
     if (h->counter) cudaFree(h->counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -1,0 +1,486 @@
+// Host side of the global-network entry points of include/phoskin_b200.h: topology upload (the
+// static part of System.odeint_args(), global_model/network.py:508-526), loss tables
+// (global_model/lossfn.py:113-121), prior centre (optproblem.py:105-114) and the batched solve
+// that replaces a loop of simulate_odeint (global_model/simulate.py:34-80).
+#include <algorithm>
+#include <cmath>
+
+#include "pk_internal.hpp"
+
+#include "global_net.cuh"
+
+namespace pkh {
+
+struct GlobalTopoHost {
+    pk::GlobalTopoDev dev;
+    pk::GlobalSmem sm;
+    int P = 0;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 1;
+    std::vector<void*> allocs;        // topology arrays
+    std::vector<void*> loss_allocs;   // loss tables (replaced by pk_global_set_loss_data)
+    void* prior_alloc = nullptr;
+    std::vector<double> kin_grid;
+    bool has_loss = false;
+    int T_loss_max = -1;              // largest time index the loss tables reference
+
+    static void free_list(std::vector<void*>& v) {
+        for (void* p : v) cudaFree(p);
+        v.clear();
+    }
+    ~GlobalTopoHost() {
+        free_list(allocs);
+        free_list(loss_allocs);
+        if (prior_alloc) cudaFree(prior_alloc);
+    }
+};
+
+void release_global_topologies(pk_handle_s* h) {
+    for (GlobalTopoHost* t : h->topos) delete t;
+    h->topos.clear();
+}
+
+namespace {
+
+template <class T>
+cudaError_t upload(std::vector<void*>& owner, const T* src, size_t count, const T** dst) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    owner.push_back(p);
+    if (count) {
+        e = cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
+    *dst = (const T*)p;
+    return cudaSuccess;
+}
+
+GlobalTopoHost* topo_of(pk_handle_s* h, int id) {
+    if (!h || id < 0 || id >= (int)h->topos.size()) return nullptr;
+    return h->topos[id];
+}
+
+int bucket_of(double t, const std::vector<double>& g) {       // jacspeedup.py:148-172 / utils.py:210-225
+    if (t <= g.front()) return 0;
+    if (t >= g.back()) return (int)g.size() - 1;
+    int j = (int)(std::upper_bound(g.begin(), g.end(), t) - g.begin()) - 1;
+    return std::min(std::max(j, 0), (int)g.size() - 1);
+}
+
+void layout_smem(GlobalTopoHost* th) {
+    const pk::GlobalTopoDev& d = th->dev;
+    pk::GlobalSmem& L = th->sm;
+    int o = 0;
+    auto take = [&](int count) {
+        const int at = o;
+        o += (count + 1) & ~1;
+        return at;
+    };
+    const int n = d.n, N = d.N, nQ = d.nQ;
+    L.ld = nQ | 1;                                   // odd leading dimension: conflict-free column walks
+    L.par = take(th->P);
+    L.Kt = take(d.K);
+    L.Sall = take(d.S);
+    L.y = take(n);
+    L.arg = take(n);
+    L.U = take(6 * n);
+    L.w = take(n);
+    L.facA = take(n);
+    L.mult = take(n);
+    L.clo = take(n);
+    L.pvec = take(N);
+    L.g = take(N);
+    L.m = take(N);
+    L.z = take(N);
+    L.Sc = take(nQ * L.ld);
+    L.idiag = take(nQ);
+    L.red = take(2 * pk::GLOBAL_WARPS + nQ);
+    L.perm = take((nQ + 1) / 2 + 1);
+    L.total = o;
+    th->smem_bytes = (size_t)o * sizeof(double);
+}
+
+}  // namespace
+}  // namespace pkh
+
+using pkh::fail;
+using pkh::GlobalTopoHost;
+
+extern "C" {
+
+int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_id) {
+    if (!h || !tp || !topo_id) return fail("pk_global_upload: null argument");
+    if (tp->model != 0 && tp->model != 1 && tp->model != 4)
+        return fail("pk_global_upload: kinetic model must be 0 (distributive), 1 (sequential) or 4 (saturating); "
+                    "the combinatorial model 2 is not supported");
+    const int N = tp->N, K = tp->K, nb = tp->n_bins;
+    if (N < 1 || K < 1 || nb < 1) return fail("pk_global_upload: N, K and n_bins must be positive");
+    if (!tp->n_sites || !tp->W_indptr || !tp->TF_indptr || !tp->kin_grid || !tp->kin_Kmat || !tp->tf_deg ||
+        !tp->driver_map)
+        return fail("pk_global_upload: missing array");
+    std::vector<int> off_y(N), off_s(N);
+    int n = 0, S = 0;
+    for (int i = 0; i < N; ++i) {
+        if (tp->n_sites[i] < 0) return fail("pk_global_upload: negative n_sites");
+        off_y[i] = n;
+        off_s[i] = S;
+        n += 2 + tp->n_sites[i];
+        S += tp->n_sites[i];
+    }
+    if (tp->W_indptr[0] != 0 || tp->TF_indptr[0] != 0) return fail("pk_global_upload: indptr must start at 0");
+    for (int s = 0; s < S; ++s)
+        if (tp->W_indptr[s + 1] < tp->W_indptr[s]) return fail("pk_global_upload: W_indptr not monotone");
+    for (int i = 0; i < N; ++i)
+        if (tp->TF_indptr[i + 1] < tp->TF_indptr[i]) return fail("pk_global_upload: TF_indptr not monotone");
+    const int nnzW = tp->W_indptr[S], nnzT = tp->TF_indptr[N];
+    if ((nnzW && (!tp->W_indices || !tp->W_data)) || (nnzT && (!tp->TF_indices || !tp->TF_data)))
+        return fail("pk_global_upload: missing CSR indices/data");
+    for (int q = 0; q < nnzW; ++q)
+        if (tp->W_indices[q] < 0 || tp->W_indices[q] >= K) return fail("pk_global_upload: W column index out of range");
+    for (int q = 0; q < nnzT; ++q)
+        if (tp->TF_indices[q] < 0 || tp->TF_indices[q] >= N) return fail("pk_global_upload: TF column index out of range");
+    for (int i = 0; i < N; ++i) {
+        if (tp->driver_map[i] < -1 || tp->driver_map[i] >= K) return fail("pk_global_upload: driver_map out of range");
+        if (!(tp->tf_deg[i] != 0.0)) return fail("pk_global_upload: tf_deg must be non-zero");
+    }
+    for (int b = 1; b < nb; ++b)
+        if (!(tp->kin_grid[b] > tp->kin_grid[b - 1])) return fail("pk_global_upload: kin_grid must be strictly increasing");
+    CK(cudaSetDevice(h->device));
+
+    // regulator set Q: non-driven proteins whose total protein enters some gene's TF input
+    std::vector<int> qpos(N, -1), qlist;
+    {
+        std::vector<char> used(N, 0);
+        for (int q = 0; q < nnzT; ++q)
+            if (tp->TF_data[q] != 0.0) used[tp->TF_indices[q]] = 1;
+        for (int i = 0; i < N; ++i)
+            if (used[i] && tp->driver_map[i] < 0) {
+                qpos[i] = (int)qlist.size();
+                qlist.push_back(i);
+            }
+    }
+
+    GlobalTopoHost* th = new GlobalTopoHost();
+    memset(&th->dev, 0, sizeof(th->dev));
+    pk::GlobalTopoDev& d = th->dev;
+    d.model = tp->model; d.N = N; d.K = K; d.nb = nb; d.n = n; d.S = S; d.nQ = (int)qlist.size();
+    th->P = K + 5 * N + S + 1;
+    th->kin_grid.assign(tp->kin_grid, tp->kin_grid + nb);
+    cudaError_t e = cudaSuccess;
+#define UP(field, src, count)                                                     \
+    if (e == cudaSuccess) e = pkh::upload(th->allocs, src, (size_t)(count), &d.field)
+    UP(offset_y, off_y.data(), N);
+    UP(offset_s, off_s.data(), N);
+    UP(n_sites, tp->n_sites, N);
+    UP(W_indptr, tp->W_indptr, S + 1);
+    UP(W_indices, tp->W_indices, nnzW);
+    UP(W_data, tp->W_data, nnzW);
+    UP(TF_indptr, tp->TF_indptr, N + 1);
+    UP(TF_indices, tp->TF_indices, nnzT);
+    UP(TF_data, tp->TF_data, nnzT);
+    UP(kin_grid, tp->kin_grid, nb);
+    UP(kin_Kmat, tp->kin_Kmat, (size_t)K * nb);
+    UP(tf_deg, tp->tf_deg, N);
+    UP(driver_map, tp->driver_map, N);
+    UP(qlist, qlist.data(), qlist.size());
+    UP(qpos, qpos.data(), N);
+#undef UP
+    if (e != cudaSuccess) {
+        delete th;
+        return fail(std::string("pk_global_upload: ") + cudaGetErrorString(e));
+    }
+    pkh::layout_smem(th);
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (th->smem_bytes > (size_t)max_optin) {
+        const size_t need = th->smem_bytes;
+        delete th;
+        return fail("pk_global_upload: network needs " + std::to_string(need) + " B of shared memory per system, device offers " +
+                    std::to_string(max_optin));
+    }
+    h->topos.push_back(th);
+    *topo_id = (int32_t)h->topos.size() - 1;
+    return 0;
+}
+
+int pk_global_set_loss_data(pk_handle_t h, int32_t topo_id, const pk_global_loss_data* ld) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th || !ld) return fail("pk_global_set_loss_data: bad handle, topology id or table");
+    if (ld->n_prot < 0 || ld->n_rna < 0 || ld->n_pho < 0) return fail("pk_global_set_loss_data: negative count");
+    CK(cudaSetDevice(h->device));
+    pk::GlobalTopoDev& d = th->dev;
+    // validate indices on the host: the kernel trusts them
+    std::vector<int> ns(d.N);
+    CK(cudaMemcpy(ns.data(), d.n_sites, d.N * sizeof(int), cudaMemcpyDeviceToHost));
+    int tmax = std::max(std::max(ld->prot_base_idx, ld->rna_base_idx), ld->pho_base_idx);
+    if (ld->prot_base_idx < 0 || ld->rna_base_idx < 0 || ld->pho_base_idx < 0)
+        return fail("pk_global_set_loss_data: negative base index");
+    for (int k = 0; k < ld->n_prot; ++k) {
+        if (ld->p_prot[k] < 0 || ld->p_prot[k] >= d.N || ld->t_prot[k] < 0) return fail("pk_global_set_loss_data: protein row out of range");
+        tmax = std::max(tmax, ld->t_prot[k]);
+    }
+    for (int k = 0; k < ld->n_rna; ++k) {
+        if (ld->p_rna[k] < 0 || ld->p_rna[k] >= d.N || ld->t_rna[k] < 0) return fail("pk_global_set_loss_data: rna row out of range");
+        tmax = std::max(tmax, ld->t_rna[k]);
+    }
+    for (int k = 0; k < ld->n_pho; ++k) {
+        if (ld->p_pho[k] < 0 || ld->p_pho[k] >= d.N || ld->t_pho[k] < 0 || ld->s_pho[k] < 0 ||
+            ld->s_pho[k] >= ns[ld->p_pho[k]])
+            return fail("pk_global_set_loss_data: phospho row out of range");
+        tmax = std::max(tmax, ld->t_pho[k]);
+    }
+    GlobalTopoHost::free_list(th->loss_allocs);
+    th->has_loss = false;
+    cudaError_t e = cudaSuccess;
+#define UP(field, count)                                                          \
+    if (e == cudaSuccess) e = pkh::upload(th->loss_allocs, ld->field, (size_t)(count), &d.field)
+    UP(p_prot, ld->n_prot); UP(t_prot, ld->n_prot); UP(obs_prot, ld->n_prot); UP(w_prot, ld->n_prot);
+    UP(p_rna, ld->n_rna); UP(t_rna, ld->n_rna); UP(obs_rna, ld->n_rna); UP(w_rna, ld->n_rna);
+    UP(p_pho, ld->n_pho); UP(s_pho, ld->n_pho); UP(t_pho, ld->n_pho); UP(obs_pho, ld->n_pho); UP(w_pho, ld->n_pho);
+#undef UP
+    if (e != cudaSuccess) return fail(std::string("pk_global_set_loss_data: ") + cudaGetErrorString(e));
+    d.n_prot = ld->n_prot; d.n_rna = ld->n_rna; d.n_pho = ld->n_pho;
+    d.prot_base = ld->prot_base_idx; d.rna_base = ld->rna_base_idx; d.pho_base = ld->pho_base_idx;
+    // optproblem.py:83-85: each modality's weighted sum is divided by max(1e-6, sum of its weights)
+    const double* ws[3] = {ld->w_prot, ld->w_rna, ld->w_pho};
+    const int cnt[3] = {ld->n_prot, ld->n_rna, ld->n_pho};
+    for (int m = 0; m < 3; ++m) {
+        double s = 0.0;
+        for (int k = 0; k < cnt[m]; ++k) s += ws[m][k];
+        d.norm[m] = 1.0 / std::max(1e-6, s);
+    }
+    th->T_loss_max = tmax;
+    th->has_loss = true;
+    return 0;
+}
+
+int pk_global_set_prior(pk_handle_t h, int32_t topo_id, const double* defaults) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_set_prior: bad handle or topology id");
+    CK(cudaSetDevice(h->device));
+    if (th->prior_alloc) { cudaFree(th->prior_alloc); th->prior_alloc = nullptr; }
+    th->dev.defaults = nullptr;
+    if (!defaults) return 0;
+    CK(cudaMalloc(&th->prior_alloc, th->P * sizeof(double)));
+    CK(cudaMemcpy(th->prior_alloc, defaults, th->P * sizeof(double), cudaMemcpyHostToDevice));
+    th->dev.defaults = (const double*)th->prior_alloc;
+    return 0;
+}
+
+int pk_global_release(pk_handle_t h, int32_t topo_id) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_release: bad handle or topology id");
+    cudaSetDevice(h->device);
+    delete th;
+    h->topos[topo_id] = nullptr;      // ids of the other topologies stay valid
+    return 0;
+}
+
+int pk_global_dims(pk_handle_t h, int32_t topo_id, int32_t* state_dim, int32_t* n_params, int32_t* n_reg,
+                   int32_t* smem_bytes) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_dims: bad handle or topology id");
+    if (state_dim) *state_dim = th->dev.n;
+    if (n_params) *n_params = th->P;
+    if (n_reg) *n_reg = th->dev.nQ;
+    if (smem_bytes) *smem_bytes = (int32_t)th->smem_bytes;
+    return 0;
+}
+
+void pk_global_job_init(pk_global_job* job) {
+    memset(job, 0, sizeof(*job));
+    job->metric = PK_GM_NONE;
+    for (int i = 0; i < 3; ++i) job->lambdas[i] = 1.0;
+    job->lambda_prior = 0.0;
+}
+
+int pk_sizeof_global_job(void) { return (int)sizeof(pk_global_job); }
+
+int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
+    if (!h || !j) return fail("null handle or job");
+    GlobalTopoHost* th = pkh::topo_of(h, j->topo);
+    if (!th) return fail("pk_global_solve_batch: unknown topology id");
+    if (j->B < 0) return fail("B < 0");
+    if (j->T < 1) return fail("T < 1");
+    if (!j->params || !j->y0 || !j->t_eval) return fail("params, y0 and t_eval are required");
+    for (int k = 1; k < j->T; ++k)
+        if (!(j->t_eval[k] > j->t_eval[k - 1])) return fail("t_eval must be strictly increasing");
+    const bool want_loss = j->out_loss || j->out_F;
+    if (want_loss && !th->has_loss) return fail("out_loss/out_F need pk_global_set_loss_data");
+    if (want_loss && th->T_loss_max >= j->T) return fail("loss tables reference a time index >= T");
+    if (want_loss && (j->loss_mode < -1 || j->loss_mode > 7)) return fail("loss_mode out of range");
+    if (j->out_metric) {
+        if (j->metric < 0 || j->metric > 3) return fail("out_metric needs a valid metric id");
+        if (j->n_mt_prot < 0 || j->n_mt_rna < 0 || j->n_mt_pho < 0) return fail("negative metric time count");
+        const int32_t* lists[3] = {j->mt_prot, j->mt_rna, j->mt_pho};
+        const int cnt[3] = {j->n_mt_prot, j->n_mt_rna, j->n_mt_pho};
+        const int base[3] = {j->mb_prot, j->mb_rna, j->mb_pho};
+        for (int m = 0; m < 3; ++m) {
+            if (cnt[m] && !lists[m]) return fail("metric time list missing");
+            if (cnt[m] && (base[m] < 0 || base[m] >= j->T)) return fail("metric base index out of range");
+            for (int k = 0; k < cnt[m]; ++k)
+                if (lists[m][k] < 0 || lists[m][k] >= j->T) return fail("metric time index out of range");
+        }
+    }
+    h->last_launches = 0;
+    h->last_ms = 0.f;
+    if (j->B == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const pk::GlobalTopoDev& d = th->dev;
+    const size_t B = (size_t)j->B;
+    const int n = d.n, T = j->T, P = th->P;
+    const bool host = j->memspace == PK_HOST;
+    cudaStream_t st = h->stream;
+
+    // stop list: outputs plus the interior kinase-grid points (the RHS jumps there)
+    std::vector<double> stops(j->t_eval, j->t_eval + T);
+    for (double g : th->kin_grid)
+        if (g > j->t_eval[0] && g < j->t_eval[T - 1]) stops.push_back(g);
+    std::sort(stops.begin(), stops.end());
+    stops.erase(std::unique(stops.begin(), stops.end()), stops.end());
+    const int ns = (int)stops.size();
+    std::vector<int> s_out(ns, -1), s_bucket(ns, 0);
+    for (int k = 0, o = 0; k < ns; ++k) {
+        if (o < T && stops[k] == j->t_eval[o]) s_out[k] = o++;
+        s_bucket[k] = pkh::bucket_of(k + 1 < ns ? 0.5 * (stops[k] + stops[k + 1]) : stops[k], th->kin_grid);
+    }
+    const int n_mt = j->out_metric ? j->n_mt_prot + j->n_mt_rna + j->n_mt_pho : 0;
+    const size_t stop_bytes = (size_t)ns * sizeof(double) + (size_t)(2 * ns + n_mt) * sizeof(int);
+    CK(h->g_stops.ensure(stop_bytes));
+    {
+        std::vector<char> blob(stop_bytes);
+        memcpy(blob.data(), stops.data(), ns * sizeof(double));
+        int* ip = (int*)(blob.data() + (size_t)ns * sizeof(double));
+        memcpy(ip, s_out.data(), ns * sizeof(int));
+        memcpy(ip + ns, s_bucket.data(), ns * sizeof(int));
+        if (n_mt) {
+            int* mp = ip + 2 * ns;
+            if (j->n_mt_prot) memcpy(mp, j->mt_prot, j->n_mt_prot * sizeof(int));
+            if (j->n_mt_rna) memcpy(mp + j->n_mt_prot, j->mt_rna, j->n_mt_rna * sizeof(int));
+            if (j->n_mt_pho) memcpy(mp + j->n_mt_prot + j->n_mt_rna, j->mt_pho, j->n_mt_pho * sizeof(int));
+        }
+        // synchronous copy from a pageable temporary: the blob dies at the end of this scope
+        CK(cudaMemcpy(h->g_stops.p, blob.data(), stop_bytes, cudaMemcpyHostToDevice));
+    }
+
+    pk::GlobalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tp = d;
+    a.sm = th->sm;
+    a.B = j->B; a.T = T; a.P = P; a.theta_mode = j->theta_mode; a.n_stops = ns;
+    a.stop_t = (const double*)h->g_stops.p;
+    a.stop_out = (const int*)((const char*)h->g_stops.p + (size_t)ns * sizeof(double));
+    a.stop_bucket = a.stop_out + ns;
+    a.mt_prot = a.stop_bucket + ns;
+    a.mt_rna = a.mt_prot + j->n_mt_prot;
+    a.mt_pho = a.mt_rna + j->n_mt_rna;
+    a.n_mt_prot = j->n_mt_prot; a.n_mt_rna = j->n_mt_rna; a.n_mt_pho = j->n_mt_pho;
+    a.mb_prot = j->mb_prot; a.mb_rna = j->mb_rna; a.mb_pho = j->mb_pho;
+    a.rtol = j->rtol > 0 ? j->rtol : 1e-6;
+    a.atol = j->atol > 0 ? j->atol : 1e-9;
+    a.max_steps = j->max_steps > 0 ? j->max_steps : 200000;
+    a.loss_mode = j->loss_mode < 0 ? 7 : j->loss_mode;
+    a.metric = j->metric;
+    for (int m = 0; m < 3; ++m) a.lam[m] = j->lambdas[m];
+    a.lam_prior = j->lambda_prior;
+    a.y0_stride = j->y0_stride;
+    a.counter = h->counter;
+
+    CK(cudaFuncSetAttribute(pk::global_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th->smem_bytes));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk::global_net_kernel, pk::GLOBAL_BLOCK, th->smem_bytes));
+    if (per_sm < 1) return fail("pk_global_solve_batch: kernel does not fit on an SM");
+    const int grid = (int)std::min<size_t>(B, (size_t)per_sm * h->sm_count);
+
+    const size_t y0_elems = j->y0_stride ? (B - 1) * (size_t)j->y0_stride + n : (size_t)n;
+    const size_t TN = (size_t)T * n;
+    if (!host) {
+        a.params = j->params; a.y0 = j->y0;
+        a.out_Y = j->out_Y; a.out_loss = j->out_loss; a.out_F = j->out_F; a.out_metric = j->out_metric;
+        a.out_status = j->out_status; a.out_nsteps = j->out_nsteps; a.out_nrej = j->out_nrej;
+    } else {
+#define WS(buf, need, bytes, dstfield)                                                        \
+    do {                                                                                      \
+        if (need) { CK(h->buf.ensure(bytes)); dstfield = (decltype(dstfield))h->buf.p; }      \
+    } while (0)
+        WS(g_params, true, B * P * sizeof(double), a.params);
+        WS(g_y0, true, y0_elems * sizeof(double), a.y0);
+        WS(g_Y, j->out_Y, B * TN * sizeof(double), a.out_Y);
+        WS(g_loss, j->out_loss, B * 3 * sizeof(double), a.out_loss);
+        WS(g_F, j->out_F, B * 3 * sizeof(double), a.out_F);
+        WS(g_metric, j->out_metric, B * sizeof(double), a.out_metric);
+        WS(g_status, j->out_status, B * sizeof(int32_t), a.out_status);
+        WS(g_nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
+        WS(g_nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
+#undef WS
+        CK(cudaMemcpyAsync((void*)a.params, j->params, B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync((void*)a.y0, j->y0, y0_elems * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (!a.out_Y) {                                   // per-CTA trajectory slot (reused for every system of that CTA)
+        CK(h->g_traj.ensure((size_t)grid * TN * sizeof(double)));
+        a.traj = (double*)h->g_traj.p;
+    }
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+    CK(cudaEventRecord(h->ev0, st));
+    pk::global_net_kernel<<<grid, pk::GLOBAL_BLOCK, th->smem_bytes, st>>>(a);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(std::string("global_net_kernel launch: ") + cudaGetErrorString(le));
+    CK(cudaEventRecord(h->ev1, st));
+    h->last_launches = 1;
+    if (host) {
+#define BACK(dst, src, bytes)                                                                 \
+    do {                                                                                      \
+        if (dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));            \
+    } while (0)
+        BACK(j->out_Y, a.out_Y, B * TN * sizeof(double));
+        BACK(j->out_loss, a.out_loss, B * 3 * sizeof(double));
+        BACK(j->out_F, a.out_F, B * 3 * sizeof(double));
+        BACK(j->out_metric, a.out_metric, B * sizeof(double));
+        BACK(j->out_status, a.out_status, B * sizeof(int32_t));
+        BACK(j->out_nsteps, a.out_nsteps, B * sizeof(int32_t));
+        BACK(j->out_nrej, a.out_nrej, B * sizeof(int32_t));
+#undef BACK
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const double* Y, int64_t B, int32_t T,
+                         int32_t loss_mode, double* out_loss) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_loss_batch: bad handle or topology id");
+    if (!th->has_loss) return fail("pk_global_loss_batch needs pk_global_set_loss_data");
+    if (B < 0 || T < 1 || !Y || !out_loss) return fail("pk_global_loss_batch: bad arguments");
+    if (th->T_loss_max >= T) return fail("loss tables reference a time index >= T");
+    if (loss_mode < -1 || loss_mode > 7) return fail("loss_mode out of range");
+    h->last_launches = 0;
+    h->last_ms = 0.f;
+    if (B == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t ybytes = (size_t)B * T * th->dev.n * sizeof(double), lbytes = (size_t)B * 3 * sizeof(double);
+    const double* dY = Y;
+    double* dL = out_loss;
+    if (memspace == PK_HOST) {
+        CK(h->g_Y.ensure(ybytes));
+        CK(h->g_loss.ensure(lbytes));
+        dY = (const double*)h->g_Y.p;
+        dL = (double*)h->g_loss.p;
+        CK(cudaMemcpyAsync(h->g_Y.p, Y, ybytes, cudaMemcpyHostToDevice, st));
+    }
+    const int grid = (int)std::min<int64_t>(B, (int64_t)h->sm_count * 8);
+    CK(cudaEventRecord(h->ev0, st));
+    pk::global_loss_kernel<<<grid, pk::GLOBAL_BLOCK, 0, st>>>(th->dev, dY, B, T, loss_mode < 0 ? 7 : loss_mode, dL);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(std::string("global_loss_kernel launch: ") + cudaGetErrorString(le));
+    CK(cudaEventRecord(h->ev1, st));
+    h->last_launches = 1;
+    if (memspace == PK_HOST) CK(cudaMemcpyAsync(out_loss, dL, lbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Host-side internals shared by the translation units of libphoskin_b200.so: error string,
+// device workspace buffers, the NCCL entry points (resolved with dlopen) and the handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/phoskin_b200.h"
+
+namespace pkh {
+
+extern thread_local std::string g_err;
+
+inline int fail(const std::string& m) {
+    g_err = m;
+    return -1;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return pkh::fail(std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+typedef struct ncclComm* ncclComm_t;
+
+struct GlobalTopoHost;   // pk_global.cu
+
+}  // namespace pkh
+
+struct pk_handle_s {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+    pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
+    pkh::DevBuf g_params, g_y0, g_t, g_stops, g_Y, g_loss, g_F, g_metric, g_status, g_nsteps, g_nrej, g_traj;
+    unsigned long long* counter = nullptr;
+    int last_launches = 0;
+    float last_ms = 0.f;
+    pkh::ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    std::vector<pkh::GlobalTopoHost*> topos;   // uploaded global networks (index = topology id)
+};
+
+namespace pkh {
+void release_global_topologies(pk_handle_s* h);   // pk_global.cu
+}

@@ -12,7 +12,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import METHOD_IDS, MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError, PkLocalJob
+from ._lib import (GLOBAL_METRIC_IDS, METHOD_IDS, MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError,
+                   PkGlobalJob, PkGlobalLossData, PkGlobalTopology, PkLocalJob)
 
 DEFAULT_RTOL = 1e-7
 DEFAULT_ATOL = 1e-10
@@ -214,6 +215,158 @@ class Engine:
         if want_ee:
             res["ee"] = ee
         return res
+
+    # --------------------------------------------------------------------- global network
+    def global_upload(self, sys_):
+        """Upload the static topology of a `GlobalSystem` (the array part of the reference's
+        System.odeint_args(), global_model/network.py:508-526) once; returns the topology id."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        arrs = {"n_sites": i32(sys_.idx.n_sites), "W_indptr": i32(sys_.W_indptr), "W_indices": i32(sys_.W_indices),
+                "W_data": f64(sys_.W_data), "TF_indptr": i32(sys_.TF_indptr), "TF_indices": i32(sys_.TF_indices),
+                "TF_data": f64(sys_.TF_data), "kin_grid": f64(sys_.kin_grid), "kin_Kmat": f64(sys_.kin_Kmat),
+                "tf_deg": f64(sys_.tf_deg), "driver_map": i32(sys_.driver_map)}
+        tp = PkGlobalTopology()
+        tp.model, tp.N, tp.K, tp.n_bins = int(sys_.model), int(sys_.idx.N), int(sys_.K), int(arrs["kin_grid"].size)
+        for k, a in arrs.items():
+            setattr(tp, k, a.ctypes.data)
+        tid = C.c_int32(-1)
+        _lib.check(self.lib.pk_global_upload(self._h, C.byref(tp), C.byref(tid)))
+        return tid.value
+
+    def global_dims(self, topo):
+        v = [C.c_int32() for _ in range(4)]
+        _lib.check(self.lib.pk_global_dims(self._h, int(topo), *[C.byref(x) for x in v]))
+        return {"state_dim": v[0].value, "n_params": v[1].value, "n_reg": v[2].value, "smem_bytes": v[3].value}
+
+    def global_set_loss_data(self, topo, ld):
+        """Install the observation tables of LOSS_FN (global_model/lossfn.py:113-121; built by
+        global_model/cache.py:19-155) for a topology.  `prot_map` is implied by the topology."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        t = PkGlobalLossData()
+        keep = []
+        for k in ("p_prot", "t_prot", "p_rna", "t_rna", "p_pho", "s_pho", "t_pho"):
+            a = i32(ld[k]); keep.append(a); setattr(t, k, a.ctypes.data)
+        for k in ("obs_prot", "w_prot", "obs_rna", "w_rna", "obs_pho", "w_pho"):
+            a = f64(ld[k]); keep.append(a); setattr(t, k, a.ctypes.data)
+        t.n_prot, t.n_rna, t.n_pho = len(ld["p_prot"]), len(ld["p_rna"]), len(ld["p_pho"])
+        if not (len(ld["t_prot"]) == len(ld["obs_prot"]) == len(ld["w_prot"]) == t.n_prot and
+                len(ld["t_rna"]) == len(ld["obs_rna"]) == len(ld["w_rna"]) == t.n_rna and
+                len(ld["s_pho"]) == len(ld["t_pho"]) == len(ld["obs_pho"]) == len(ld["w_pho"]) == t.n_pho):
+            raise ValueError("loss tables of one modality must have equal lengths")
+        t.prot_base_idx, t.rna_base_idx, t.pho_base_idx = (int(ld["prot_base_idx"]), int(ld["rna_base_idx"]),
+                                                           int(ld["pho_base_idx"]))
+        _lib.check(self.lib.pk_global_set_loss_data(self._h, int(topo), C.byref(t)))
+
+    def global_set_prior(self, topo, defaults_vec):
+        a = None if defaults_vec is None else np.ascontiguousarray(defaults_vec, dtype=np.float64)
+        _lib.check(self.lib.pk_global_set_prior(self._h, int(topo), None if a is None else a.ctypes.data))
+
+    def global_release(self, topo):
+        _lib.check(self.lib.pk_global_release(self._h, int(topo)))
+
+    def global_solve_batch(self, topo, params, y0, t_eval, want=("Y",), *, rtol=None, atol=None, max_steps=0,
+                           theta_mode=False, loss_mode=0, metric="total_signal", metric_times=None,
+                           lambdas=(1.0, 1.0, 1.0), lambda_prior=0.0, out=None):
+        """Integrate B parameter vectors of one uploaded network.  Returns a dict with the requested
+        keys among Y[B,T,state_dim], loss[B,3], F[B,3], metric[B] plus status/nsteps/nrej[B].
+
+        params : [B,P] physical values (or raw theta with theta_mode=True: softplus is applied on the
+                 device, global_model/params.py:106-132), order c_k|A|B|C|D|Dp|E|tf_scale
+        metric_times : dict(t_prot, t_rna, t_pho index lists, prot_b, rna_b, pho_b) — which rows of
+                 t_eval simulate_and_measure tabulates (global_model/simulate.py:105-182)
+        """
+        want = tuple(want)
+        unknown = set(want) - {"Y", "loss", "F", "metric"}
+        if unknown:
+            raise ValueError(f"unknown outputs {sorted(unknown)}")
+        dev = _is_torch(params)
+        xp = _TorchOps(params.device) if dev else _NumpyOps()
+        params = xp.f64(params)
+        if params.ndim == 1:
+            params = params.reshape(1, -1)
+        B = int(params.shape[0])
+        dims = self.global_dims(topo)
+        n, P = dims["state_dim"], dims["n_params"]
+        if params.shape[1] != P:
+            raise ValueError(f"this network takes {P} parameters, got {params.shape[1]}")
+        t_arr = np.ascontiguousarray(t_eval, dtype=np.float64).reshape(-1)
+        T = int(t_arr.size)
+        y0 = xp.f64(y0)
+        if y0.ndim == 1:
+            if y0.shape[0] != n:
+                raise ValueError(f"y0 must have {n} entries")
+            y0_stride = 0
+        else:
+            if tuple(y0.shape) != (B, n):
+                raise ValueError(f"y0 must be [{n}] or [{B},{n}]")
+            y0_stride = n
+        job = PkGlobalJob()
+        self.lib.pk_global_job_init(C.byref(job))
+        job.topo, job.memspace, job.B, job.T = int(topo), PK_DEVICE if dev else PK_HOST, B, T
+        job.theta_mode = int(bool(theta_mode))
+        job.params, job.y0, job.y0_stride, job.t_eval = xp.ptr(params), xp.ptr(y0), y0_stride, t_arr.ctypes.data
+        job.rtol = 0.0 if rtol is None else float(rtol)
+        job.atol = 0.0 if atol is None else float(atol)
+        job.max_steps, job.loss_mode = int(max_steps), int(loss_mode)
+        for i in range(3):
+            job.lambdas[i] = float(lambdas[i])
+        job.lambda_prior = float(lambda_prior)
+        res, keep = {}, [params, y0, t_arr]
+        out = out or {}
+
+        def alloc(key, shape, dtype="f64"):
+            buf = out.get(key)
+            if buf is None:
+                buf = xp.empty(shape, dtype)
+            res[key] = buf
+            return xp.ptr(buf)
+
+        if "Y" in want:
+            job.out_Y = alloc("Y", (B, T, n))
+        if "loss" in want:
+            job.out_loss = alloc("loss", (B, 3))
+        if "F" in want:
+            job.out_F = alloc("F", (B, 3))
+        if "metric" in want:
+            if metric_times is None:
+                raise ValueError("metric needs metric_times")
+            job.metric = GLOBAL_METRIC_IDS[metric]
+            for name, key in (("prot", "t_prot"), ("rna", "t_rna"), ("pho", "t_pho")):
+                a = np.ascontiguousarray(metric_times[key], dtype=np.int32).reshape(-1)
+                keep.append(a)
+                setattr(job, "n_mt_" + name, int(a.size))
+                setattr(job, "mt_" + name, a.ctypes.data)
+            job.mb_prot, job.mb_rna, job.mb_pho = (int(metric_times["prot_b"]), int(metric_times["rna_b"]),
+                                                   int(metric_times["pho_b"]))
+            job.out_metric = alloc("metric", (B,))
+        job.out_status = alloc("status", (B,), "i32")
+        job.out_nsteps = alloc("nsteps", (B,), "i32")
+        job.out_nrej = alloc("nrej", (B,), "i32")
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_global_solve_batch(self._h, C.byref(job)))
+        del keep
+        return res
+
+    def global_loss_batch(self, topo, Y, loss_mode=0):
+        """(loss_p, loss_r, loss_ph) per trajectory for Y[B,T,state_dim] (or [T,state_dim])."""
+        dev = _is_torch(Y)
+        xp = _TorchOps(Y.device) if dev else _NumpyOps()
+        Y = xp.f64(Y)
+        if Y.ndim == 2:
+            Y = Y.reshape(1, *Y.shape)
+        n = self.global_dims(topo)["state_dim"]
+        if Y.ndim != 3 or Y.shape[2] != n:
+            raise ValueError(f"Y must be [B,T,{n}]")
+        B, T = int(Y.shape[0]), int(Y.shape[1])
+        out = xp.empty((B, 3), "f64")
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_global_loss_batch(self._h, int(topo), PK_DEVICE if dev else PK_HOST, xp.ptr(Y), B, T,
+                                                 int(loss_mode), xp.ptr(out)))
+        return out
 
     # ------------------------------------------------------------------------- multi-GPU
     def init_nccl(self, world, rank, id_bytes):

@@ -1,2 +1,3 @@
 """Global coupled kinase-TF-protein network path."""
 from .network import GlobalSystem, synthetic_system, synthetic_loss_data  # noqa: F401
+from .simulate import LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint  # noqa: F401

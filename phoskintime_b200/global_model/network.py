@@ -55,6 +55,7 @@ class GlobalSystem:
         self.tf_scale = self.defaults["tf_scale"]
         self.custom_y0 = None if y0 is None else f64(y0).copy()
         self._topo_id = {}          # engine id -> uploaded topology id
+        self._loss_key = {}         # engine id -> loss-table dict currently installed
 
     # ---- reference surface -----------------------------------------------------------------
     def update(self, c_k, A_i, B_i, C_i, D_i, Dp_i, E_i, tf_scale):

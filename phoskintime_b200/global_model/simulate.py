@@ -1,0 +1,101 @@
+"""Drop-in surface of the reference's `global_model/simulate.py`, `lossfn.py` dispatch and the batched
+forms the GPU path adds.
+
+`simulate_odeint(sys, t_eval, rtol, atol, mxstep)` keeps the reference's signature
+(global_model/simulate.py:34-80) and return value (`Y[T, state_dim]`, C-contiguous float64); it is a
+batch of one through `simulate_batch`.  All arithmetic runs in libphoskin_b200.so (kernel
+`global_net_kernel`, csrc/global_net.cuh); there is no CPU path — without the library or a GPU every
+call raises `PhoskinError`.
+
+Differences a caller can observe (documented, not hidden):
+  * the integrator is a Rosenbrock method with the analytic Jacobian that lands on the kinase-grid
+    points where the RHS jumps; the reference's LSODA integrates through them with a finite-difference
+    Jacobian.  Results agree with the reference's own tight-tolerance solution to <=1e-6 relative
+    (tests/test_gpu_global.py); `mxstep` bounds the steps of the whole solve, not of one output interval;
+  * failed systems come back as NaN rows with a non-zero status instead of SciPy warnings.
+"""
+import numpy as np
+
+from ..engine import get_engine
+
+METRIC_BASE_TIMES = (0.0, 4.0, 0.0)       # simulate.py:116-118: protein, RNA (t=4), phospho baselines
+
+
+def _topology(sys_, engine):
+    key = id(engine)
+    if key not in sys_._topo_id:
+        sys_._topo_id[key] = engine.global_upload(sys_)
+    return sys_._topo_id[key]
+
+
+def simulate_batch(sys_, params, t_eval, want=("Y",), *, y0=None, rtol=None, atol=None, mxstep=0, theta_mode=False,
+                   loss_data=None, loss_mode=0, metric="total_signal", metric_times=None, lambdas=(1.0, 1.0, 1.0),
+                   lambda_prior=0.0, engine=None, out=None):
+    """B parameter vectors of one network -> any of Y[B,T,n], loss[B,3], F[B,3], metric[B] (+status, nsteps, nrej).
+
+    params: [B,P] in the order `GlobalSystem.pack_params` (c_k|A|B|C|D|Dp|E|tf_scale); numpy (host path, the
+    library stages through HBM) or torch CUDA tensors (used in place, outputs are torch tensors).
+    """
+    eng = engine or get_engine()
+    topo = _topology(sys_, eng)
+    if loss_data is not None and sys_._loss_key.get(id(eng)) is not loss_data:
+        eng.global_set_loss_data(topo, loss_data)
+        sys_._loss_key[id(eng)] = loss_data
+    if "F" in want:
+        eng.global_set_prior(topo, sys_.pack_params(sys_.defaults) if lambda_prior else None)
+    if y0 is None:
+        y0 = sys_.y0()
+    return eng.global_solve_batch(topo, params, y0, t_eval, want, rtol=rtol, atol=atol, max_steps=mxstep,
+                                  theta_mode=theta_mode, loss_mode=loss_mode, metric=metric, metric_times=metric_times,
+                                  lambdas=lambdas, lambda_prior=lambda_prior, out=out)
+
+
+def simulate_odeint(sys, t_eval, rtol, atol, mxstep):
+    """Reference signature (global_model/simulate.py:34): current parameters of `sys` -> Y[T, state_dim]."""
+    t_eval = np.asarray(t_eval, dtype=np.float64)
+    res = simulate_batch(sys, sys.pack_params()[None, :], t_eval, ("Y",), rtol=rtol, atol=atol, mxstep=int(mxstep))
+    return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
+
+
+def metric_time_indices(times, t_points_p, t_points_r, t_points_pho):
+    """Which rows of the union grid `times` simulate_and_measure keeps per modality (simulate.py:107-124,
+    :189-200) and the three baseline rows."""
+    times = np.asarray(times, float)
+    pick = lambda tp: np.flatnonzero(np.isin(times, np.asarray(tp, float))).astype(np.int32)
+    bidx = lambda t0: int(np.argmin(np.abs(times - t0)))
+    return {"t_prot": pick(t_points_p), "t_rna": pick(t_points_r), "t_pho": pick(t_points_pho),
+            "prot_b": bidx(METRIC_BASE_TIMES[0]), "rna_b": bidx(METRIC_BASE_TIMES[1]), "pho_b": bidx(METRIC_BASE_TIMES[2])}
+
+
+def LOSS_FN(Y, p_prot, t_prot, obs_prot, w_prot, p_rna, t_rna, obs_rna, w_rna, p_pho, s_pho, t_pho, obs_pho, w_pho,
+            prot_map, prot_base_idx, rna_base_idx, pho_base_idx, *, loss_mode=0, engine=None):
+    """Reference signature of `LOSS_FN` (global_model/lossfn.py:113-121, :386) for models 0/1/4:
+    one trajectory Y[T, state_dim] -> (loss_p, loss_r, loss_ph).  `prot_map[i] = (offset_y, n_sites)`
+    (cache.py:128-139) is all the topology the loss needs, so a loss-only topology is uploaded per
+    distinct prot_map and cached."""
+    eng = engine or get_engine()
+    prot_map = np.ascontiguousarray(prot_map, dtype=np.int32)
+    key = (id(eng), prot_map.tobytes())
+    topo = _LOSS_TOPOS.get(key)
+    if topo is None:
+        from .network import GlobalSystem
+        n_sites = prot_map[:, 1]
+        N, S = n_sites.size, int(n_sites.sum())
+        if not np.array_equal(prot_map[:, 0], np.concatenate([[0], np.cumsum(2 + n_sites)[:-1]])):
+            raise ValueError("prot_map offsets must be the packed [mRNA, P0, sites...] layout (network.py:28-167)")
+        z = np.zeros(N)
+        shell = GlobalSystem(n_sites=n_sites, W_indptr=np.zeros(S + 1, np.int32), W_indices=[], W_data=[],
+                             TF_indptr=np.zeros(N + 1, np.int32), TF_indices=[], TF_data=[], kin_grid=[0.0],
+                             kin_Kmat=np.ones((1, 1)), tf_deg=np.ones(N), driver_map=np.full(N, -1),
+                             defaults={"c_k": [1.0], "A_i": z, "B_i": z, "C_i": z, "D_i": z, "Dp_i": np.zeros(S), "E_i": z,
+                                       "tf_scale": 0.0})
+        topo = _LOSS_TOPOS[key] = eng.global_upload(shell)
+    eng.global_set_loss_data(topo, dict(p_prot=p_prot, t_prot=t_prot, obs_prot=obs_prot, w_prot=w_prot, p_rna=p_rna,
+                                        t_rna=t_rna, obs_rna=obs_rna, w_rna=w_rna, p_pho=p_pho, s_pho=s_pho, t_pho=t_pho,
+                                        obs_pho=obs_pho, w_pho=w_pho, prot_base_idx=prot_base_idx,
+                                        rna_base_idx=rna_base_idx, pho_base_idx=pho_base_idx))
+    out = eng.global_loss_batch(topo, np.asarray(Y, dtype=np.float64), loss_mode)
+    return float(out[0, 0]), float(out[0, 1]), float(out[0, 2])
+
+
+_LOSS_TOPOS = {}

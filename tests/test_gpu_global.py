@@ -1,0 +1,199 @@
+"""GPU parity tests of the global-network path: `global_net_kernel`
+called through the C ABI against the committed goldens of the UNMODIFIED reference
+(tests/golden/global_*.npz: `simulate_odeint` stock at rtol=atol=1e-8 = O1, reference RHS bucket by
+bucket at 1e-12 = O2, `LOSS_FN` in all 8 modes) and against the oracle restatement.
+
+Tolerances:
+  * vs O2:  |ours - ref| <= 1e-6*|ref| + 1e-9   at the library defaults (rtol 1e-6, atol 1e-9)
+  * vs O1:  |ours - ref| <= 1e-5*|ref| + 1e-6 everywhere, >= 99 % within 1e-6*|ref| + 1e-7
+            (the stock reference integrates THROUGH the kinase-bucket jumps, SURVEY.md quirk 8, and is
+             itself up to 0.6x the O2 bound away from O2)
+  * loss / objectives / Morris scalar vs the oracle formulas on OUR trajectories: 1e-11 relative
+  * LOSS_FN on the REFERENCE's trajectories vs the reference's own loss values: 1e-11 relative
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import global_models as og  # noqa: E402
+from phoskintime_b200.global_model import (LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint,  # noqa: E402
+                                           synthetic_loss_data, synthetic_system)
+
+pytestmark = pytest.mark.gpu
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "global_*.npz")))
+IDS = [os.path.basename(f)[7:-4] for f in FILES]
+T_PROT = [0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0]
+T_RNA = [4.0, 8.0, 15.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0]
+
+
+def load_case(path):
+    g = np.load(path)
+    s = synthetic_system(seed=int(g["seed"]), N=int(g["N"]), K=int(g["K"]), max_sites=int(g["max_sites"]),
+                         model=int(g["model"]))
+    ld = {k[3:]: g[k] for k in g.files if k.startswith("ld_")}
+    for k in ("prot_base_idx", "rna_base_idx", "pho_base_idx"):
+        ld[k] = int(ld[k])
+    return g, s, ld
+
+
+def _ratio(a, ref, rtol, atol):
+    return float((np.abs(a - ref) / (rtol * np.abs(ref) + atol)).max())
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_trajectories_match_reference(engine, path):
+    g, s, _ = load_case(path)
+    r = simulate_batch(s, g["params"], g["t"], ("Y",), y0=g["y0"], engine=engine)
+    assert (r["status"] == 0).all(), r["status"]
+    Y = r["Y"]
+    assert Y.shape == g["Y"].shape
+    assert _ratio(Y, g["Y_tight"], 1e-6, 1e-9) <= 1.0
+    assert _ratio(Y, g["Y"], 1e-5, 1e-6) <= 1.0
+    assert (np.abs(Y - g["Y"]) <= 1e-6 * np.abs(g["Y"]) + 1e-7).mean() >= 0.99
+    # closer to the tight reference than the stock reference is
+    assert _ratio(Y, g["Y_tight"], 1e-6, 1e-9) <= _ratio(g["Y"], g["Y_tight"], 1e-6, 1e-9)
+    assert (r["nsteps"] > 0).all() and (r["nrej"] >= 0).all()
+
+
+@pytest.mark.parametrize("path", FILES[:2], ids=IDS[:2])
+def test_tighter_tolerance_converges(engine, path):
+    g, s, _ = load_case(path)
+    r6 = simulate_batch(s, g["params"], g["t"], ("Y",), y0=g["y0"], engine=engine)
+    r8 = simulate_batch(s, g["params"], g["t"], ("Y",), y0=g["y0"], rtol=1e-8, atol=1e-11, engine=engine)
+    e6, e8 = _ratio(r6["Y"], g["Y_tight"], 1e-6, 1e-9), _ratio(r8["Y"], g["Y_tight"], 1e-6, 1e-9)
+    assert e8 < 0.1 * e6 + 1e-3 and e8 < 0.02
+    assert (r8["nsteps"] > r6["nsteps"]).all()
+
+
+def test_reference_signature_single_system(engine):
+    g, s, _ = load_case(FILES[0])
+    s.update(**s.unpack_params(g["params"][1]))
+    Y = simulate_odeint(s, g["t"], 1e-6, 1e-9, 200000)
+    assert Y.shape == g["Y"][1].shape and Y.flags["C_CONTIGUOUS"] and Y.dtype == np.float64
+    assert _ratio(Y, g["Y_tight"][1], 1e-6, 1e-9) <= 1.0
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_fused_loss_objectives_metric(engine, path):
+    g, s, ld = load_case(path)
+    net = s.as_dict()
+    mt = metric_time_indices(g["t"], T_PROT, T_RNA, T_PROT)
+    lambdas, lam_prior = (1.0, 0.7, 1.3), 0.1
+    for mode in (0, 1, 3, 4, 5, 6, 7):
+        for metric in (("total_signal",) if mode else ("total_signal", "mean", "variance", "l2_norm")):
+            r = simulate_batch(s, g["params"], g["t"], ("Y", "loss", "F", "metric"), y0=g["y0"], loss_data=ld,
+                               loss_mode=mode, metric=metric, metric_times=mt, lambdas=lambdas, lambda_prior=lam_prior,
+                               engine=engine)
+            for b in range(g["params"].shape[0]):
+                ref = np.array(og.loss_noncomb(r["Y"][b], ld, mode if mode < 7 else -1))
+                assert np.allclose(r["loss"][b], ref, rtol=1e-11, atol=1e-13), (mode, b)
+                F = og.objectives(ref, ld, og.unpack_params(g["params"][b], net), net["defaults"], lambdas, lam_prior)
+                assert np.allclose(r["F"][b], F, rtol=1e-11, atol=1e-13), (mode, b)
+                m = og.scalar_metric(r["Y"][b], net, mt, metric)
+                assert np.isclose(r["metric"][b], m, rtol=1e-10, atol=1e-12), (metric, b)
+
+
+def test_outputs_without_trajectory_match(engine):
+    """loss/metric computed from the per-CTA trajectory slot (no Y output) equal the ones computed with Y."""
+    g, s, ld = load_case(FILES[1])
+    mt = metric_time_indices(g["t"], T_PROT, T_RNA, T_PROT)
+    P = np.repeat(g["params"], 40, axis=0)            # more systems than a few CTAs hold at once
+    a = simulate_batch(s, P, g["t"], ("Y", "loss", "metric"), y0=g["y0"], loss_data=ld, metric_times=mt, engine=engine)
+    b = simulate_batch(s, P, g["t"], ("loss", "metric"), y0=g["y0"], loss_data=ld, metric_times=mt, engine=engine)
+    assert np.array_equal(a["loss"], b["loss"]) and np.array_equal(a["metric"], b["metric"])
+    # repeated parameter rows are reproduced bit for bit whichever CTA integrates them
+    assert np.array_equal(a["Y"][0], a["Y"][1]) and np.array_equal(a["loss"][0], a["loss"][39])
+
+
+@pytest.mark.parametrize("path", [f for f in FILES if "loss_mode0" in np.load(f).files],
+                         ids=[i for f, i in zip(FILES, IDS) if "loss_mode0" in np.load(f).files])
+def test_loss_fn_on_reference_trajectories(engine, path):
+    """LOSS_FN with the reference's signature on the reference's own Y vs the reference's own loss values."""
+    g, s, ld = load_case(path)
+    for mode in (0, 1, 2, 3, 4, 5, 6, -1):
+        ref = g[f"loss_mode{mode}"]
+        for b in range(ref.shape[0]):
+            mine = np.array(LOSS_FN(g["Y"][b], ld["p_prot"], ld["t_prot"], ld["obs_prot"], ld["w_prot"], ld["p_rna"],
+                                    ld["t_rna"], ld["obs_rna"], ld["w_rna"], ld["p_pho"], ld["s_pho"], ld["t_pho"],
+                                    ld["obs_pho"], ld["w_pho"], ld["prot_map"], ld["prot_base_idx"], ld["rna_base_idx"],
+                                    ld["pho_base_idx"], loss_mode=mode, engine=engine))
+            both_nan = np.isnan(mine) & np.isnan(ref[b])        # mode 2 is NaN by design
+            assert np.all(both_nan | (np.abs(mine - ref[b]) <= 1e-11 * np.abs(ref[b]) + 1e-13)), (mode, b, mine, ref[b])
+
+
+def test_theta_mode_and_device_buffers(engine):
+    """raw theta -> softplus on the device (params.py:106-132); torch CUDA tensors are used in place."""
+    import torch
+    g, s, ld = load_case(FILES[0])
+    phys = g["params"]
+    theta = np.log(np.expm1(phys))                     # inverse softplus
+    a = simulate_batch(s, phys, g["t"], ("Y",), y0=g["y0"], engine=engine)
+    b = simulate_batch(s, torch.tensor(theta, device="cuda:0"), g["t"], ("Y",), y0=torch.tensor(g["y0"], device="cuda:0"),
+                       theta_mode=True, engine=engine)
+    assert isinstance(b["Y"], torch.Tensor) and b["Y"].is_cuda
+    assert np.allclose(b["Y"].cpu().numpy(), a["Y"], rtol=1e-9, atol=1e-12)
+
+
+def test_per_system_initial_conditions_and_failures(engine):
+    g, s, _ = load_case(FILES[0])
+    B = 6
+    P = np.repeat(g["params"][:1], B, axis=0)
+    y0 = np.repeat(g["y0"][None, :], B, axis=0)
+    y0[1] *= 1.5
+    r = simulate_batch(s, P, g["t"], ("Y",), y0=y0, engine=engine)
+    assert np.array_equal(r["Y"][0], r["Y"][2]) and not np.allclose(r["Y"][0], r["Y"][1])
+    assert np.allclose(r["Y"][1][0], y0[1])
+    # a step budget that cannot be met -> status 1 and NaN rows, the batch itself succeeds
+    r = simulate_batch(s, P, g["t"], ("Y",), y0=y0, mxstep=5, engine=engine)
+    assert (r["status"] == 1).all() and np.isnan(r["Y"]).all()
+    # non-finite parameters -> status 3
+    Pbad = P.copy()
+    Pbad[3, 0] = np.nan
+    r = simulate_batch(s, Pbad, g["t"], ("Y",), y0=y0, engine=engine)
+    assert r["status"][3] != 0 and np.isnan(r["Y"][3]).all() and (np.delete(r["status"], 3) == 0).all()
+
+
+def test_time_grid_subsets(engine):
+    """t_eval need not contain the kinase-grid points: steps still land on them (same values at shared times)."""
+    g, s, _ = load_case(FILES[2])
+    full = simulate_batch(s, g["params"], g["t"], ("Y",), y0=g["y0"], engine=engine)["Y"]
+    sub_t = g["t"][[0, 3, 7, 11, 14]]
+    sub = simulate_batch(s, g["params"], sub_t, ("Y",), y0=g["y0"], engine=engine)["Y"]
+    assert _ratio(sub, g["Y_tight"][:, [0, 3, 7, 11, 14]], 1e-6, 1e-9) <= 1.0
+    assert np.allclose(sub, full[:, [0, 3, 7, 11, 14]], rtol=2e-6, atol=1e-9)
+
+
+def test_unsupported_model_and_bad_inputs(engine):
+    from phoskintime_b200 import PhoskinError
+    s = synthetic_system(seed=1, N=6, K=3, max_sites=2, model=0)
+    s.model = 2
+    with pytest.raises(PhoskinError):
+        engine.global_upload(s)
+    s.model = 0
+    with pytest.raises(ValueError):
+        simulate_batch(s, np.ones((2, 5)), [0.0, 1.0], engine=engine)
+    with pytest.raises(PhoskinError):
+        simulate_batch(s, s.pack_params()[None], [0.0, 1.0, 1.0], engine=engine)      # not increasing
+    with pytest.raises(PhoskinError):
+        simulate_batch(s, s.pack_params()[None], [0.0, 1.0], ("loss",), engine=engine)  # no loss tables
+
+
+def test_full_size_network_sanity(engine):
+    """BASELINE configs[4] shape (N=120, state_dim ~500): every system integrates, results are positive,
+    finite, and a tighter tolerance agrees to 1e-6 (size-independent self-consistency)."""
+    s = synthetic_system(seed=5, N=120, K=40, max_sites=4, model=0)
+    rng = np.random.default_rng(0)
+    base = s.pack_params()
+    P = base[None, :] * np.exp(0.05 * rng.standard_normal((32, base.size)))
+    t = np.array([0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 15.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])
+    a = simulate_batch(s, P, t, ("Y",), engine=engine)
+    b = simulate_batch(s, P, t, ("Y",), rtol=1e-8, atol=1e-11, engine=engine)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.isfinite(a["Y"]).all() and (a["Y"] > -1e-9).all()
+    assert _ratio(a["Y"], b["Y"], 1e-6, 1e-9) <= 1.0
