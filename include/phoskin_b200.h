@@ -163,6 +163,8 @@ typedef struct pk_global_topology {
     const double* kin_Kmat;      /* [K, n_bins] row-major                                           */
     const double* tf_deg;        /* [N]                                                             */
     const int32_t* driver_map;   /* [N] kinase index driving protein i's TF activity, or -1         */
+    int32_t force_generic_schur; /* testing: 1 = shared-memory LU path even when the register path fits */
+    int32_t reserved0;
 } pk_global_topology;
 
 typedef struct pk_global_loss_data {

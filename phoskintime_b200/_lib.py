@@ -48,7 +48,7 @@ class PkGlobalTopology(C.Structure):
         ("W_indptr", C.c_void_p), ("W_indices", C.c_void_p), ("W_data", C.c_void_p),
         ("TF_indptr", C.c_void_p), ("TF_indices", C.c_void_p), ("TF_data", C.c_void_p),
         ("kin_grid", C.c_void_p), ("kin_Kmat", C.c_void_p), ("tf_deg", C.c_void_p),
-        ("driver_map", C.c_void_p),
+        ("driver_map", C.c_void_p), ("force_generic_schur", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

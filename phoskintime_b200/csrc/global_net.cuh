@@ -42,9 +42,14 @@ struct GlobalTopoDev {
     double norm[3];                   // 1/max(1e-6, sum w) per modality (optproblem.py:83-85)
 };
 
-struct GlobalSmem {                   // offsets in doubles
-    int par, Kt, Sall, y, arg, U, w, facA, mult, clo, pvec, g, m, z, Sc, idiag, red, perm, total;
-    int ld;
+struct GlobalSmem {                   // offsets in doubles unless stated
+    int par, Kt, Sall, y, arg, U, w, facA, mult, clo, pvec, g, m, z, red, total;
+    int Sc, idiag, perm, ld;          // TILE == 0: Schur matrix + LU in shared memory
+    int colbuf, rowbuf, bp, partial;  // TILE  > 0: Schur matrix in registers (Gauss-Jordan), exchange buffers
+    int tfdata, tfdeg;                // staged topology (doubles)
+    int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
+    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv;
+    int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
 };
 
 struct GlobalArgs {
@@ -71,6 +76,7 @@ struct GlobalArgs {
 
 constexpr int GLOBAL_BLOCK = 256;
 constexpr int GLOBAL_WARPS = GLOBAL_BLOCK / 32;
+constexpr int GJ_MAX_TILE = 8;        // register-resident Schur block up to 128 regulators
 
 // RODAS4 (Hairer & Wanner II, RODAS METH=1), gamma = 1/4
 __constant__ double G_A[5][4] = {
@@ -246,27 +252,39 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK) global_loss_kernel(const GlobalT
     }
 }
 
+struct StepState {                    // step controller of the system a CTA is integrating (shared memory)
+    double t, h;
+    double hh;                        // size of the attempt in flight (h clamped to land on the next stop)
+    float hacc, erracc;
+    int naccpt, rejected_last, nst, nrej, status, land;
+};
+
 struct GlobalCtx {
     const GlobalTopoDev& tp;
     double *par, *Kt, *Sall, *y, *arg, *U, *w, *facA, *mult, *clo, *pvec, *g, *m, *z, *Sc, *idiag, *red;
     int* perm;
-    int ld, n, N;
+    int ld, n, N, nQ, model;
     const double *cA, *cB, *cC, *cD, *cDp, *cE;      // views into par
     double tfs;
+    // topology staged in shared memory once per CTA
+    const int *offy, *offs, *ns, *drv, *tfptr, *tfidx, *qlist, *qpos;
+    const double *tfdata, *tfdeg;
+    // Gauss-Jordan exchange buffers
+    double *colbuf, *rowbuf, *bp, *partial;
+    int *piv, *pinv;
 };
 
 // f(src) -> dst.  With FACTOR: also the transcription gains g_i, the per-protein tree factorisation of
 // A = I - c J_blk, the unit responses w = A^-1 e_R and m_i.  Two phases, thread per protein.
 template <bool FACTOR>
 __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src, double* dst, double c) {
-    const GlobalTopoDev& tp = cx.tp;
-    const int N = cx.N, model = tp.model;
+    const int N = cx.N, model = cx.model;
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
-        const int d = tp.driver_map[i];
+        const int d = cx.drv[i];
         double pv;
         if (d >= 0) pv = cx.Kt[d];                                   // live drive (jacspeedup.py:210-221)
         else {
-            const int st = tp.offset_y[i], ns = tp.n_sites[i];
+            const int st = cx.offy[i], ns = cx.ns[i];
             pv = src[st + 1];
             for (int j = 0; j < ns; ++j) pv += src[st + 2 + j];
         }
@@ -274,10 +292,11 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
     }
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
-        const int st = tp.offset_y[i], ss = tp.offset_s[i], ns = tp.n_sites[i];
+        const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
         double v = 0.0;
-        for (int q = tp.TF_indptr[i]; q < tp.TF_indptr[i + 1]; ++q) v = fma(tp.TF_data[q], cx.pvec[tp.TF_indices[q]], v);
-        v /= tp.tf_deg[i];
+        for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) v = fma(cx.tfdata[q], cx.pvec[cx.tfidx[q]], v);
+        const double itd = 1.0 / cx.tfdeg[i];
+        v *= itd;
         double synth, dsdv;
         synth_rate(model, v, cx.cA[i], cx.tfs, synth, dsdv);
         const double R = src[st], P = src[st + 1];
@@ -324,7 +343,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
             }
         }
         if (FACTOR) {
-            cx.g[i] = dsdv / tp.tf_deg[i];
+            cx.g[i] = dsdv * itd;
             // pivots: facA[st+1] (P0), facA[st+2+j] (site j); children are eliminated before parents
             const double lo_scale = (model == 4) ? 1.0 / ((1.0 + P) * (1.0 + P)) : 1.0;
             cx.facA[st + 1] = fma(-c, dPP, 1.0);
@@ -366,21 +385,155 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
     __syncthreads();
 }
 
-// Dense LU with partial pivoting of the nQ x nQ Schur matrix in shared memory (row-major, ld).
+// ------------------------------------------------------------------------------------------------
+// Schur block  Sc = I - c diag(m) G  restricted to the regulator set Q  (nQ x nQ).
+//
+// TILE > 0 (nQ <= 16*TILE <= 128): the matrix never touches memory.  The 256 threads form a 16x16
+// grid; thread (tr, tc) owns entries (tr + 16a, tc + 16b), a,b < TILE, in registers.  The matrix is
+// INVERTED in place by Gauss-Jordan elimination with implicit partial pivoting (the pivot row of
+// column k is chosen among the unused physical rows, nothing is swapped): per column only the
+// pivot column and pivot row travel through shared memory (double buffered, 2 barriers), the
+// TILE*TILE rank-1 update runs on registers.  The six stage solves of a step then are register
+// mat-vecs (no sequential triangular solves):   z = Phys . b[piv]  read back through pinv.
+// TILE == 0: generic fallback, LU with partial pivoting in shared memory + triangular solves.
+// ------------------------------------------------------------------------------------------------
+template <int TILE>
+__device__ __forceinline__ void gj_assemble(const GlobalCtx& cx, double c, double (&A)[TILE][TILE]) {
+    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    const int nQ = cx.nQ;
+#pragma unroll
+    for (int a = 0; a < TILE; ++a) {
+#pragma unroll
+        for (int b = 0; b < TILE; ++b) A[a][b] = 0.0;
+        const int r = tr + 16 * a;
+        if (r < nQ) {
+            const int i = cx.qlist[r];
+            const double f = -c * cx.m[i] * cx.g[i];
+            for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) {
+                const int qj = cx.qpos[cx.tfidx[q]];
+                if (qj >= 0 && (qj & 15) == tc) {
+                    const double v = f * cx.tfdata[q];
+                    const int bb = qj >> 4;
+#pragma unroll
+                    for (int b = 0; b < TILE; ++b)
+                        if (b == bb) A[a][b] += v;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < TILE; ++b)
+                if (r == tc + 16 * b) A[a][b] += 1.0;
+        }
+    }
+}
+
+template <int TILE>
+__device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE][TILE]) {
+    constexpr int GP = 16 * TILE;
+    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4, lane = threadIdx.x & 31;
+    const int nQ = cx.nQ;
+    unsigned mymask = 0;                 // bit w: physical row lane + 32 w has already served as a pivot row
+#pragma unroll
+    for (int kb = 0; kb < TILE; ++kb) {
+#pragma unroll 1
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = kb * 16 + kk;
+            if (k >= nQ) break;
+            double* colb = cx.colbuf + (k & 1) * GP;
+            double* rowb = cx.rowbuf + (k & 1) * GP;
+            if (tc == kk) {
+#pragma unroll
+                for (int a = 0; a < TILE; ++a) colb[tr + 16 * a] = A[a][kb];
+            }
+            __syncthreads();
+            // pivot search, redundantly in every warp (no broadcast barrier): FP32 magnitudes suffice
+            float best = -1.f;
+            int bi = 0;
+#pragma unroll
+            for (int w = 0; w < (TILE + 1) / 2; ++w) {
+                const int r = lane + 32 * w;
+                if (r < nQ && !((mymask >> w) & 1u)) {
+                    const float v = fabsf((float)colb[r]);
+                    if (v > best) { best = v; bi = r; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            const int p = bi;
+            if ((p & 31) == lane) mymask |= 1u << (p >> 5);
+            if (threadIdx.x == 0) { cx.piv[k] = p; cx.pinv[p] = k; }
+            if (tr == (p & 15)) {
+                const int pa = p >> 4;
+#pragma unroll
+                for (int a = 0; a < TILE; ++a)
+                    if (a == pa) {
+#pragma unroll
+                        for (int b = 0; b < TILE; ++b) rowb[tc + 16 * b] = A[a][b];
+                    }
+            }
+            __syncthreads();
+            const double ip = 1.0 / colb[p];
+            double rv[TILE];
+#pragma unroll
+            for (int b = 0; b < TILE; ++b) rv[b] = rowb[tc + 16 * b];
+#pragma unroll
+            for (int a = 0; a < TILE; ++a) {
+                const int r = tr + 16 * a;
+                const double g = (r == p) ? (ip - 1.0) : -colb[r] * ip;
+#pragma unroll
+                for (int b = 0; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
+                if (tc == kk) A[a][kb] = (r == p) ? ip : g;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// z[Q] <- Sc^-1 z0[Q] with the inverse held in registers (z0 in cx.pvec, result into cx.z)
+template <int TILE>
+__device__ __forceinline__ void gj_apply(const GlobalCtx& cx, const double (&A)[TILE][TILE]) {
+    constexpr int GP = 16 * TILE, PLD = GP + 1;
+    const int nQ = cx.nQ;
+    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    for (int l = threadIdx.x; l < GP; l += GLOBAL_BLOCK) cx.bp[l] = l < nQ ? cx.pvec[cx.qlist[cx.piv[l]]] : 0.0;
+    __syncthreads();
+    double bv[TILE];
+#pragma unroll
+    for (int b = 0; b < TILE; ++b) bv[b] = cx.bp[tc + 16 * b];
+#pragma unroll
+    for (int a = 0; a < TILE; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < TILE; ++b) acc = fma(A[a][b], bv[b], acc);
+        cx.partial[tc * PLD + tr + 16 * a] = acc;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < nQ; r += GLOBAL_BLOCK) {
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc += cx.partial[t * PLD + r];
+        cx.z[cx.qlist[cx.pinv[r]]] = acc;
+    }
+    __syncthreads();
+}
+
+// Generic path: dense LU with partial pivoting of the nQ x nQ Schur matrix in shared memory (row-major, ld).
 __device__ __forceinline__ void schur_factor(const GlobalCtx& cx, double c) {
-    const GlobalTopoDev& tp = cx.tp;
-    const int nQ = tp.nQ, ld = cx.ld;
+    const int nQ = cx.nQ, ld = cx.ld;
     double* Sc = cx.Sc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int idx = threadIdx.x; idx < nQ * ld; idx += GLOBAL_BLOCK) Sc[idx] = 0.0;
     __syncthreads();
     for (int qi = threadIdx.x; qi < nQ; qi += GLOBAL_BLOCK) {
-        const int i = tp.qlist[qi];
+        const int i = cx.qlist[qi];
         double* row = Sc + qi * ld;
         const double f = -c * cx.m[i] * cx.g[i];
-        for (int q = tp.TF_indptr[i]; q < tp.TF_indptr[i + 1]; ++q) {
-            const int qj = tp.qpos[tp.TF_indices[q]];
-            if (qj >= 0) row[qj] = fma(f, tp.TF_data[q], row[qj]);
+        for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) {
+            const int qj = cx.qpos[cx.tfidx[q]];
+            if (qj >= 0) row[qj] = fma(f, cx.tfdata[q], row[qj]);
         }
         row[qi] += 1.0;
         cx.perm[qi] = qi;
@@ -428,15 +581,39 @@ __device__ __forceinline__ void schur_factor(const GlobalCtx& cx, double c) {
     }
 }
 
-// x (vector in shared memory, holds the right-hand side b) <- (I - cJ)^-1 b
-__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c) {
-    const GlobalTopoDev& tp = cx.tp;
-    const int N = cx.N, nQ = tp.nQ, ld = cx.ld;
-    const bool chain = tp.model == 1;
+__device__ __forceinline__ void lu_apply(const GlobalCtx& cx) {
+    const int nQ = cx.nQ, ld = cx.ld;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0 && nQ > 0) {
+        double* xq = cx.red + 2 * GLOBAL_WARPS;                      // [nQ] scratch behind the reduction slots
+        for (int k = lane; k < nQ; k += 32) xq[k] = cx.pvec[cx.qlist[cx.perm[k]]];
+        __syncwarp();
+        const double* Sc = cx.Sc;
+        for (int k = 0; k < nQ - 1; ++k) {                           // L y = P z0
+            const double xk = xq[k];
+            for (int i = k + 1 + lane; i < nQ; i += 32) xq[i] = fma(-Sc[i * ld + k], xk, xq[i]);
+            __syncwarp();
+        }
+        for (int k = nQ - 1; k >= 0; --k) {                          // U z = y
+            if (lane == 0) xq[k] *= cx.idiag[k];
+            __syncwarp();
+            const double xk = xq[k];
+            for (int i = lane; i < k; i += 32) xq[i] = fma(-Sc[i * ld + k], xk, xq[i]);
+            __syncwarp();
+        }
+        for (int k = lane; k < nQ; k += 32) cx.z[cx.qlist[k]] = xq[k];
+    }
+    __syncthreads();
+}
+
+// x (vector in shared memory, holds the right-hand side b) <- (I - cJ)^-1 b
+template <int TILE>
+__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1]) {
+    const int N = cx.N;
+    const bool chain = cx.model == 1;
     // block solves x0 = A^-1 b and z0 (into pvec)
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
-        const int st = tp.offset_y[i], ns = tp.n_sites[i];
+        const int st = cx.offy[i], ns = cx.ns[i];
         const double xr = x[st] * cx.facA[st];
         x[st] = xr;
         double xp = fma(cx.mult[st + 1], xr, x[st + 1]);
@@ -459,48 +636,38 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
         cx.z[i] = 0.0;
     }
     __syncthreads();
-    if (warp == 0 && nQ > 0) {
-        double* xq = cx.red + 2 * GLOBAL_WARPS;                      // [nQ] scratch behind the reduction slots
-        for (int k = lane; k < nQ; k += 32) xq[k] = cx.pvec[tp.qlist[cx.perm[k]]];
-        __syncwarp();
-        const double* Sc = cx.Sc;
-        for (int k = 0; k < nQ - 1; ++k) {                           // L y = P z0
-            const double xk = xq[k];
-            for (int i = k + 1 + lane; i < nQ; i += 32) xq[i] = fma(-Sc[i * ld + k], xk, xq[i]);
-            __syncwarp();
-        }
-        for (int k = nQ - 1; k >= 0; --k) {                          // U z = y
-            if (lane == 0) xq[k] *= cx.idiag[k];
-            __syncwarp();
-            const double xk = xq[k];
-            for (int i = lane; i < k; i += 32) xq[i] = fma(-Sc[i * ld + k], xk, xq[i]);
-            __syncwarp();
-        }
-        for (int k = lane; k < nQ; k += 32) cx.z[tp.qlist[k]] = xq[k];
+    if (cx.nQ > 0) {
+        if constexpr (TILE > 0) gj_apply<TILE>(cx, A);
+        else lu_apply(cx);
     }
-    __syncthreads();
     // x += c (G z)_i w_i
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
         double gz = 0.0;
-        for (int q = tp.TF_indptr[i]; q < tp.TF_indptr[i + 1]; ++q) gz = fma(tp.TF_data[q], cx.z[tp.TF_indices[q]], gz);
+        for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) gz = fma(cx.tfdata[q], cx.z[cx.tfidx[q]], gz);
         gz *= c * cx.g[i];
-        const int st = tp.offset_y[i], ns = tp.n_sites[i];
+        const int st = cx.offy[i], ns = cx.ns[i];
         for (int s = st; s < st + 2 + ns; ++s) x[s] = fma(gz, cx.w[s], x[s]);
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const GlobalArgs a) {
+template <int TILE>
+__global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1) global_net_kernel(const GlobalArgs a) {
     extern __shared__ double smem[];
     const GlobalTopoDev& tp = a.tp;
     const GlobalSmem& L = a.sm;
     const int n = tp.n, N = tp.N, K = tp.K, S = tp.S, T = a.T, P = a.P;
     __shared__ long long s_sys;
+    __shared__ StepState S_;
+    int* const ismem = (int*)(smem + L.ints);
     GlobalCtx cx{tp,
                  smem + L.par, smem + L.Kt, smem + L.Sall, smem + L.y, smem + L.arg, smem + L.U, smem + L.w,
                  smem + L.facA, smem + L.mult, smem + L.clo, smem + L.pvec, smem + L.g, smem + L.m, smem + L.z,
-                 smem + L.Sc, smem + L.idiag, smem + L.red, (int*)(smem + L.perm), L.ld, n, N,
-                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0};
+                 smem + L.Sc, smem + L.idiag, smem + L.red, (int*)(smem + L.perm), L.ld, n, N, tp.nQ, tp.model,
+                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                 ismem + L.i_offy, ismem + L.i_offs, ismem + L.i_ns, ismem + L.i_drv, ismem + L.i_tfptr, ismem + L.i_tfidx,
+                 ismem + L.i_qlist, ismem + L.i_qpos, smem + L.tfdata, smem + L.tfdeg,
+                 smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv};
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
     cx.cC = cx.cB + N;
@@ -511,36 +678,73 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const Globa
     double* const arg = cx.arg;
     double* const U = cx.U;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double A[TILE ? TILE : 1][TILE ? TILE : 1];        // Schur block / its inverse (register resident)
+
+    // topology -> shared memory, once per CTA (the CTA is persistent over its systems)
+    {
+        const int nnz = tp.TF_indptr[N];
+        for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+            ismem[L.i_offy + i] = tp.offset_y[i];
+            ismem[L.i_offs + i] = tp.offset_s[i];
+            ismem[L.i_ns + i] = tp.n_sites[i];
+            ismem[L.i_drv + i] = tp.driver_map[i];
+            ismem[L.i_qpos + i] = tp.qpos[i];
+            smem[L.tfdeg + i] = tp.tf_deg[i];
+        }
+        for (int i = threadIdx.x; i <= N; i += GLOBAL_BLOCK) ismem[L.i_tfptr + i] = tp.TF_indptr[i];
+        for (int q = threadIdx.x; q < nnz; q += GLOBAL_BLOCK) {
+            ismem[L.i_tfidx + q] = tp.TF_indices[q];
+            smem[L.tfdata + q] = tp.TF_data[q];
+        }
+        for (int q = threadIdx.x; q < tp.nQ; q += GLOBAL_BLOCK) ismem[L.i_qlist + q] = tp.qlist[q];
+    }
 
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_sys = (long long)atomicAdd(a.counter, 1ull);
         __syncthreads();
-        const long long sys = s_sys;
-        if (sys >= a.B) break;
+        if (s_sys >= a.B) break;
 
         // ------------------------------------------------------------------------ load
-        const double* pr = a.params + (size_t)sys * P;
-        for (int i = threadIdx.x; i < P; i += GLOBAL_BLOCK) {
-            const double v = pr[i];
-            cx.par[i] = a.theta_mode ? softplus_d(v) : v;             // params.py:106-132
+        {
+            const long long sys = s_sys;
+            const double* pr = a.params + (size_t)sys * P;
+            for (int i = threadIdx.x; i < P; i += GLOBAL_BLOCK) {
+                const double v = pr[i];
+                cx.par[i] = a.theta_mode ? softplus_d(v) : v;         // params.py:106-132
+            }
+            const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = y0[i];
         }
-        const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
-        double* traj = a.out_Y ? a.out_Y + (size_t)sys * T * n : a.traj + (size_t)blockIdx.x * T * n;
-        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = y0[i];
         __syncthreads();
         cx.tfs = cx.par[P - 1];
-
-        double t = a.stop_t[0];
-        double h = 0.0;
-        float hacc = 0.f, erracc = 1.f;
-        int naccpt = 0, rejected_last = 0;
-        int nst = 0, nrej = 0, status = 0;
-        if (a.stop_out[0] >= 0)
+        // trajectory rows of this system: the caller's Y, or this CTA's scratch slot (re-derived where it is
+        // needed instead of being held in registers across the factorisation)
+        auto traj_of = [&]() -> double* {
+            return a.out_Y ? a.out_Y + (size_t)s_sys * T * n : a.traj + (size_t)blockIdx.x * T * n;
+        };
+        if (a.stop_out[0] >= 0) {
+            double* const traj = traj_of();
             for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) traj[(size_t)a.stop_out[0] * n + i] = y[i];
+        }
+        // The step controller's state lives in shared memory (written by thread 0 after each attempt,
+        // read by everyone at the top of the next): it is identical for all threads and would otherwise
+        // occupy ~20 registers per thread across the register-resident factorisation.
+        if (threadIdx.x == 0) {
+            S_.t = a.stop_t[0];
+            S_.h = 0.0;
+            S_.hacc = 0.f;
+            S_.erracc = 1.f;
+            S_.naccpt = 0;
+            S_.rejected_last = 0;
+            S_.nst = 0;
+            S_.nrej = 0;
+            S_.status = 0;
+        }
+        __syncthreads();
 
-        for (int si = 0; si + 1 < a.n_stops && status == 0; ++si) {
-            const double tend = a.stop_t[si + 1];
+        for (int si = 0; si + 1 < a.n_stops; ++si) {
+            if (S_.status != 0) break;
             const int jb = a.stop_bucket[si];
             // kinase input of this bucket: Kt = Kmat[:, jb] * c_k;  S = W . Kt   (jacspeedup.py:148-172, 70-113)
             if (si == 0 || jb != a.stop_bucket[si - 1]) {
@@ -564,26 +768,48 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const Globa
                     d1 = fmaxf(d1, (float)(fabs(arg[i]) * sc));
                 }
                 const double D0 = block_max_f(d0, cx.red), D1 = block_max_f(d1, cx.red);
-                h = (D0 < 1e-5 || D1 < 1e-5 || !(D1 < 3.0e38)) ? 1e-6 : 0.01 * D0 / D1;
-                hacc = (float)h;
+                if (threadIdx.x == 0) {
+                    S_.h = (D0 < 1e-5 || D1 < 1e-5 || !(D1 < 3.0e38)) ? 1e-6 : 0.01 * D0 / D1;
+                    S_.hacc = (float)S_.h;
+                }
+                __syncthreads();
             }
-            while (status == 0) {
-                const double rem = tend - t;
-                if (!(rem > 0.0)) break;
-                double hh = h;
-                bool land = false;
-                if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
-                else if (hh > 0.5 * rem) hh = 0.5 * rem;
-                const double c = hh * G_GAMMA;
-                const double ih = 1.0 / hh;
+            for (;;) {
+                {
+                    const double rem = a.stop_t[si + 1] - S_.t;
+                    if (S_.status != 0 || !(rem > 0.0)) break;
+                    if (threadIdx.x == 0) {
+                        double hh = S_.h;
+                        int land = 0;
+                        if (LAND_STRETCH * hh >= rem) { hh = rem; land = 1; }
+                        else if (hh > 0.5 * rem) hh = 0.5 * rem;
+                        S_.hh = hh;
+                        S_.land = land;
+                    }
+                    __syncthreads();
+                }
+                // c = gamma*h is re-read from shared memory after every barrier-separated phase (one LDS) so that
+                // no step-scoped scalar stays live across the register-resident Schur inversion
+#define STEP_C (S_.hh * G_GAMMA)
 
                 // stage 1: f(y), Jacobian pieces, factorisation
-                eval_rhs<true>(cx, y, U, c);
-                schur_factor(cx, c);
-                for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) U[i] *= c;
+                eval_rhs<true>(cx, y, U, STEP_C);
+                if (cx.nQ > 0) {
+                    if constexpr (TILE > 0) {
+                        gj_assemble<TILE>(cx, STEP_C, A);
+                        gj_invert<TILE>(cx, A);
+                    } else {
+                        schur_factor(cx, STEP_C);
+                    }
+                }
+                {
+                    const double c = STEP_C;
+                    for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) U[i] *= c;
+                }
                 __syncthreads();
-                schur_solve(cx, U, c);
+                schur_solve<TILE>(cx, U, STEP_C, A);
                 // stages 2..6:  (I - cJ) U_s = c ( f(y + sum a_sj U_j) + sum c_sj/h U_j )
+#pragma unroll 1
                 for (int s = 1; s < 6; ++s) {
                     for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
                         double v = y[i];
@@ -593,14 +819,17 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const Globa
                     }
                     __syncthreads();
                     double* Us = U + s * n;
-                    eval_rhs<false>(cx, arg, Us, c);
-                    for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
-                        double v = 0.0;
-                        for (int j = 0; j < s; ++j) v = fma(G_C[s - 1][j], U[j * n + i], v);
-                        Us[i] = c * fma(v, ih, Us[i]);
+                    eval_rhs<false>(cx, arg, Us, 0.0);
+                    {
+                        const double c = STEP_C, gam = G_GAMMA;              // gam = c/h
+                        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
+                            double v = 0.0;
+                            for (int j = 0; j < s; ++j) v = fma(G_C[s - 1][j], U[j * n + i], v);
+                            Us[i] = fma(c, Us[i], gam * v);
+                        }
                     }
                     __syncthreads();
-                    schur_solve(cx, Us, c);
+                    schur_solve<TILE>(cx, Us, STEP_C, A);
                 }
                 // y_new = arg_6 + U_6, err = U_6
                 float err = 0.f;
@@ -615,47 +844,58 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const Globa
                 }
                 if (bad) err = __int_as_float(0x7f800000);
                 err = (float)block_max_f(err, cx.red);
-                if (!(err < 3.0e38f)) {
-                    // non-finite stage values: treat as a rejected step with maximal shrink unless h is already tiny
-                    ++nrej;
-                    rejected_last = 1;
-                    h = hh * 0.2;
-                    if (h < 1e-14 * fmax(1.0, fabs(t))) status = 3;
-                } else if (err <= 1.0f) {
-                    ++nst;
-                    float fac = ctl_factor(err, 0.25f);
-                    const float hf = (float)hh;
-                    if (naccpt > 0) {
-                        const float r = __fdividef(err * err, erracc);
-                        float fg = __fdividef(hacc, hf) * __powf(r, 0.25f) * CTL_INV_SAFE;
-                        fg = fmaxf(CTL_FAC_GROW, fminf(CTL_FAC_SHRINK, fg));
-                        fac = fmaxf(fac, fg);
+                const bool accept = err <= 1.0f;                        // false for inf / NaN
+                if (threadIdx.x == 0) {
+                    const double t = S_.t, h = S_.h, hh = S_.hh, tend = a.stop_t[si + 1];
+                    const bool land = S_.land != 0;
+                    if (!(err < 3.0e38f)) {
+                        // non-finite stage values: rejected step with maximal shrink unless h is already tiny
+                        ++S_.nrej;
+                        S_.rejected_last = 1;
+                        S_.h = hh * 0.2;
+                        if (S_.h < 1e-14 * fmax(1.0, fabs(t))) S_.status = 3;
+                    } else if (accept) {
+                        ++S_.nst;
+                        float fac = ctl_factor(err, 0.25f);
+                        const float hf = (float)hh;
+                        if (S_.naccpt > 0) {
+                            const float r = __fdividef(err * err, S_.erracc);
+                            float fg = __fdividef(S_.hacc, hf) * __powf(r, 0.25f) * CTL_INV_SAFE;
+                            fg = fmaxf(CTL_FAC_GROW, fminf(CTL_FAC_SHRINK, fg));
+                            fac = fmaxf(fac, fg);
+                        }
+                        S_.hacc = hf;
+                        S_.erracc = fmaxf(1.0e-2f, err);
+                        ++S_.naccpt;
+                        double hnew = hh / (double)fac;
+                        if (S_.rejected_last) hnew = fmin(hnew, hh);
+                        S_.rejected_last = 0;
+                        S_.h = (hh < h) ? fmax(hnew, fmin(h, 6.0 * hh)) : hnew;
+                        S_.t = land ? tend : t + hh;
+                    } else {
+                        ++S_.nrej;
+                        S_.rejected_last = 1;
+                        S_.h = hh / (double)ctl_factor(err, 0.25f);
+                        if (S_.h < 1e-14 * fmax(1.0, fabs(t))) S_.status = 2;
                     }
-                    hacc = hf;
-                    erracc = fmaxf(1.0e-2f, err);
-                    ++naccpt;
-                    double hnew = hh / (double)fac;
-                    if (rejected_last) hnew = fmin(hnew, hh);
-                    rejected_last = 0;
-                    h = (hh < h) ? fmax(hnew, fmin(h, 6.0 * hh)) : hnew;
-                    for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = arg[i];
-                    t = land ? tend : t + hh;
-                    __syncthreads();
-                } else {
-                    ++nrej;
-                    rejected_last = 1;
-                    h = hh / (double)ctl_factor(err, 0.25f);
-                    if (h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
+                    if (S_.status == 0 && S_.nst + S_.nrej >= a.max_steps && S_.t < tend) S_.status = 1;
                 }
-                if (status == 0 && nst + nrej >= a.max_steps && t < tend) status = 1;
+                if (accept)
+                    for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = arg[i];
+                __syncthreads();
             }
-            if (status == 0) {
-                t = tend;
+#undef STEP_C
+            if (S_.status == 0) {
                 const int ko = a.stop_out[si + 1];
-                if (ko >= 0)
+                if (ko >= 0) {
+                    double* const traj = traj_of();
                     for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) traj[(size_t)ko * n + i] = y[i];
+                }
             }
         }
+        const int status = S_.status;
+        double* const traj = traj_of();
+        const long long sys = s_sys;
         if (status != 0) {                                           // failed system: NaN trajectory
             for (int i = threadIdx.x; i < T * n; i += GLOBAL_BLOCK) traj[i] = qnan;
         }
@@ -664,8 +904,8 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 1) global_net_kernel(const Globa
         // ---------------------------------------------------------------------- epilogue
         if (threadIdx.x == 0) {
             if (a.out_status) a.out_status[sys] = status;
-            if (a.out_nsteps) a.out_nsteps[sys] = nst;
-            if (a.out_nrej) a.out_nrej[sys] = nrej;
+            if (a.out_nsteps) a.out_nsteps[sys] = S_.nst;
+            if (a.out_nrej) a.out_nrej[sys] = S_.nrej;
         }
         if (a.out_loss || a.out_F) {
             double lp, lr, lph;

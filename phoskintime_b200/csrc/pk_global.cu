@@ -68,9 +68,10 @@ int bucket_of(double t, const std::vector<double>& g) {       // jacspeedup.py:1
     return std::min(std::max(j, 0), (int)g.size() - 1);
 }
 
-void layout_smem(GlobalTopoHost* th) {
+void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     const pk::GlobalTopoDev& d = th->dev;
     pk::GlobalSmem& L = th->sm;
+    memset(&L, 0, sizeof(L));
     int o = 0;
     auto take = [&](int count) {
         const int at = o;
@@ -78,7 +79,8 @@ void layout_smem(GlobalTopoHost* th) {
         return at;
     };
     const int n = d.n, N = d.N, nQ = d.nQ;
-    L.ld = nQ | 1;                                   // odd leading dimension: conflict-free column walks
+    // register-resident Gauss-Jordan path for up to 128 regulators, shared-memory LU beyond
+    L.tile = (force_generic || nQ > 16 * pk::GJ_MAX_TILE) ? 0 : (nQ <= 32 ? 2 : nQ <= 64 ? 4 : nQ <= 96 ? 6 : 8);
     L.par = take(th->P);
     L.Kt = take(d.K);
     L.Sall = take(d.S);
@@ -93,12 +95,53 @@ void layout_smem(GlobalTopoHost* th) {
     L.g = take(N);
     L.m = take(N);
     L.z = take(N);
-    L.Sc = take(nQ * L.ld);
-    L.idiag = take(nQ);
-    L.red = take(2 * pk::GLOBAL_WARPS + nQ);
-    L.perm = take((nQ + 1) / 2 + 1);
+    L.tfdata = take(nnzT);
+    L.tfdeg = take(N);
+    if (L.tile == 0) {
+        L.ld = nQ | 1;                               // odd leading dimension: conflict-free column walks
+        L.Sc = take(nQ * L.ld);
+        L.idiag = take(nQ);
+        L.red = take(2 * pk::GLOBAL_WARPS + nQ);
+        L.perm = take((nQ + 1) / 2 + 1);
+    } else {
+        const int GP = 16 * L.tile;
+        L.colbuf = take(2 * GP);
+        L.rowbuf = take(2 * GP);
+        L.bp = take(GP);
+        L.partial = take(16 * (GP + 1));
+        L.red = take(2 * pk::GLOBAL_WARPS);
+    }
+    L.ints = o;
+    int io = 0;
+    auto itake = [&](int count) {
+        const int at = io;
+        io += count;
+        return at;
+    };
+    L.i_offy = itake(N);
+    L.i_offs = itake(N);
+    L.i_ns = itake(N);
+    L.i_drv = itake(N);
+    L.i_qpos = itake(N);
+    L.i_tfptr = itake(N + 1);
+    L.i_tfidx = itake(nnzT);
+    L.i_qlist = itake(nQ);
+    L.i_piv = itake(16 * pk::GJ_MAX_TILE);
+    L.i_pinv = itake(16 * pk::GJ_MAX_TILE);
+    o += (io + 1) / 2;
     L.total = o;
     th->smem_bytes = (size_t)o * sizeof(double);
+}
+
+typedef void (*global_kernel_t)(const pk::GlobalArgs);
+global_kernel_t kernel_for_tile(int tile) {
+    switch (tile) {
+        case 2: return pk::global_net_kernel<2>;
+        case 4: return pk::global_net_kernel<4>;
+        case 6: return pk::global_net_kernel<6>;
+        case 8: return pk::global_net_kernel<8>;
+        default: return pk::global_net_kernel<0>;
+    }
 }
 
 }  // namespace
@@ -190,7 +233,7 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         delete th;
         return fail(std::string("pk_global_upload: ") + cudaGetErrorString(e));
     }
-    pkh::layout_smem(th);
+    pkh::layout_smem(th, nnzT, tp->force_generic_schur);
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     if (th->smem_bytes > (size_t)max_optin) {
@@ -387,9 +430,10 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     a.y0_stride = j->y0_stride;
     a.counter = h->counter;
 
-    CK(cudaFuncSetAttribute(pk::global_net_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th->smem_bytes));
+    const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th->smem_bytes));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk::global_net_kernel, pk::GLOBAL_BLOCK, th->smem_bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pk::GLOBAL_BLOCK, th->smem_bytes));
     if (per_sm < 1) return fail("pk_global_solve_batch: kernel does not fit on an SM");
     const int grid = (int)std::min<size_t>(B, (size_t)per_sm * h->sm_count);
 
@@ -423,7 +467,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     }
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(h->ev0, st));
-    pk::global_net_kernel<<<grid, pk::GLOBAL_BLOCK, th->smem_bytes, st>>>(a);
+    kern<<<grid, pk::GLOBAL_BLOCK, th->smem_bytes, st>>>(a);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(std::string("global_net_kernel launch: ") + cudaGetErrorString(le));
     CK(cudaEventRecord(h->ev1, st));

@@ -217,7 +217,7 @@ class Engine:
         return res
 
     # --------------------------------------------------------------------- global network
-    def global_upload(self, sys_):
+    def global_upload(self, sys_, force_generic=False):
         """Upload the static topology of a `GlobalSystem` (the array part of the reference's
         System.odeint_args(), global_model/network.py:508-526) once; returns the topology id."""
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -230,6 +230,7 @@ class Engine:
         tp.model, tp.N, tp.K, tp.n_bins = int(sys_.model), int(sys_.idx.N), int(sys_.K), int(arrs["kin_grid"].size)
         for k, a in arrs.items():
             setattr(tp, k, a.ctypes.data)
+        tp.force_generic_schur = int(bool(force_generic))
         tid = C.c_int32(-1)
         _lib.check(self.lib.pk_global_upload(self._h, C.byref(tp), C.byref(tid)))
         return tid.value

@@ -159,6 +159,22 @@ def test_per_system_initial_conditions_and_failures(engine):
     assert r["status"][3] != 0 and np.isnan(r["Y"][3]).all() and (np.delete(r["status"], 3) == 0).all()
 
 
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_generic_schur_path_agrees(engine, path):
+    """The shared-memory LU fallback (used beyond 128 regulators) against the register-resident
+    Gauss-Jordan path and the tight reference."""
+    g, s, _ = load_case(path)
+    topo = engine.global_upload(s, force_generic=True)
+    try:
+        r = engine.global_solve_batch(topo, g["params"], g["y0"], g["t"], ("Y",))
+    finally:
+        engine.global_release(topo)
+    assert (r["status"] == 0).all()
+    assert _ratio(r["Y"], g["Y_tight"], 1e-6, 1e-9) <= 1.0
+    fast = simulate_batch(s, g["params"], g["t"], ("Y",), y0=g["y0"], engine=engine)
+    assert np.allclose(r["Y"], fast["Y"], rtol=1e-7, atol=1e-10)
+
+
 def test_time_grid_subsets(engine):
     """t_eval need not contain the kinase-grid points: steps still land on them (same values at shared times)."""
     g, s, _ = load_case(FILES[2])
