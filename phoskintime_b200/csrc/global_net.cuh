@@ -20,7 +20,15 @@
 // the analytic Jacobian above, one factorisation per step; steps land exactly on every output time
 // and on every kinase-bucket boundary (the RHS is discontinuous there).
 #pragma once
+#include <type_traits>
+
 #include "pk_common.cuh"
+
+// Cycle-stamp hooks used only by tools/bench_gj.cu (which defines them before including this header).
+#ifndef GJ_TRACE
+#define GJ_TRACE_DECL
+#define GJ_TRACE(slot)
+#endif
 
 namespace pk {
 
@@ -399,7 +407,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
 // ------------------------------------------------------------------------------------------------
 template <int TILE>
 __device__ __forceinline__ void gj_assemble(const GlobalCtx& cx, double c, double (&A)[TILE][TILE]) {
-    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
     const int nQ = cx.nQ;
 #pragma unroll
     for (int a = 0; a < TILE; ++a) {
@@ -426,67 +434,148 @@ __device__ __forceinline__ void gj_assemble(const GlobalCtx& cx, double c, doubl
     }
 }
 
+// 1/x to within ~1 ulp without the IEEE division's special-case handling: MUFU.RCP64H seed (2^-23)
+// and two Newton steps.  x = 0 / inf / NaN give inf or NaN, which the step controller treats as a
+// failed (rejected) step.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// Pivot-search key of entry v in physical row r: FP32 magnitude with the low 7 mantissa bits replaced by
+// (127 - r), so ONE integer max (redux.sync) returns the largest entry and, on ties, the lowest row.
+__device__ __forceinline__ unsigned gj_key(double v, int r) {
+    return (__float_as_uint(fabsf((float)v)) & ~127u) | (unsigned)(127 - r);
+}
+
+// Uniform dispatch of a run-time value v in [LO, HI) to a compile-time constant through a binary tree of
+// branches.  The comparisons are opaque (inline PTX) so that the compiler cannot fold the tree back into a
+// jump table: BRX + indexed constant load measured ~200 cycles per dispatch on B200, the tree ~40.
+__device__ __forceinline__ bool opaque_lt(int x, int c) {
+    int f;
+    asm volatile("{ .reg .pred q; setp.lt.s32 q, %1, %2; selp.s32 %0, 1, 0, q; }" : "=r"(f) : "r"(x), "r"(c));
+    return f != 0;
+}
+template <int LO, int HI, class F>
+__device__ __forceinline__ void dispatch_uniform(int v, F&& f) {
+    if constexpr (HI - LO == 1) {
+        f(std::integral_constant<int, LO>{});
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        if (opaque_lt(v, MID)) dispatch_uniform<LO, MID>(v, f);
+        else dispatch_uniform<MID, HI>(v, f);
+    }
+}
+
 template <int TILE>
 __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE][TILE]) {
-    constexpr int GP = 16 * TILE;
-    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4, lane = threadIdx.x & 31;
+    constexpr int GP = 16 * TILE;            // padded order
+    constexpr int NW = (TILE + 1) / 2;       // pivot candidates per lane
+    const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4, lane = threadIdx.x & 31;
     const int nQ = cx.nQ;
-    unsigned mymask = 0;                 // bit w: physical row lane + 32 w has already served as a pivot row
+    unsigned mymask = 0;                     // bit w: physical row lane + 32 w has already served as a pivot row
+    GJ_TRACE_DECL
+    // Thread (tr, tc) = (tid & 15, tid >> 4): the 16 owners of one matrix ROW segment sit in one half-warp, so
+    // the pivot row reaches every thread by a warp shuffle; only the pivot COLUMN crosses warps, through shared
+    // memory, written by its 16 owner lanes at the end of the previous iteration (other parity buffer).
+    // => ONE block barrier per eliminated column.
+    // The loop body is kept SMALL (one copy, ~300 instructions): the column slots of the tile are rotated by one
+    // after every 16 columns so that the active column always sits in slot 0 (TILE rotations = identity), and the
+    // row slot of the pivot is resolved by one uniform branch tree.  (An unrolled body of 12 copies measured
+    // ~2x slower: the column sweep became instruction-fetch bound.)
+    if (nQ > 0 && tc == 0) {
 #pragma unroll
+        for (int a = 0; a < TILE; ++a) cx.colbuf[tr + 16 * a] = A[a][0];
+    }
+#pragma unroll 1
     for (int kb = 0; kb < TILE; ++kb) {
 #pragma unroll 1
         for (int kk = 0; kk < 16; ++kk) {
             const int k = kb * 16 + kk;
             if (k >= nQ) break;
-            double* colb = cx.colbuf + (k & 1) * GP;
-            double* rowb = cx.rowbuf + (k & 1) * GP;
-            if (tc == kk) {
-#pragma unroll
-                for (int a = 0; a < TILE; ++a) colb[tr + 16 * a] = A[a][kb];
-            }
+            const double* const colb = cx.colbuf + (kk & 1) * GP;
             __syncthreads();
-            // pivot search, redundantly in every warp (no broadcast barrier): FP32 magnitudes suffice
-            float best = -1.f;
-            int bi = 0;
+            GJ_TRACE(0)
+            double cv[TILE];                 // this thread's rows of column k
 #pragma unroll
-            for (int w = 0; w < (TILE + 1) / 2; ++w) {
+            for (int a = 0; a < TILE; ++a) cv[a] = colb[tr + 16 * a];
+            // Pivot search, redundantly in every warp.  Key = FP32 magnitude with the low 7 mantissa bits replaced
+            // by (127 - row): ONE integer max (redux.sync) returns the largest entry and, on ties, the lowest row.
+            // Used rows carry key 0; padded rows hold exact zeros and lose to any valid row.
+            unsigned key = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
                 const int r = lane + 32 * w;
-                if (r < nQ && !((mymask >> w) & 1u)) {
-                    const float v = fabsf((float)colb[r]);
-                    if (v > best) { best = v; bi = r; }
+                if (r < GP) {
+                    const unsigned kq = (__float_as_uint(fabsf((float)colb[r])) & ~127u) | (unsigned)(127 - r);
+                    key = max(key, ((mymask >> w) & 1u) ? 0u : kq);
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            const int p = bi;
+            key = __reduce_max_sync(0xffffffffu, key);
+            const int p = 127 - (int)(key & 127u);
+            GJ_TRACE(1)
             if ((p & 31) == lane) mymask |= 1u << (p >> 5);
             if (threadIdx.x == 0) { cx.piv[k] = p; cx.pinv[p] = k; }
-            if (tr == (p & 15)) {
-                const int pa = p >> 4;
-#pragma unroll
-                for (int a = 0; a < TILE; ++a)
-                    if (a == pa) {
-#pragma unroll
-                        for (int b = 0; b < TILE; ++b) rowb[tc + 16 * b] = A[a][b];
-                    }
-            }
-            __syncthreads();
-            const double ip = 1.0 / colb[p];
+            const double nip = -fast_rcp(colb[p]);        // -1/pivot
+            const int src = (lane & 16) | (p & 15);       // lane of this half-warp that owns row p
+            const bool prow = tr == (p & 15);
+            const bool pcol = tc == kk;
             double rv[TILE];
+            GJ_TRACE(2)
+            // Row p sits in register slot p >> 4 (uniform over the CTA).  Inside the dispatched block: fetch it,
+            // and arrange the operands so that the generic rank-1 update below ALSO produces the special entries:
+            //   column k  (threads tc == kk): A := 0, rv := 1        ->  fma(g, 1, 0) = g = -col/pivot
+            //   pivot row (lanes tr == p&15): A := -rv*nip, col := 0 ->  fma(0, rv, A) = row/pivot, 1/pivot at (p,k)
+            dispatch_uniform<0, TILE>(p >> 4, [&](auto slot) {
+                constexpr int a = decltype(slot)::value;
 #pragma unroll
-            for (int b = 0; b < TILE; ++b) rv[b] = rowb[tc + 16 * b];
+                for (int b = 0; b < TILE; ++b) rv[b] = __shfl_sync(0xffffffffu, A[a][b], src);
+                if (pcol) {
+                    rv[0] = 1.0;
+#pragma unroll
+                    for (int a2 = 0; a2 < TILE; ++a2) A[a2][0] = 0.0;
+                }
+                if (prow) {
+#pragma unroll
+                    for (int b = 0; b < TILE; ++b) A[a][b] = -rv[b] * nip;
+                    cv[a] = 0.0;
+                }
+            });
+            GJ_TRACE(3)
 #pragma unroll
             for (int a = 0; a < TILE; ++a) {
-                const int r = tr + 16 * a;
-                const double g = (r == p) ? (ip - 1.0) : -colb[r] * ip;
+                const double g = cv[a] * nip;
 #pragma unroll
                 for (int b = 0; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
-                if (tc == kk) A[a][kb] = (r == p) ? ip : g;
             }
+            GJ_TRACE(4)
+            // column k+1 for the next iteration (other parity: nobody reads that buffer any more); after column 15
+            // of a block it is the first column of the NEXT slot (the rotation below has not happened yet)
+            if (k + 1 < nQ) {
+                double* const coln = cx.colbuf + ((kk + 1) & 1) * GP;
+                if (kk < 15) {
+                    if (tc == kk + 1) {
+#pragma unroll
+                        for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][0];
+                    }
+                } else if (tc == 0) {
+#pragma unroll
+                    for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][TILE > 1 ? 1 : 0];
+                }
+            }
+            GJ_TRACE(5)
+        }
+        // rotate the column slots: slot b <- slot b+1 (executed TILE times in total = identity)
+#pragma unroll
+        for (int a = 0; a < TILE; ++a) {
+            const double t0 = A[a][0];
+#pragma unroll
+            for (int b = 0; b + 1 < TILE; ++b) A[a][b] = A[a][b + 1];
+            A[a][TILE - 1] = t0;
         }
     }
     __syncthreads();
@@ -497,7 +586,7 @@ template <int TILE>
 __device__ __forceinline__ void gj_apply(const GlobalCtx& cx, const double (&A)[TILE][TILE]) {
     constexpr int GP = 16 * TILE, PLD = GP + 1;
     const int nQ = cx.nQ;
-    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
     for (int l = threadIdx.x; l < GP; l += GLOBAL_BLOCK) cx.bp[l] = l < nQ ? cx.pvec[cx.qlist[cx.piv[l]]] : 0.0;
     __syncthreads();
     double bv[TILE];
@@ -707,14 +796,18 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
 
         // ------------------------------------------------------------------------ load
         {
+            // thread id re-read here: otherwise its 64-bit zero extension is kept alive (and spilled) across
+            // the register-resident factorisation just for this once-per-system addressing
+            int tid;
+            asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
             const long long sys = s_sys;
             const double* pr = a.params + (size_t)sys * P;
-            for (int i = threadIdx.x; i < P; i += GLOBAL_BLOCK) {
+            for (int i = tid; i < P; i += GLOBAL_BLOCK) {
                 const double v = pr[i];
                 cx.par[i] = a.theta_mode ? softplus_d(v) : v;         // params.py:106-132
             }
             const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
-            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = y0[i];
+            for (int i = tid; i < n; i += GLOBAL_BLOCK) y[i] = y0[i];
         }
         __syncthreads();
         cx.tfs = cx.par[P - 1];
