@@ -10,6 +10,10 @@ $(LIB): $(SRCS) $(HDRS)
 	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -Xptxas -v -shared -Xcompiler -fPIC -o $@ $(SRCS) -ldl 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -c "0 bytes spill stores" $(CSRC)/ptxas.log >/dev/null
 
+# debug build with per-phase cycle counters in the global-network kernel (tools/trace_global.py)
+trace: $(SRCS) $(HDRS)
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -DPK_GLOBAL_TRACE -shared -Xcompiler -fPIC -o phoskintime_b200/libphoskin_b200_trace.so $(SRCS) -ldl
+
 clean:
 	rm -f $(LIB) $(CSRC)/ptxas.log
-.PHONY: clean
+.PHONY: clean trace

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphoskin_b200.so")
+LIB_PATH = os.environ.get("PHOSKIN_LIB") or os.path.join(_HERE, "libphoskin_b200.so")   # PHOSKIN_LIB: debug builds
 
 PK_HOST, PK_DEVICE = 0, 1
 MODEL_IDS = {"distmod": 0, "succmod": 1, "randmod": 2}

@@ -30,6 +30,24 @@
 #define GJ_TRACE(slot)
 #endif
 
+// Per-phase cycle accounting of the step loop (debug build only: make trace -> libphoskin_b200_trace.so).
+#ifdef PK_GLOBAL_TRACE
+__device__ unsigned long long g_phase_cycles[16];
+#define PH_DECL long long ph_last_ = clock64();
+#define PH_ARG , ph_last_
+#define PH(i)                                                                          \
+    do {                                                                               \
+        __syncthreads();                                                               \
+        const long long ph_now_ = clock64();                                           \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[i] += (unsigned long long)(ph_now_ - ph_last_); \
+        ph_last_ = clock64();                                                          \
+    } while (0)
+#else
+#define PH_DECL
+#define PH_ARG
+#define PH(i)
+#endif
+
 namespace pk {
 
 struct GlobalTopoDev {
@@ -56,7 +74,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int colbuf, rowbuf, bp, partial;  // TILE  > 0: Schur matrix in registers (Gauss-Jordan), exchange buffers
     int tfdata, tfdeg;                // staged topology (doubles)
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
-    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv;
+    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent;
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
 };
 
@@ -130,29 +148,37 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return r;
 }
 
+// 1/x to within ~1 ulp without the IEEE division's special-case handling: MUFU.RCP64H seed (2^-23)
+// and two Newton steps.  x = 0 / inf / NaN give inf or NaN, which the step controller treats as a
+// failed (rejected) step.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // mRNA synthesis rate and its derivative w.r.t. the raw TF input v = (TF.p)_i / tf_deg_i.
 // models 0/1: the wrapper squashes once (jacspeedup.py:225-228), the kernel again (models.py:52);
 // model 4: only the kernel's squash (jacspeedup.py:371-373).  1e-6 in the denominator (models.py:58).
 __device__ __forceinline__ void synth_rate(int model, double v, double Ai, double tfs, double& synth, double& dsdv) {
-    double u_raw = v, du_raw = 1.0;
-    if (model != 4) {
-        const double q = 1.0 / (1.0 + fabs(v));
-        u_raw = v * q;
-        du_raw = q * q;
-    }
-    const double q2 = 1.0 / (1.0 + fabs(u_raw));
-    const double u = u_raw * q2;
-    double ds;
-    if (u >= 0.0) {
-        const double d = 1.0 / (1.0 + u + 1e-6);
-        synth = Ai * (1.0 + tfs * u * d);
-        ds = Ai * tfs * (1.0 + 1e-6) * d * d;
+    // u = squash(squash(v)) = v/(1+2|v|) for models 0/1, u = v/(1+|v|) for model 4; substituting into
+    // models.py:52-65 leaves ONE reciprocal for the rate and its derivative:
+    //   v >= 0:  A (1 + tfs v / D),          D = (1+1e-6) + ((1+1e-6) k + 1) v,   d/dv = A tfs (1+1e-6) / D^2
+    //   v <  0:  A (1 + k|v|) / D,           D = 1 + (k + tfs) |v|,               d/dv = A tfs / D^2
+    const double k = (model != 4) ? 2.0 : 1.0;
+    const double w = fabs(v);
+    if (v >= 0.0) {
+        const double r = fast_rcp(fma(fma(1.0 + 1e-6, k, 1.0), w, 1.0 + 1e-6));
+        synth = Ai * fma(tfs * w, r, 1.0);
+        dsdv = Ai * tfs * (1.0 + 1e-6) * r * r;
     } else {
-        const double d = 1.0 / (1.0 + tfs * fabs(u));
-        synth = Ai * d;
-        ds = Ai * tfs * d * d;
+        const double r = fast_rcp(fma(k + tfs, w, 1.0));
+        synth = Ai * fma(k, w, 1.0) * r;
+        dsdv = Ai * tfs * r * r;
     }
-    dsdv = ds * q2 * q2 * du_raw;
 }
 
 // lossfn.py:28-110 residual atoms as dispatched at lossfn.py:150-246
@@ -275,7 +301,8 @@ struct GlobalCtx {
     const double *cA, *cB, *cC, *cD, *cDp, *cE;      // views into par
     double tfs;
     // topology staged in shared memory once per CTA
-    const int *offy, *offs, *ns, *drv, *tfptr, *tfidx, *qlist, *qpos;
+    const int *offy, *offs, *ns, *drv, *tfptr, *tfidx, *qlist, *qpos, *sprot;
+    const unsigned char* ent;         // [TILE*TILE][256]: offset of entry (row slot a, col slot b) in its TF row, 255 = none
     const double *tfdata, *tfdeg;
     // Gauss-Jordan exchange buffers
     double *colbuf, *rowbuf, *bp, *partial;
@@ -303,7 +330,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
         const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
         double v = 0.0;
         for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) v = fma(cx.tfdata[q], cx.pvec[cx.tfidx[q]], v);
-        const double itd = 1.0 / cx.tfdeg[i];
+        const double itd = cx.tfdeg[i];                               // 1/tf_deg, inverted once at staging
         v *= itd;
         double synth, dsdv;
         synth_rate(model, v, cx.cA[i], cx.tfs, synth, dsdv);
@@ -323,7 +350,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
             dst[st + 1] = fma(Ci, R, fma(-(Di + sumS), P, Ei * back));
             dPP = -(Di + sumS);
         } else if (model == 4) {
-            const double iP = 1.0 / (1.0 + P), iR = 1.0 / (1.0 + R);
+            const double iP = fast_rcp(1.0 + P), iR = fast_rcp(1.0 + R);
             double sumS = 0.0, back = 0.0;
             for (int j = 0; j < ns; ++j) {
                 const double s = cx.Sall[ss + j], ps = src[st + 2 + j];
@@ -353,7 +380,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
         if (FACTOR) {
             cx.g[i] = dsdv * itd;
             // pivots: facA[st+1] (P0), facA[st+2+j] (site j); children are eliminated before parents
-            const double lo_scale = (model == 4) ? 1.0 / ((1.0 + P) * (1.0 + P)) : 1.0;
+            const double lo_scale = (model == 4) ? fast_rcp((1.0 + P) * (1.0 + P)) : 1.0;
             cx.facA[st + 1] = fma(-c, dPP, 1.0);
             for (int j = 0; j < ns; ++j) {
                 double dg;
@@ -363,7 +390,7 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
             }
             for (int j = ns - 1; j >= 0; --j) {
                 const int par = chain ? st + 1 + j : st + 1;
-                const double ip = 1.0 / cx.facA[st + 2 + j];
+                const double ip = fast_rcp(cx.facA[st + 2 + j]);
                 const double clo = c * cx.Sall[ss + j] * lo_scale;
                 const double mu = -c * Ei * ip;                         // A(par, j) / pivot_j
                 cx.facA[par] = fma(mu, clo, cx.facA[par]);              // pivot_par -= mu * A(j, par), A(j,par) = -clo
@@ -371,10 +398,10 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
                 cx.mult[st + 2 + j] = mu;
                 cx.clo[st + 2 + j] = clo;
             }
-            const double ipP = 1.0 / cx.facA[st + 1];
+            const double ipP = fast_rcp(cx.facA[st + 1]);
             cx.facA[st + 1] = ipP;
             cx.mult[st + 1] = c * cPR;
-            const double iRr = 1.0 / fma(c, Bi, 1.0);
+            const double iRr = fast_rcp(fma(c, Bi, 1.0));
             cx.facA[st] = iRr;
             // w = A^-1 e_R for this block, m_i = total-protein response
             cx.w[st] = iRr;
@@ -407,49 +434,31 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
 // ------------------------------------------------------------------------------------------------
 template <int TILE>
 __device__ __forceinline__ void gj_assemble(const GlobalCtx& cx, double c, double (&A)[TILE][TILE]) {
-    const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
+    // Which TF entry (if any) lands in each of this thread's TILE x TILE slots is static: it was resolved once per
+    // CTA into cx.ent (offset inside the regulated gene's CSR row, 255 = structurally zero), so assembling
+    // Sc = I - c diag(m g) G is one byte load + one multiply per slot, with no search and no divergence.
+    // (thread id re-read through volatile asm: otherwise the loop-invariant diagonal tests are hoisted out of the
+    //  step loop as a packed predicate register that then lives - and spills - across the whole kernel)
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int tr = tid & 15, tc = tid >> 4;
     const int nQ = cx.nQ;
+    const unsigned char* ent = cx.ent + tid;
 #pragma unroll
     for (int a = 0; a < TILE; ++a) {
-#pragma unroll
-        for (int b = 0; b < TILE; ++b) A[a][b] = 0.0;
         const int r = tr + 16 * a;
-        if (r < nQ) {
-            const int i = cx.qlist[r];
-            const double f = -c * cx.m[i] * cx.g[i];
-            for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) {
-                const int qj = cx.qpos[cx.tfidx[q]];
-                if (qj >= 0 && (qj & 15) == tc) {
-                    const double v = f * cx.tfdata[q];
-                    const int bb = qj >> 4;
+        const bool live = r < nQ;
+        const int i = live ? cx.qlist[r] : 0;
+        const int base = cx.tfptr[i];
+        const double f = live ? -c * cx.m[i] * cx.g[i] : 0.0;
 #pragma unroll
-                    for (int b = 0; b < TILE; ++b)
-                        if (b == bb) A[a][b] += v;
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < TILE; ++b)
-                if (r == tc + 16 * b) A[a][b] += 1.0;
+        for (int b = 0; b < TILE; ++b) {
+            const unsigned off = ent[(a * TILE + b) * GLOBAL_BLOCK];
+            double v = (off != 255u) ? f * cx.tfdata[base + off] : 0.0;
+            if (live && r == tc + 16 * b) v += 1.0;
+            A[a][b] = v;
         }
     }
-}
-
-// 1/x to within ~1 ulp without the IEEE division's special-case handling: MUFU.RCP64H seed (2^-23)
-// and two Newton steps.  x = 0 / inf / NaN give inf or NaN, which the step controller treats as a
-// failed (rejected) step.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
-
-// Pivot-search key of entry v in physical row r: FP32 magnitude with the low 7 mantissa bits replaced by
-// (127 - r), so ONE integer max (redux.sync) returns the largest entry and, on ties, the lowest row.
-__device__ __forceinline__ unsigned gj_key(double v, int r) {
-    return (__float_as_uint(fabsf((float)v)) & ~127u) | (unsigned)(127 - r);
 }
 
 // Uniform dispatch of a run-time value v in [LO, HI) to a compile-time constant through a binary tree of
@@ -697,7 +706,11 @@ __device__ __forceinline__ void lu_apply(const GlobalCtx& cx) {
 
 // x (vector in shared memory, holds the right-hand side b) <- (I - cJ)^-1 b
 template <int TILE>
-__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1]) {
+__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1]
+#ifdef PK_GLOBAL_TRACE
+                                            , long long& ph_last_
+#endif
+) {
     const int N = cx.N;
     const bool chain = cx.model == 1;
     // block solves x0 = A^-1 b and z0 (into pvec)
@@ -725,19 +738,22 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
         cx.z[i] = 0.0;
     }
     __syncthreads();
+    PH(10);
     if (cx.nQ > 0) {
         if constexpr (TILE > 0) gj_apply<TILE>(cx, A);
         else lu_apply(cx);
     }
-    // x += c (G z)_i w_i
+    PH(11);
+    // x += c (G z)_i w_i : the gene-level factor per protein, then one thread per state
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
         double gz = 0.0;
         for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) gz = fma(cx.tfdata[q], cx.z[cx.tfidx[q]], gz);
-        gz *= c * cx.g[i];
-        const int st = cx.offy[i], ns = cx.ns[i];
-        for (int s = st; s < st + 2 + ns; ++s) x[s] = fma(gz, cx.w[s], x[s]);
+        cx.pvec[i] = gz * c * cx.g[i];
     }
     __syncthreads();
+    for (int s = threadIdx.x; s < cx.n; s += GLOBAL_BLOCK) x[s] = fma(cx.pvec[cx.sprot[s]], cx.w[s], x[s]);
+    __syncthreads();
+    PH(12);
 }
 
 template <int TILE>
@@ -755,7 +771,8 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                  smem + L.Sc, smem + L.idiag, smem + L.red, (int*)(smem + L.perm), L.ld, n, N, tp.nQ, tp.model,
                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
                  ismem + L.i_offy, ismem + L.i_offs, ismem + L.i_ns, ismem + L.i_drv, ismem + L.i_tfptr, ismem + L.i_tfidx,
-                 ismem + L.i_qlist, ismem + L.i_qpos, smem + L.tfdata, smem + L.tfdeg,
+                 ismem + L.i_qlist, ismem + L.i_qpos, ismem + L.i_sprot, (const unsigned char*)(ismem + L.i_ent),
+                 smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv};
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
@@ -768,6 +785,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
     double* const U = cx.U;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double A[TILE ? TILE : 1][TILE ? TILE : 1];        // Schur block / its inverse (register resident)
+    PH_DECL
 
     // topology -> shared memory, once per CTA (the CTA is persistent over its systems)
     {
@@ -778,7 +796,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
             ismem[L.i_ns + i] = tp.n_sites[i];
             ismem[L.i_drv + i] = tp.driver_map[i];
             ismem[L.i_qpos + i] = tp.qpos[i];
-            smem[L.tfdeg + i] = tp.tf_deg[i];
+            smem[L.tfdeg + i] = 1.0 / tp.tf_deg[i];
         }
         for (int i = threadIdx.x; i <= N; i += GLOBAL_BLOCK) ismem[L.i_tfptr + i] = tp.TF_indptr[i];
         for (int q = threadIdx.x; q < nnz; q += GLOBAL_BLOCK) {
@@ -786,6 +804,27 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
             smem[L.tfdata + q] = tp.TF_data[q];
         }
         for (int q = threadIdx.x; q < tp.nQ; q += GLOBAL_BLOCK) ismem[L.i_qlist + q] = tp.qlist[q];
+        for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {          // state -> protein map
+            const int st = tp.offset_y[i], ns = tp.n_sites[i];
+            for (int j = 0; j < 2 + ns; ++j) ismem[L.i_sprot + st + j] = i;
+        }
+        if constexpr (TILE > 0) {
+            // static sparsity of the Schur block as seen by this thread's tile (see gj_assemble); rows of the uploaded
+            // TF matrix have unique column indices (pk_global_upload merges duplicates)
+            unsigned char* ent = (unsigned char*)(ismem + L.i_ent);
+            const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
+            for (int a = 0; a < TILE; ++a)
+                for (int b = 0; b < TILE; ++b) {
+                    const int r = tr + 16 * a, cq = tc + 16 * b;
+                    unsigned off = 255u;
+                    if (r < tp.nQ && cq < tp.nQ) {
+                        const int i = tp.qlist[r], j = tp.qlist[cq];
+                        for (int q = tp.TF_indptr[i]; q < tp.TF_indptr[i + 1]; ++q)
+                            if (tp.TF_indices[q] == j) { off = (unsigned)(q - tp.TF_indptr[i]); break; }
+                    }
+                    ent[(a * TILE + b) * GLOBAL_BLOCK + threadIdx.x] = (unsigned char)off;
+                }
+        }
     }
 
     for (;;) {
@@ -886,43 +925,59 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
 #define STEP_C (S_.hh * G_GAMMA)
 
                 // stage 1: f(y), Jacobian pieces, factorisation
+                PH(0);
                 eval_rhs<true>(cx, y, U, STEP_C);
+                PH(1);
                 if (cx.nQ > 0) {
                     if constexpr (TILE > 0) {
                         gj_assemble<TILE>(cx, STEP_C, A);
+                        PH(2);
                         gj_invert<TILE>(cx, A);
                     } else {
                         schur_factor(cx, STEP_C);
                     }
                 }
+                PH(3);
                 {
                     const double c = STEP_C;
                     for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) U[i] *= c;
                 }
                 __syncthreads();
-                schur_solve<TILE>(cx, U, STEP_C, A);
+                PH(4);
+                schur_solve<TILE>(cx, U, STEP_C, A PH_ARG);
                 // stages 2..6:  (I - cJ) U_s = c ( f(y + sum a_sj U_j) + sum c_sj/h U_j )
 #pragma unroll 1
                 for (int s = 1; s < 6; ++s) {
-                    for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
-                        double v = y[i];
-                        for (int j = 0; j < s && j < 4; ++j) v = fma(G_A[s - 1][j], U[j * n + i], v);
-                        if (s == 5) v += U[4 * n + i];
-                        arg[i] = v;
-                    }
+                    // stage number -> compile-time constant (uniform branch tree): the tableau entries become
+                    // constant-bank operands of the FMAs, no registers and no dependent constant loads
+                    dispatch_uniform<1, 6>(s, [&](auto S) {
+                        constexpr int sc = decltype(S)::value;
+                        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
+                            double v = y[i];
+#pragma unroll
+                            for (int j = 0; j < (sc < 4 ? sc : 4); ++j) v = fma(G_A[sc - 1][j], U[j * n + i], v);
+                            if (sc == 5) v += U[4 * n + i];
+                            arg[i] = v;
+                        }
+                    });
                     __syncthreads();
+                    PH(5);
                     double* Us = U + s * n;
                     eval_rhs<false>(cx, arg, Us, 0.0);
-                    {
-                        const double c = STEP_C, gam = G_GAMMA;              // gam = c/h
+                    PH(6);
+                    dispatch_uniform<1, 6>(s, [&](auto S) {
+                        constexpr int sc = decltype(S)::value;
+                        const double c = STEP_C;
                         for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
-                            double v = 0.0;
-                            for (int j = 0; j < s; ++j) v = fma(G_C[s - 1][j], U[j * n + i], v);
-                            Us[i] = fma(c, Us[i], gam * v);
+                            double v = c * Us[i];
+#pragma unroll
+                            for (int j = 0; j < sc; ++j) v = fma(G_C[sc - 1][j] * G_GAMMA, U[j * n + i], v);   // gamma = c/h
+                            Us[i] = v;
                         }
-                    }
+                    });
                     __syncthreads();
-                    schur_solve<TILE>(cx, Us, STEP_C, A);
+                    PH(7);
+                    schur_solve<TILE>(cx, Us, STEP_C, A PH_ARG);
                 }
                 // y_new = arg_6 + U_6, err = U_6
                 float err = 0.f;
@@ -976,6 +1031,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                 if (accept)
                     for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = arg[i];
                 __syncthreads();
+                PH(9);
             }
 #undef STEP_C
             if (S_.status == 0) {

@@ -4,6 +4,7 @@
 // that replaces a loop of simulate_odeint (global_model/simulate.py:34-80).
 #include <algorithm>
 #include <cmath>
+#include <utility>
 
 #include "pk_internal.hpp"
 
@@ -128,6 +129,8 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     L.i_qlist = itake(nQ);
     L.i_piv = itake(16 * pk::GJ_MAX_TILE);
     L.i_pinv = itake(16 * pk::GJ_MAX_TILE);
+    L.i_sprot = itake(n);
+    L.i_ent = itake(L.tile * L.tile * pk::GLOBAL_BLOCK / 4);    // one byte per tile slot and thread
     o += (io + 1) / 2;
     L.total = o;
     th->smem_bytes = (size_t)o * sizeof(double);
@@ -191,12 +194,29 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         if (!(tp->kin_grid[b] > tp->kin_grid[b - 1])) return fail("pk_global_upload: kin_grid must be strictly increasing");
     CK(cudaSetDevice(h->device));
 
+    // canonical TF rows for the device: column indices sorted and unique (duplicates summed) — the kernel's static
+    // sparsity table of the Schur block needs at most one entry per (gene, regulator)
+    std::vector<int> tf_ptr(N + 1, 0), tf_idx;
+    std::vector<double> tf_val;
+    for (int i = 0; i < N; ++i) {
+        std::vector<std::pair<int, double>> row;
+        for (int q = tp->TF_indptr[i]; q < tp->TF_indptr[i + 1]; ++q) row.emplace_back(tp->TF_indices[q], tp->TF_data[q]);
+        std::stable_sort(row.begin(), row.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+        for (size_t e = 0; e < row.size(); ++e) {
+            if (!tf_idx.empty() && (int)tf_idx.size() > tf_ptr[i] && tf_idx.back() == row[e].first) tf_val.back() += row[e].second;
+            else { tf_idx.push_back(row[e].first); tf_val.push_back(row[e].second); }
+        }
+        tf_ptr[i + 1] = (int)tf_idx.size();
+        if (tf_ptr[i + 1] - tf_ptr[i] > 254) return fail("pk_global_upload: a gene has more than 254 distinct regulators");
+    }
+    const int nnzC = (int)tf_idx.size();
+
     // regulator set Q: non-driven proteins whose total protein enters some gene's TF input
     std::vector<int> qpos(N, -1), qlist;
     {
         std::vector<char> used(N, 0);
-        for (int q = 0; q < nnzT; ++q)
-            if (tp->TF_data[q] != 0.0) used[tp->TF_indices[q]] = 1;
+        for (int q = 0; q < nnzC; ++q)
+            if (tf_val[q] != 0.0) used[tf_idx[q]] = 1;
         for (int i = 0; i < N; ++i)
             if (used[i] && tp->driver_map[i] < 0) {
                 qpos[i] = (int)qlist.size();
@@ -219,9 +239,9 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     UP(W_indptr, tp->W_indptr, S + 1);
     UP(W_indices, tp->W_indices, nnzW);
     UP(W_data, tp->W_data, nnzW);
-    UP(TF_indptr, tp->TF_indptr, N + 1);
-    UP(TF_indices, tp->TF_indices, nnzT);
-    UP(TF_data, tp->TF_data, nnzT);
+    UP(TF_indptr, tf_ptr.data(), N + 1);
+    UP(TF_indices, tf_idx.data(), nnzC);
+    UP(TF_data, tf_val.data(), nnzC);
     UP(kin_grid, tp->kin_grid, nb);
     UP(kin_Kmat, tp->kin_Kmat, (size_t)K * nb);
     UP(tf_deg, tp->tf_deg, N);
@@ -233,7 +253,7 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         delete th;
         return fail(std::string("pk_global_upload: ") + cudaGetErrorString(e));
     }
-    pkh::layout_smem(th, nnzT, tp->force_generic_schur);
+    pkh::layout_smem(th, nnzC, tp->force_generic_schur);
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     if (th->smem_bytes > (size_t)max_optin) {
@@ -526,5 +546,15 @@ int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const
     CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }
+
+#ifdef PK_GLOBAL_TRACE
+// debug build only: per-phase cycle totals of CTA 0 (see PH() in global_net.cuh); reading clears them
+int pk_global_trace_read(unsigned long long* out16) {
+    unsigned long long zero[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(zero)) != cudaSuccess) return fail("trace read failed");
+    if (cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero)) != cudaSuccess) return fail("trace clear failed");
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -99,6 +99,63 @@ __global__ void __launch_bounds__(256) probes(long long* out, double* sink, doub
     }
     t1 = clock64();
     if (threadIdx.x == 0) out[7] = (t1 - t0) / 64;
+    // (i) column-step skeleton: barrier, 6 LDS, 6 DMUL, 36 DFMA, owner publish (6 STS by 16 lanes)
+    {
+        const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
+        t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it) {
+            const double* colb = sh + (it & 1) * 96;
+            __syncthreads();
+            double cv[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cv[i] = colb[tr + 16 * i];
+            const double nip = colb[it % 96] + 2.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double gg = cv[i] * nip;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a[i * 6 + j] = fma(gg, r, a[i * 6 + j]);
+            }
+            if (tc == ((it + 1) & 15)) {
+                double* coln = sh + ((it + 1) & 1) * 96;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) coln[tr + 16 * i] = a[i * 6];
+            }
+        }
+        t1 = clock64();
+        if (threadIdx.x == 0) out[8] = (t1 - t0) / 64;
+    }
+    // (j) same plus 12 shuffles (pivot-row gather) before the FMAs
+    {
+        const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4;
+        t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it) {
+            const double* colb = sh + (it & 1) * 96;
+            __syncthreads();
+            double cv[6], rv[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cv[i] = colb[tr + 16 * i];
+            const double nip = colb[it % 96] + 2.0;
+            const int src = (lane & 16) | (it & 15);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) rv[j] = __shfl_sync(0xffffffffu, a[j], src);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double gg = cv[i] * nip;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a[i * 6 + j] = fma(gg, rv[j], a[i * 6 + j]);
+            }
+            if (tc == ((it + 1) & 15)) {
+                double* coln = sh + ((it + 1) & 1) * 96;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) coln[tr + 16 * i] = a[i * 6];
+            }
+        }
+        t1 = clock64();
+        if (threadIdx.x == 0) out[9] = (t1 - t0) / 64;
+    }
     for (int i = 0; i < 36; ++i) s += a[i];
     sink[blockIdx.x * 256 + threadIdx.x] = s;
 }
@@ -108,10 +165,10 @@ int main() {
     for (int ctas : {1, 148, 296}) {
         probes<<<ctas, 256>>>(out, sink, 1.5);
         cudaDeviceSynchronize();
-        long long h[8];
-        cudaMemcpy(h, out, 64, cudaMemcpyDeviceToHost);
-        printf("ctas=%d (256 thr): 36 indep DFMA %lld | 16 dep DFMA %lld | STS+BAR+LDS+BAR %lld | dep LDS %lld | redux %lld | F2F x2+DADD %lld | rcp %lld | update(12 LDS+6 DMUL+36 DFMA) %lld cycles\n",
-               ctas, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        long long h[10];
+        cudaMemcpy(h, out, 80, cudaMemcpyDeviceToHost);
+        printf("ctas=%d (256 thr): 36 indep DFMA %lld | 16 dep DFMA %lld | STS+BAR+LDS+BAR %lld | dep LDS %lld | redux %lld | F2F x2+DADD %lld | rcp %lld | update(12 LDS+6 DMUL+36 DFMA) %lld | skeleton %lld | skeleton+shfl %lld cycles\n",
+               ctas, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
     }
     return 0;
 }
