@@ -1,3 +1,5 @@
 """Global coupled kinase-TF-protein network path."""
 from .network import GlobalSystem, synthetic_system, synthetic_loss_data  # noqa: F401
-from .simulate import LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint  # noqa: F401
+from .simulate import LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint, solve_custom  # noqa: F401
+from .optproblem import GlobalODE_MOO, init_raw_params, unpack_params  # noqa: F401
+from .sensitivity import compute_bounds, run_sensitivity_analysis  # noqa: F401

@@ -57,6 +57,15 @@ def simulate_odeint(sys, t_eval, rtol, atol, mxstep):
     return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
 
 
+def solve_custom(sys, y0, t_eval, rtol, atol):
+    """Reference signature of the `USE_CUSTOM_SOLVER` branch (global_model/jacspeedup.py:31-67, used at
+    simulate.py:55-58): explicit y0, current parameters of `sys` -> Y[T, state_dim].  The reference integrates
+    this branch with its Numba DOPRI5 (solvers.py:292-758); here it is the same kernel as `simulate_odeint`."""
+    res = simulate_batch(sys, sys.pack_params()[None, :], np.asarray(t_eval, dtype=np.float64), ("Y",),
+                         y0=np.asarray(y0, dtype=np.float64), rtol=rtol, atol=atol)
+    return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
+
+
 def metric_time_indices(times, t_points_p, t_points_r, t_points_pho):
     """Which rows of the union grid `times` simulate_and_measure keeps per modality (simulate.py:107-124,
     :189-200) and the three baseline rows."""

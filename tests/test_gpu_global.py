@@ -22,8 +22,10 @@ from conftest import GOLDEN, ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import global_models as og  # noqa: E402
-from phoskintime_b200.global_model import (LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint,  # noqa: E402
-                                           synthetic_loss_data, synthetic_system)
+from phoskintime_b200.global_model import (LOSS_FN, GlobalODE_MOO, init_raw_params, metric_time_indices,  # noqa: E402
+                                           run_sensitivity_analysis, simulate_batch, simulate_odeint, solve_custom,
+                                           synthetic_loss_data, synthetic_system, unpack_params)
+import morris as omorris  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "global_*.npz")))
@@ -213,3 +215,55 @@ def test_full_size_network_sanity(engine):
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert np.isfinite(a["Y"]).all() and (a["Y"] > -1e-9).all()
     assert _ratio(a["Y"], b["Y"], 1e-6, 1e-9) <= 1.0
+
+
+def test_solve_custom_signature(engine):
+    g, s, _ = load_case(FILES[2])
+    s.update(**s.unpack_params(g["params"][2]))
+    Y = solve_custom(s, g["y0"] * 1.0, g["t"], 1e-6, 1e-9)
+    assert _ratio(Y, g["Y_tight"][2], 1e-6, 1e-9) <= 1.0
+
+
+def test_population_objectives_match_oracle(engine):
+    """GlobalODE_MOO.evaluate_batch: raw thetas -> softplus, prior, solve, loss, normalised objectives on the
+    device vs the oracle's objectives (optproblem.py:87-160) evaluated on the device trajectories."""
+    g, s, ld = load_case(FILES[0])
+    net = s.as_dict()
+    bounds = {k: (1e-4, 50.0) for k in ("c_k", "A_i", "B_i", "C_i", "D_i", "Dp_i", "E_i", "tf_scale")}
+    theta0, slices, xl, xu = init_raw_params(s.defaults, bounds)
+    lam = {"protein": 1.0, "rna": 0.5, "phospho": 2.0, "prior": 0.1}
+    prob = GlobalODE_MOO(s, slices, ld, s.defaults, lam, g["t"], xl, xu, engine=engine)
+    rng = np.random.default_rng(3)
+    X = theta0[None, :] + 0.3 * rng.standard_normal((6, theta0.size))
+    X[5, 0] = np.nan                                             # a broken individual
+    F = prob.evaluate_batch(X)
+    assert F.shape == (6, 3) and (F[5] == 1e12).all()
+    for b in range(5):
+        p = unpack_params(X[b], slices)
+        Y = simulate_batch(s, s.pack_params(p)[None], g["t"], ("Y",), engine=engine)["Y"][0]
+        ref = og.objectives(og.loss_noncomb(Y, ld, 0), ld, p, net["defaults"], (1.0, 0.5, 2.0), 0.1)
+        assert np.allclose(F[b], ref, rtol=1e-9, atol=1e-12), (b, F[b], ref)
+    out = {}
+    prob._evaluate(X[1], out)
+    assert np.array_equal(out["F"], F[1]) and np.allclose(s.pack_params(), s.pack_params(unpack_params(X[1], slices)))
+
+
+def test_global_morris_ranking_matches_oracle(engine):
+    """Morris mu*/sigma of the fused scalar metric vs the oracle pipeline (reference trajectories' metric through
+    the restated SALib analysis) on the SAME sample X: identical ranking of the influential parameters."""
+    g, s, _ = load_case(FILES[0])
+    net = s.as_dict()
+    s.update(**s.unpack_params(g["params"][0]))
+    res = run_sensitivity_analysis(s, metric="total_signal", N=3, num_levels=4, seed=11, engine=engine)
+    X, D = res["X"], len(res["names"])
+    assert X.shape == (3 * (D + 1), D) and (res["status"] == 0).all()
+    times = np.unique(np.concatenate([T_PROT, T_RNA]))
+    mt = metric_time_indices(times, T_PROT, T_RNA, T_PROT)
+    rows = np.arange(0, X.shape[0], 7)                            # the oracle solves a subset of rows (LSODA is slow)
+    for r in rows:
+        Y = og.simulate_odeint(0, net, times, 1e-8, 1e-8, 200000, params=og.unpack_params(X[r], net))
+        assert np.isclose(res["Y"][r], og.scalar_metric(Y, net, mt, "total_signal"), rtol=2e-5), r
+    Si = omorris.analyze(X, res["Y"], D, num_levels=4, scaled=False)
+    assert np.allclose(res["mu_star"], Si["mu_star"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(res["sigma"], Si["sigma"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(res["order"][:10], np.argsort(-Si["mu_star"], kind="stable")[:10])
