@@ -69,6 +69,9 @@ class ShardedRun:
             return local
         is_np = isinstance(local, np.ndarray)
         loc = torch.from_numpy(np.ascontiguousarray(local)) if is_np else local.contiguous()
+        host_in = not loc.is_cuda
+        if host_in and self.backend == "nccl":               # host results on a GPU run: stage through this rank's GPU
+            loc = loc.cuda(self.local_rank)
         inner = int(np.prod(loc.shape[1:])) if loc.dim() > 1 else 1
         pad = max(sizes)
         send = torch.zeros((pad,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
@@ -82,6 +85,8 @@ class ShardedRun:
         parts = [recv[r * pad:r * pad + sizes[r]] for r in range(self.world)]
         full = torch.cat(parts, dim=0)
         assert full.shape[0] == total and inner >= 1
+        if host_in and full.is_cuda:
+            full = full.cpu()
         return full.numpy() if is_np else full
 
     def barrier(self):
