@@ -148,18 +148,6 @@ __device__ __forceinline__ double block_sum_d(double v, double* red) {
     return r;
 }
 
-// 1/x to within ~1 ulp without the IEEE division's special-case handling: MUFU.RCP64H seed (2^-23)
-// and two Newton steps.  x = 0 / inf / NaN give inf or NaN, which the step controller treats as a
-// failed (rejected) step.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
-
 // mRNA synthesis rate and its derivative w.r.t. the raw TF input v = (TF.p)_i / tf_deg_i.
 // models 0/1: the wrapper squashes once (jacspeedup.py:225-228), the kernel again (models.py:52);
 // model 4: only the kernel's squash (jacspeedup.py:371-373).  1e-6 in the denominator (models.py:58).

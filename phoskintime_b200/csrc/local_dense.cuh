@@ -1,11 +1,15 @@
-// Warp-per-system RODAS4 kernel with a dense shared-memory LU: the random (2^ns-state hypercube)
+// Warp-per-system kernel with a dense shared-memory inverse: the random (2^ns-state hypercube)
 // model (models/randmod.py) and distributive / successive systems too large for the
-// register-resident kernel.  One warp owns one system: W = I/(h*gamma) - J is assembled in shared
-// memory from the analytic Jacobian (the models are linear, J is the transition-rate matrix),
-// factorised in place (right-looking LU, lanes own columns of the trailing block, no pivoting:
-// for non-negative rates W is strictly column diagonally dominant once the decoupled mRNA row is
-// removed), and the six stage systems are solved by substitution with the stage vector in shared
-// memory.  Warps pull systems from the global queue as they finish.
+// register-resident kernel.  One warp owns one system: W = I - h*gamma*M is assembled in shared
+// memory from the analytic Jacobian (the models are linear, M is the transition-rate matrix) and
+// INVERTED in place (Gauss-Jordan, lanes own columns, no pivoting: for non-negative rates W is
+// strictly column diagonally dominant once the decoupled mRNA row is removed; zero multipliers are
+// skipped, so the early sparse columns are cheap).  The six Krylov vectors of a step, v_k = W^-1
+// v_{k-1}, are then lane-parallel mat-vecs instead of sequential triangular solves, and — because
+// the models are linear with constant coefficients — W^-1 depends on the step size only: proposed
+// steps are rounded down to a geometric grid (ratio 2^(1/HQ)), so consecutive steps share one
+// inverse and a solve needs ~50 inversions for ~120 steps.  Warps pull systems from the global
+// queue as they finish.
 #pragma once
 #include "pk_common.cuh"
 
@@ -14,21 +18,28 @@ namespace pk {
 struct DenseLayout {       // per-warp shared-memory carve-up, in doubles
     int n, ld, P, nobs;
     __host__ __device__ int W() const { return 0; }
-    __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..3: y, v, y_new, err
-    __host__ __device__ int par() const { return n * ld + 4 * n; }
+    __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..4: y, v, y_new, err, v'
+    __host__ __device__ int par() const { return n * ld + 5 * n; }
     __host__ __device__ int prev() const { return par() + P; }
     __host__ __device__ int total() const { return prev() + nobs; }
 };
 
+// NT threads (1, 2 or 4 warps) cooperate on one system.
+template <int NT>
+__device__ __forceinline__ void dsync() {
+    if (NT > 32) __syncthreads();
+    else __syncwarp();
+}
+
 // ------------------------------------------------------------------ model: rhs and W assembly
 // p = physical parameters in shared memory.  All functions are warp-cooperative (lane strided).
-template <int MODEL>
+template <int MODEL, int NT>
 __device__ __forceinline__ void dense_rhs(int ns, int n, const double* p, const double* y, double* f, int lane) {
     if (MODEL == 2) {
         const double* S = p + 4;
         const double* Dd = p + 4 + ns;
         const double Pv = y[1];
-        for (int r = lane; r < n; r += 32) {
+        for (int r = lane; r < n; r += NT) {
             double v;
             if (r == 0) v = fma(-p[1], y[0], p[0]);
             else if (r == 1) {
@@ -58,7 +69,7 @@ __device__ __forceinline__ void dense_rhs(int ns, int n, const double* p, const 
     } else {
         const double* S = p + 4;
         const double* Dr = p + 4 + ns;
-        for (int r = lane; r < n; r += 32) {
+        for (int r = lane; r < n; r += NT) {
             double v;
             if (r == 0) v = fma(-p[1], y[0], p[0]);
             else if (MODEL == 0) {
@@ -84,12 +95,12 @@ __device__ __forceinline__ void dense_rhs(int ns, int n, const double* p, const 
 }
 
 // W = I - c*J (row-major, leading dimension ld), c = h*gamma.  Each lane assembles whole rows.
-template <int MODEL>
+template <int MODEL, int NT>
 __device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double* p, double c, double* W, int lane) {
-    for (int idx = lane; idx < n * ld; idx += 32) W[idx] = 0.0;
-    __syncwarp();
+    for (int idx = lane; idx < n * ld; idx += NT) W[idx] = 0.0;
+    dsync<NT>();
     const double* S = p + 4;
-    for (int r = lane; r < n; r += 32) {
+    for (int r = lane; r < n; r += NT) {
         double* row = W + r * ld;
         if (r == 0) { row[0] = fma(c, p[1], 1.0); continue; }
         if (MODEL == 2) {
@@ -133,43 +144,111 @@ __device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double*
             }
         }
     }
-    __syncwarp();
+    dsync<NT>();
 }
 
-// In-place LU (unit lower), no pivoting.  Lanes own columns of the trailing block; the pivot row
-// element stays in a register while the lane walks down its column.
-__device__ __forceinline__ void dense_lu(int n, int ld, double* W, int lane) {
-    for (int k = 0; k < n - 1; ++k) {
-        const double ipiv = 1.0 / W[k * ld + k];
-        for (int i = k + 1 + lane; i < n; i += 32) W[i * ld + k] *= ipiv;
-        __syncwarp();
-        for (int j = k + 1 + lane; j < n; j += 32) {
-            const double ukj = W[k * ld + j];
-            if (ukj != 0.0) {
-                for (int i = k + 1; i < n; ++i) {
-                    double* wij = W + i * ld + j;
-                    *wij = fma(-W[i * ld + k], ukj, *wij);
-                }
+constexpr int DENSE_HQ = 2;       // step-size grid: 2^(j/DENSE_HQ)
+
+// largest grid value <= h
+__device__ __forceinline__ double dense_quantize_h(double h) {
+    if (!(h > 0.0) || !(h < 1.0e300)) return h;
+    return exp2(floor(log2(h) * (double)DENSE_HQ) * (1.0 / (double)DENSE_HQ));
+}
+
+// In-place inverse by Gauss-Jordan elimination without pivoting.  Thread (tx, ty) = (tid & 31, tid >> 5) updates
+// columns tx, tx+32, ... of rows ty, ty+NW, ...; column k (multipliers) and the scaled pivot row are staged in
+// `colk` / `rowk` so that the whole matrix can be rewritten in one sweep.  Zero multipliers / zero pivot-row
+// entries are skipped (the early columns of I - c M are sparse).
+template <int NT>
+__device__ __forceinline__ void dense_invert(int n, int ld, double* W, double* colk, double* rowk, int tid) {
+    constexpr int NW = NT / 32;
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int k = 0; k < n; ++k) {
+        const double ipiv = fast_rcp(W[k * ld + k]);
+        dsync<NT>();                                                   // everyone has the pivot before it is overwritten
+        for (int i = tid; i < n; i += NT) {
+            colk[i] = (i == k) ? 0.0 : W[i * ld + k];
+            rowk[i] = (i == k) ? 0.0 : W[k * ld + i] * ipiv;
+        }
+        dsync<NT>();
+        // Columns 1.. are dealt to the lanes as j = 1 + tx + 32 c (the random model has 2^ns - 1 + 2 states: 64
+        // columns besides the mRNA column 0, i.e. exactly two per lane); this thread's pivot-row entries stay in
+        // registers and the rows are walked branch-free with the multiplier loaded once per row.
+        const double u0 = 1 + tx < n ? rowk[1 + tx] : 0.0, u1 = 33 + tx < n ? rowk[33 + tx] : 0.0,
+                     u2 = 65 + tx < n ? rowk[65 + tx] : 0.0, u3 = 97 + tx < n ? rowk[97 + tx] : 0.0;
+        const bool h1 = 33 + tx < n, h2 = 65 + tx < n, h3 = 97 + tx < n, h0 = 1 + tx < n;
+        const bool any2 = n > 65;                                       // uniform: third/fourth column slots in use
+#pragma unroll 2
+        for (int i = ty; i < n; i += NW) {
+            const double ci = -colk[i];                                 // uniform over the warp
+            double* wi = W + i * ld + 1 + tx;
+            if (h0) wi[0] = fma(ci, u0, wi[0]);
+            if (h1) wi[32] = fma(ci, u1, wi[32]);
+            if (any2) {
+                if (h2) wi[64] = fma(ci, u2, wi[64]);
+                if (h3) wi[96] = fma(ci, u3, wi[96]);
             }
         }
-        __syncwarp();
+        {                                                               // column 0 (mRNA): one element per thread
+            const double uc = rowk[0];
+            if (uc != 0.0)
+                for (int i = tid; i < n; i += NT) W[i * ld] = fma(-colk[i], uc, W[i * ld]);
+        }
+        for (int j = 129 + tx; j < n; j += 32) {                        // n > 129 (not reached by the shipped models)
+            const double ukj = rowk[j];
+            if (ukj != 0.0)
+                for (int i = ty; i < n; i += NW) W[i * ld + j] = fma(-colk[i], ukj, W[i * ld + j]);
+        }
+        // column k <- -col/pivot, row k <- row/pivot, pivot <- 1/pivot
+        for (int i = tid; i < n; i += NT) {
+            if (i != k) {
+                W[i * ld + k] = -colk[i] * ipiv;
+                W[k * ld + i] = rowk[i];
+            } else {
+                W[k * ld + k] = ipiv;
+            }
+        }
+        dsync<NT>();
     }
 }
 
-// Solve W x = r in place (x in shared memory).
-__device__ __forceinline__ void dense_solve(int n, int ld, const double* W, double* x, int lane) {
-    for (int k = 0; k < n - 1; ++k) {              // L y = r
-        const double xk = x[k];
-        for (int i = k + 1 + lane; i < n; i += 32) x[i] = fma(-W[i * ld + k], xk, x[i]);
-        __syncwarp();
+// dst = Winv * src.  Threads own rows (odd leading dimension -> conflict-free); when there are at least two threads
+// per row the row is split between the two lanes of a pair and combined with one shuffle.
+template <int NT>
+__device__ __forceinline__ void dense_apply(int n, int ld, const double* Winv, const double* src, double* dst, int tid) {
+    if (NT >= 64 && 2 * (n - 1) <= NT) {                // uniform condition: one lane pair per row 1..n-1
+        // row 0 of W is (1 + c B, 0, ..., 0) in every model (mRNA is decoupled), so is row 0 of the inverse
+        if (tid == NT - 1) dst[0] = Winv[0] * src[0];
+        const int i = 1 + (tid >> 1), half = tid & 1;
+        double acc0 = 0.0, acc1 = 0.0;
+        if (i < n) {
+            const int mid = (n + 1) >> 1;
+            const int j0 = half ? mid : 0, j1 = half ? n : mid;
+            const double* row = Winv + i * ld;
+            int j = j0;
+            for (; j + 1 < j1; j += 2) {
+                acc0 = fma(row[j], src[j], acc0);
+                acc1 = fma(row[j + 1], src[j + 1], acc1);
+            }
+            if (j < j1) acc0 = fma(row[j], src[j], acc0);
+        }
+        double acc = acc0 + acc1;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (i < n && half == 0) dst[i] = acc;
+    } else {
+        for (int i = tid; i < n; i += NT) {
+            const double* row = Winv + i * ld;
+            double acc0 = 0.0, acc1 = 0.0;
+            int j = 0;
+            for (; j + 1 < n; j += 2) {
+                acc0 = fma(row[j], src[j], acc0);
+                acc1 = fma(row[j + 1], src[j + 1], acc1);
+            }
+            if (j < n) acc0 = fma(row[j], src[j], acc0);
+            dst[i] = acc0 + acc1;
+        }
     }
-    for (int k = n - 1; k >= 0; --k) {             // U x = y
-        if (lane == 0) x[k] /= W[k * ld + k];
-        __syncwarp();
-        const double xk = x[k];
-        for (int i = lane; i < k; i += 32) x[i] = fma(-W[i * ld + k], xk, x[i]);
-        __syncwarp();
-    }
+    dsync<NT>();
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -183,16 +262,47 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-template <int MODEL>
-__global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+// block-wide reductions through shared memory (NT = 32: plain warp shuffles)
+template <int NT>
+__device__ __forceinline__ double dense_sum(double v, double* red) {
+    v = warp_sum(v);
+    if (NT > 32) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = red[0];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w) v += red[w];
+    }
+    return v;
+}
+template <int NT>
+__device__ __forceinline__ double dense_max(double v, double* red) {
+    v = warp_max(v);
+    if (NT > 32) {
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = red[0];
+#pragma unroll
+        for (int w = 1; w < NT / 32; ++w) v = fmax(v, red[w]);
+    }
+    return v;
+}
+
+template <int MODEL, int NT>
+__global__ void __launch_bounds__(NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     extern __shared__ double smem[];
-    const int lane = threadIdx.x;
+    __shared__ double red[4];
+    __shared__ unsigned long long s_idx;
+    const int lane = threadIdx.x;                 // thread index inside the group that owns one system
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
     double* W = smem + lay.W();
     double* y = smem + lay.vec(0);
     double* v = smem + lay.vec(1);
     double* w = smem + lay.vec(2);
     double* E = smem + lay.vec(3);
+    double* v2 = smem + lay.vec(4);
     double* p = smem + lay.par();
     double* prev = smem + lay.prev();
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
@@ -200,34 +310,36 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
 
     for (;;) {
-        unsigned long long idx = 0;
-        if (lane == 0) idx = atomicAdd(a.counter, 1ull);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
+        dsync<NT>();
+        if (lane == 0) s_idx = atomicAdd(a.counter, 1ull);
+        dsync<NT>();
+        const unsigned long long idx = s_idx;
         if ((long long)idx >= a.B) break;
         const size_t sys = (size_t)idx;
 
         // ---------------------------------------------------------------------------- init
         double p2l = 0.0;
-        for (int i = lane; i < P; i += 32) {
+        for (int i = lane; i < P; i += NT) {
             double v = a.params[sys * P + i];
             if (a.log_params) v = exp(v);
             p[i] = v;
             p2l = fma(v, v, p2l);
         }
         const double* y0 = a.y0 + (a.y0_stride ? sys * (size_t)a.y0_stride : 0);
-        for (int i = lane; i < n; i += 32) y[i] = y0[i];
-        __syncwarp();
+        for (int i = lane; i < n; i += NT) y[i] = y0[i];
+        dsync<NT>();
         const int grp = a.group ? a.group[sys] : 0;
         const double* tg = a.target ? a.target + (size_t)grp * a.L : nullptr;
         const double* sg = a.sigma ? a.sigma + (size_t)grp * a.sigma_len : nullptr;
         EpiAcc e{0, 0, 0, 0, 0, 0};
         double t = a.t[0];
         int nst = 0, nrej = 0, status = 0, kout = 1;
+        double h_inv = -1.0;            // step size whose (I - h gamma M)^-1 currently sits in W
 
         // lane-parallel emit of output index k from vector src (nullptr -> NaN)
         auto emit = [&](int k, const double* src) {
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-            for (int i = lane; i < n; i += 32) {
+            for (int i = lane; i < n; i += NT) {
                 double v = src ? fmax(src[i], 0.0) : qnan;
                 if (a.normalize) v *= 1.0 / y0[i];
                 if (a.out_sol) a.out_sol[(sys * T + k) * n + i] = v;
@@ -257,18 +369,18 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
         };
 
         // initial step from the error-weighted time scale |y|/|f|
-        dense_rhs<MODEL>(ns, n, p, y, v, lane);
-        __syncwarp();
+        dense_rhs<MODEL, NT>(ns, n, p, y, v, lane);
+        dsync<NT>();
         double d0 = 0.0, d1 = 0.0;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = lane; i < n; i += NT) {
             double sc = 1.0 / fma(a.rtol, fabs(y[i]), a.atol);
             d0 = fmax(d0, fabs(y[i]) * sc);
             d1 = fmax(d1, fabs(v[i]) * sc);
         }
-        d0 = warp_max(d0);
-        d1 = warp_max(d1);
+        d0 = dense_max<NT>(d0, red);
+        d1 = dense_max<NT>(d1, red);
         const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        StepCtl ctl{h0, (float)h0, 1.0f, 0, 0};
+        StepCtl ctl{dense_quantize_h(h0), (float)h0, 1.0f, 0, 0};
         emit(0, y);
 
         // ---------------------------------------------------------------------- time loop
@@ -280,52 +392,63 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             bool land = false;
             if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
             else if (hh > 0.5 * rem) hh = 0.5 * rem;
-            dense_fillW<MODEL>(ns, n, ld, p, hh * a.m.gamma, W, lane);
-            dense_lu(n, ld, W, lane);
+            if (hh != h_inv) {                        // a new step size: assemble and invert; otherwise reuse
+                dense_fillW<MODEL, NT>(ns, n, ld, p, hh * a.m.gamma, W, lane);
+                dense_invert<NT>(n, ld, W, v2, v, lane);
+                h_inv = hh;
+#ifdef PK_DENSE_COUNT_INV
+                ++nrej;
+#endif
+            }
 
-            // v_0 = h f(y); v_k = A^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
-            dense_rhs<MODEL>(ns, n, p, y, v, lane);
-            for (int i = lane; i < n; i += 32) v[i] *= hh;
-            __syncwarp();
-            dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) w[i] = fma(a.m.mu[0], v[i], y[i]);
-            dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[1], v[i], w[i]); E[i] = a.m.eps[1] * v[i]; }
-            dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[2], v[i], w[i]); E[i] = fma(a.m.eps[2], v[i], E[i]); }
-            dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[3], v[i], w[i]); E[i] = fma(a.m.eps[3], v[i], E[i]); }
-            dense_solve(n, ld, W, v, lane);
-            for (int i = lane; i < n; i += 32) { w[i] = fma(a.m.mu[4], v[i], w[i]); E[i] = fma(a.m.eps[4], v[i], E[i]); }
-            dense_solve(n, ld, W, v, lane);
+            // v_0 = h f(y); v_k = W^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
+            dense_rhs<MODEL, NT>(ns, n, p, y, v2, lane);
+            for (int i = lane; i < n; i += NT) v2[i] *= hh;
+            dsync<NT>();
+            dense_apply<NT>(n, ld, W, v2, v, lane);
+            for (int i = lane; i < n; i += NT) w[i] = fma(a.m.mu[0], v[i], y[i]);
+            dense_apply<NT>(n, ld, W, v, v2, lane);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[1], v2[i], w[i]); E[i] = a.m.eps[1] * v2[i]; }
+            dense_apply<NT>(n, ld, W, v2, v, lane);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[2], v[i], w[i]); E[i] = fma(a.m.eps[2], v[i], E[i]); }
+            dense_apply<NT>(n, ld, W, v, v2, lane);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[3], v2[i], w[i]); E[i] = fma(a.m.eps[3], v2[i], E[i]); }
+            dense_apply<NT>(n, ld, W, v2, v, lane);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[4], v[i], w[i]); E[i] = fma(a.m.eps[4], v[i], E[i]); }
+            dense_apply<NT>(n, ld, W, v, v2, lane);
             float err = 0.0f;
             bool bad = false;
-            for (int i = lane; i < n; i += 32) {
-                const double yn = fma(a.m.mu[5], v[i], w[i]);
-                const double ei = fma(a.m.eps[5], v[i], E[i]);
+            for (int i = lane; i < n; i += NT) {
+                const double yn = fma(a.m.mu[5], v2[i], w[i]);
+                const double ei = fma(a.m.eps[5], v2[i], E[i]);
                 w[i] = yn;
                 const float q = err_ratio(ei, y[i], yn, a.rtol, a.atol);
                 bad |= !(q < 3.0e38f) || !(fabs(yn) < 1.0e300);
                 err = fmaxf(err, q);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) err = fmaxf(err, __shfl_xor_sync(0xffffffffu, err, o));
-            bad = __any_sync(0xffffffffu, bad);
-            __syncwarp();
+            if (bad) err = __int_as_float(0x7f800000);
+            err = (float)dense_max<NT>((double)err, red);          // +inf marks a non-finite stage value
+            bad = !(err < 3.0e38f);
+            dsync<NT>();
 
             if (bad) { status = 3; break; }
             if (err <= 1.0f) {
                 ++nst;
                 const double hprop = ctl.h;
                 const double hnew = ctl_accept(ctl, hh, err, a.m.expo);
-                ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
-                for (int i = lane; i < n; i += 32) y[i] = w[i];
-                __syncwarp();
+                const double hp = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
+                double hq = dense_quantize_h(hp);
+                // hysteresis: a proposal only slightly below the current grid step keeps it (the proposal already
+                // carries the 0.9 safety factor), so the controller does not flip between two neighbouring levels
+                if (hq < hprop && hp >= 0.85 * hprop) hq = hprop;
+                ctl.h = hq;
+                for (int i = lane; i < n; i += NT) y[i] = w[i];
+                dsync<NT>();
                 if (land) { t = tout; emit(kout, y); ++kout; }
                 else t += hh;
             } else {
                 ++nrej;
-                ctl.h = ctl_reject(ctl, hh, err, a.m.expo);
+                ctl.h = dense_quantize_h(ctl_reject(ctl, hh, err, a.m.expo));
                 if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
             }
             if (status == 0 && kout < T && nst + nrej >= a.max_steps) status = 1;
@@ -341,15 +464,15 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
         if (want_loss) {
             double ssr = e.ssr;
             if (a.lam != 0.0) {
-                for (int i = lane; i < P; i += 32) {
+                for (int i = lane; i < P; i += NT) {
                     double th = a.params[sys * P + i];
                     double ww = a.lam / (double)P * th * th;
                     if (sg && a.sigma_len > a.L) ww /= __ldg(sg + a.L + i);
                     ssr = fma(ww, ww, ssr);
                 }
             }
-            ssr = warp_sum(ssr);
-            const double sr = warp_sum(e.sr), sr2 = warp_sum(e.sr2), p2 = warp_sum(p2l);
+            ssr = dense_sum<NT>(ssr, red);
+            const double sr = dense_sum<NT>(e.sr, red), sr2 = dense_sum<NT>(e.sr2, red), p2 = dense_sum<NT>(p2l, red);
             if (lane == 0) {
                 if (a.out_ssr) a.out_ssr[sys] = ssr;
                 if (a.out_score) {
@@ -362,7 +485,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
             }
         }
         if (want_y) {
-            const double s1 = warp_sum(e.s1), s2 = warp_sum(e.s2), dyn = warp_sum(e.dyn);
+            const double s1 = dense_sum<NT>(e.s1, red), s2 = dense_sum<NT>(e.s2, red), dyn = dense_sum<NT>(e.dyn, red);
             if (lane == 0) {
                 const double len = (double)(T * nobs), mean = s1 / len;
                 double yv;
@@ -376,7 +499,7 @@ __global__ void __launch_bounds__(32) local_dense_kernel(const LocalArgs a, cons
                 a.out_Y[sys] = yv;
             }
         }
-        __syncwarp();
+        dsync<NT>();
     }
 }
 

@@ -20,4 +20,4 @@ target = torch.rand(L, dtype=torch.float64).cuda()
 for rep in range(reps):
     r = eng.solve_local_batch(model, params, y0, ns, tt, want=want, target=target)
     nl, ms = eng.last_launch_info()
-    print(f"{model}-{ns} B={B} {want}: kernel {ms:.3f} ms -> {B/ms*1e3:.4g} solves/s steps {r['nsteps'].double().mean().item():.1f}", flush=True)
+    print(f"{model}-{ns} B={B} {want}: kernel {ms:.3f} ms -> {B/ms*1e3:.4g} solves/s steps {r["nsteps"].double().mean().item():.1f} nrej {r["nrej"].double().mean().item():.1f}", flush=True)
