@@ -190,7 +190,7 @@ typedef struct pk_global_job {
     const double* y0;            /* [state_dim] (y0_stride 0) or [B, y0_stride]                     */
     int64_t y0_stride;
     const double* t_eval;        /* [T] strictly increasing, HOST                                   */
-    double rtol, atol;           /* <=0 -> 1e-6 / 1e-9                                              */
+    double rtol, atol;           /* <=0 -> 2e-6 / 2e-9                                              */
     int32_t max_steps;           /* per system, <=0 -> 200000                                       */
     int32_t loss_mode;           /* LOSS_MODE 0..7 (lossfn.py:150-246)                              */
     int32_t metric;              /* pk_global_metric                                                */

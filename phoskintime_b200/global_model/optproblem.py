@@ -13,7 +13,7 @@ from ..engine import get_engine
 from .network import PARAM_KEYS
 from .simulate import simulate_batch
 
-ODE_REL_TOL, ODE_ABS_TOL, ODE_MAX_STEPS = 1e-6, 1e-9, 200000      # library defaults (reference: config.toml:403-406)
+ODE_REL_TOL, ODE_ABS_TOL, ODE_MAX_STEPS = 2e-6, 2e-9, 200000      # library defaults (reference: config.toml:403-406)
 
 
 def softplus(x):

@@ -4,7 +4,7 @@ called through the C ABI against the committed goldens of the UNMODIFIED referen
 bucket at 1e-12 = O2, `LOSS_FN` in all 8 modes) and against the oracle restatement.
 
 Tolerances:
-  * vs O2:  |ours - ref| <= 1e-6*|ref| + 1e-9   at the library defaults (rtol 1e-6, atol 1e-9)
+  * vs O2:  |ours - ref| <= 1e-6*|ref| + 1e-9   at the library defaults (rtol 2e-6, atol 2e-9)
   * vs O1:  |ours - ref| <= 1e-5*|ref| + 1e-6 everywhere, >= 99 % within 1e-6*|ref| + 1e-7
             (the stock reference integrates THROUGH the kinase-bucket jumps, SURVEY.md quirk 8, and is
              itself up to 0.6x the O2 bound away from O2)
