@@ -291,7 +291,7 @@ __device__ __forceinline__ double dense_max(double v, double* red) {
 }
 
 template <int MODEL, int NT>
-__global__ void __launch_bounds__(NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+__global__ void __launch_bounds__(NT, 512 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     extern __shared__ double smem[];
     __shared__ double red[4];
     __shared__ unsigned long long s_idx;
