@@ -58,7 +58,8 @@ struct pk_handle_s {
     int clock_khz = 0;
     char name[128] = {0};
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[4] = {nullptr, nullptr, nullptr, nullptr}, ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
+    static constexpr int MAX_CHUNKS = 8;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
     pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
     pkh::DevBuf g_params, g_y0, g_t, g_stops, g_Y, g_loss, g_F, g_metric, g_status, g_nsteps, g_nrej, g_traj;
