@@ -147,7 +147,7 @@ __device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double*
     dsync<NT>();
 }
 
-constexpr int DENSE_HQ = 2;       // step-size grid: 2^(j/DENSE_HQ)
+constexpr int DENSE_HQ = 1;       // step-size grid: 2^(j/DENSE_HQ)
 
 // largest grid value <= h
 __device__ __forceinline__ double dense_quantize_h(double h) {
@@ -294,6 +294,7 @@ template <int MODEL, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     extern __shared__ double smem[];
     __shared__ double red[4];
+    __shared__ double coef[48];           // scratch + results of ros5l_coeffs
     __shared__ unsigned long long s_idx;
     const int lane = threadIdx.x;                 // thread index inside the group that owns one system
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
@@ -392,13 +393,32 @@ __global__ void __launch_bounds__(NT, 512 / NT) local_dense_kernel(const LocalAr
             bool land = false;
             if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
             else if (hh > 0.5 * rem) hh = 0.5 * rem;
-            if (hh != h_inv) {                        // a new step size: assemble and invert; otherwise reuse
-                dense_fillW<MODEL, NT>(ns, n, ld, p, hh * a.m.gamma, W, lane);
+            // Coefficients of this step.  W holds (I - h_inv*gamma*M)^-1.  A step of exactly h_inv uses it as is; a
+            // step SHORTENED by the output grid (landing / halving) uses it too, as the ROS5L member with
+            // gamma' = gamma*h_inv/hh (pk_common.cuh: ros5l_coeffs) — so inversions only happen when the controller
+            // moves to another level of the step-size grid.
+            double mu[6], eps[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { mu[k] = a.m.mu[k]; eps[k] = a.m.eps[k]; }
+            const bool forced = hh != ctl.h;          // hh was set by the output grid, not by the controller
+            bool reuse = hh == h_inv;
+            if (!reuse && a.m.family == 1 && forced && h_inv > 0.0 && hh <= 1.03 * h_inv && hh * 16.0 >= h_inv) reuse = true;
+            if (!reuse) {
+                // invert at the controller's grid value when it covers this (forced) step, else at the step itself
+                const double hnew = (a.m.family == 1 && forced && hh <= 1.03 * ctl.h && hh * 16.0 >= ctl.h) ? ctl.h : hh;
+                dense_fillW<MODEL, NT>(ns, n, ld, p, hnew * a.m.gamma, W, lane);
                 dense_invert<NT>(n, ld, W, v2, v, lane);
-                h_inv = hh;
+                h_inv = hnew;
 #ifdef PK_DENSE_COUNT_INV
                 ++nrej;
 #endif
+            }
+            if (hh != h_inv) {                      // uniform over the system's threads
+                if (lane == 0) ros5l_coeffs(a.m.gamma * h_inv / hh, coef);
+                dsync<NT>();
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { mu[k] = coef[36 + k]; eps[k] = coef[42 + k]; }
+                dsync<NT>();
             }
 
             // v_0 = h f(y); v_k = W^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
@@ -406,21 +426,21 @@ __global__ void __launch_bounds__(NT, 512 / NT) local_dense_kernel(const LocalAr
             for (int i = lane; i < n; i += NT) v2[i] *= hh;
             dsync<NT>();
             dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) w[i] = fma(a.m.mu[0], v[i], y[i]);
+            for (int i = lane; i < n; i += NT) w[i] = fma(mu[0], v[i], y[i]);
             dense_apply<NT>(n, ld, W, v, v2, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[1], v2[i], w[i]); E[i] = a.m.eps[1] * v2[i]; }
+            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[1], v2[i], w[i]); E[i] = eps[1] * v2[i]; }
             dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[2], v[i], w[i]); E[i] = fma(a.m.eps[2], v[i], E[i]); }
+            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[2], v[i], w[i]); E[i] = fma(eps[2], v[i], E[i]); }
             dense_apply<NT>(n, ld, W, v, v2, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[3], v2[i], w[i]); E[i] = fma(a.m.eps[3], v2[i], E[i]); }
+            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[3], v2[i], w[i]); E[i] = fma(eps[3], v2[i], E[i]); }
             dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(a.m.mu[4], v[i], w[i]); E[i] = fma(a.m.eps[4], v[i], E[i]); }
+            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[4], v[i], w[i]); E[i] = fma(eps[4], v[i], E[i]); }
             dense_apply<NT>(n, ld, W, v, v2, lane);
             float err = 0.0f;
             bool bad = false;
             for (int i = lane; i < n; i += NT) {
-                const double yn = fma(a.m.mu[5], v2[i], w[i]);
-                const double ei = fma(a.m.eps[5], v2[i], E[i]);
+                const double yn = fma(mu[5], v2[i], w[i]);
+                const double ei = fma(eps[5], v2[i], E[i]);
                 w[i] = yn;
                 const float q = err_ratio(ei, y[i], yn, a.rtol, a.atol);
                 bad |= !(q < 3.0e38f) || !(fabs(yn) < 1.0e300);
