@@ -125,6 +125,10 @@ int pk_measure_fp64_peak(pk_handle_t h, double* tflops, float* ms);
 
 /* NCCL all-gather of per-sample doubles (device pointers). `comm` is an ncclComm_t created by the
  * caller (or NULL with world==1 -> plain copy). */
+/* Coefficients MU[6], EPS[6] of the ROS5L(gamma) member: the dense kernel derives them at run time
+ * for steps that reuse an inverse computed for a larger step; exported for verification (host arithmetic). */
+int pk_ros5l_coeffs(double gamma, double* mu6, double* eps6);
+
 int pk_nccl_unique_id(char* out128);
 int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank);
 int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev);

@@ -105,6 +105,7 @@ SYMBOLS = {
     "pk_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "pk_host_free": (C.c_int, [C.c_void_p]),
     "pk_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "pk_ros5l_coeffs": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

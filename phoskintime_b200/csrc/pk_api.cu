@@ -252,6 +252,15 @@ int dims(int model, int ns, int T, int* n, int* P, int* L) {
 extern "C" {
 
 int pk_abi_version(void) { return PK_ABI_VERSION; }
+
+// host evaluation of the run-time ROS5L(gamma) coefficient construction the dense kernel uses (for tests)
+int pk_ros5l_coeffs(double gamma, double* mu6, double* eps6) {
+    if (!(gamma > 0.0) || !mu6 || !eps6) return fail("pk_ros5l_coeffs: bad arguments");
+    double scratch[48];
+    pk::ros5l_coeffs(gamma, scratch);
+    for (int k = 0; k < 6; ++k) { mu6[k] = scratch[36 + k]; eps6[k] = scratch[42 + k]; }
+    return 0;
+}
 const char* pk_last_error(void) { return pkh::g_err.c_str(); }
 
 int pk_device_count(int* out) {

@@ -58,3 +58,48 @@ def test_order_and_stability_of_compiled_coefficients():
         assert np.abs(_R(mu, g, 1j * y)).max() <= 1.0 + 1e-12
         x = -np.logspace(-3, 8, 2000)
         assert np.abs(_R(mu, g, x)).max() < 1.0 and abs(_R(mu, g, -1e8)) < 1e-6
+
+
+def test_runtime_ros5l_family_matches_design_and_stays_stable():
+    """`ros5l_coeffs` (csrc/pk_common.cuh; the dense kernel evaluates it on the device for steps that reuse an
+    inverse computed for a larger step) through its host export `pk_ros5l_coeffs`:
+    at gamma = 0.19 it reproduces the compiled ROS5L constants; for every gamma' the kernel can request
+    (0.19/1.03 .. 0.19*16) the member has order 5 with an order-4 estimate, MU[0] = gamma' (L-stable), is stable on
+    the negative real axis and in the 60-degree sector, and a shortened step's local error stays within 1.5x of the
+    full step's (and drops quickly for larger gamma')."""
+    import ctypes as C
+    from phoskintime_b200 import _lib
+    lib = _lib.load()
+
+    def coeffs(g):
+        mu, eps = (C.c_double * 6)(), (C.c_double * 6)()
+        assert lib.pk_ros5l_coeffs(g, mu, eps) == 0
+        return np.array(mu[:]), np.array(eps[:])
+
+    ref = _parse_methods()["METHOD_ROS5L"]
+    mu0, eps0 = coeffs(0.19)
+    assert np.allclose(mu0, ref["mu"], rtol=1e-10, atol=1e-11) and np.allclose(eps0, ref["eps"], rtol=1e-9, atol=1e-10)
+    from math import comb, factorial
+    c6 = lambda g, mu: 1 / factorial(6) - sum(mu[k] * comb(k + 5, 5) * g ** 5 for k in range(6))
+    C60 = abs(c6(0.19, mu0))
+    assert abs(C60 - 7.6482963444444444e-5) < 1e-12
+    x = -np.logspace(-3, 8, 3000)
+    sector = np.logspace(-3, 8, 3000) * np.exp(1j * (np.pi - np.pi / 3))
+    for g in (0.19 / 1.03, 0.2, 0.25, 0.3, 0.334, 0.5, 0.76, 1.0, 1.9, 3.04):
+        mu, eps = coeffs(g)
+        assert mu[0] == g and eps[0] == 0.0
+        z1, z2 = 0.01 / max(g, 0.19), 0.02 / max(g, 0.19)
+        e1, e2 = abs(_R(mu, g, z1) - np.exp(z1)), abs(_R(mu, g, z2) - np.exp(z2))
+        if abs(c6(g, mu)) > 1e-5:                                  # (C6 changes sign near gamma = 0.334)
+            assert abs(np.log2(e2 / e1) - 6) < 0.2, (g, np.log2(e2 / e1))
+        s1 = abs(z1 * sum(e * (1 / (1 - g * z1)) ** (k + 1) for k, e in enumerate(eps)))
+        s2 = abs(z2 * sum(e * (1 / (1 - g * z2)) ** (k + 1) for k, e in enumerate(eps)))
+        assert abs(np.log2(s2 / s1) - 5) < 0.1
+        assert np.abs(_R(mu, g, x)).max() < 1.0 and abs(_R(mu, g, -1e8)) < 1e-6
+        assert np.abs(_R(mu, g, sector)).max() <= 1.0 + 1e-12
+        # local error of the shortened step (gamma' = g, step h*0.19/g) relative to the full step at gamma = 0.19:
+        # at most 1.5x (gamma' in 0.19..0.27, where C6 grows faster than the step shrinks), far smaller beyond
+        rel = abs(c6(g, mu)) / C60 * (0.19 / g) ** 6
+        assert rel <= 1.5 and (g < 0.3 or rel < 0.7)
+    with np.errstate(all="ignore"):
+        assert lib.pk_ros5l_coeffs(-1.0, (C.c_double * 6)(), (C.c_double * 6)()) != 0
