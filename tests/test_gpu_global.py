@@ -267,3 +267,47 @@ def test_global_morris_ranking_matches_oracle(engine):
     assert np.allclose(res["mu_star"], Si["mu_star"], rtol=1e-9, atol=1e-12)
     assert np.allclose(res["sigma"], Si["sigma"], rtol=1e-9, atol=1e-12)
     assert np.array_equal(res["order"][:10], np.argsort(-Si["mu_star"], kind="stable")[:10])
+
+
+@pytest.mark.parametrize("N,K,expect_tile_range", [(70, 20, (33, 64)), (150, 40, (97, 128))], ids=["tile4", "tile8"])
+def test_other_register_tile_sizes(engine, N, K, expect_tile_range):
+    """Regulator sets of 33-64 and 97-128 proteins select the 4x4 / 8x8 register tiles: the default run agrees with
+    a tight-tolerance run, and (where shared memory allows) with the shared-memory LU fallback."""
+    s = synthetic_system(seed=21, N=N, K=K, max_sites=3, model=0)
+    topo = engine.global_upload(s)
+    dims = engine.global_dims(topo)
+    assert expect_tile_range[0] <= dims["n_reg"] <= expect_tile_range[1], dims
+    rng = np.random.default_rng(1)
+    base = s.pack_params()
+    P = base[None, :] * np.exp(0.1 * rng.standard_normal((6, base.size)))
+    t = np.array([0.0, 0.5, 1.0, 4.0, 15.0, 16.0, 60.0, 240.0, 960.0])
+    a = engine.global_solve_batch(topo, P, s.y0(), t, ("Y",))
+    b = engine.global_solve_batch(topo, P, s.y0(), t, ("Y",), rtol=1e-8, atol=1e-11)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert _ratio(a["Y"], b["Y"], 1e-6, 1e-9) <= 1.0
+    if dims["n_reg"] <= 64:
+        tg = engine.global_upload(s, force_generic=True)
+        c = engine.global_solve_batch(tg, P, s.y0(), t, ("Y",), rtol=1e-8, atol=1e-11)
+        engine.global_release(tg)
+        assert np.allclose(c["Y"], b["Y"], rtol=1e-7, atol=1e-10)
+    engine.global_release(topo)
+
+
+def test_network_without_transcriptional_coupling(engine):
+    """No TF edges: empty regulator set (no Schur block at all); every protein block integrates on its own and
+    must match the oracle's tight solution."""
+    s = synthetic_system(seed=8, N=6, K=3, max_sites=3, tf_density=0.0, model=1)
+    assert s.TF_indptr[-1] == 0
+    net = s.as_dict()
+    t = np.array([0.0, 0.5, 1.0, 4.0, 16.0, 60.0, 960.0])
+    r = simulate_batch(s, s.pack_params()[None, :], t, ("Y",), engine=engine)
+    assert r["status"][0] == 0 and engine.global_dims(s._topo_id[id(engine)])["n_reg"] == 0
+    ref = og.simulate_exact_buckets(1, net, t)
+    assert _ratio(r["Y"][0], ref, 1e-6, 1e-9) <= 1.0
+
+
+def test_oversized_network_is_rejected_with_a_message(engine):
+    from phoskintime_b200 import PhoskinError
+    s = synthetic_system(seed=2, N=400, K=40, max_sites=4, model=0)
+    with pytest.raises(PhoskinError, match="shared memory"):
+        engine.global_upload(s)
