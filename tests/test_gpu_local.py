@@ -297,3 +297,20 @@ def test_large_batch_properties(engine):
     r4 = engine.solve_local_batch("succmod", p, ys, 5, t, want=("sol",))
     drift = (r4["sol"] - ys[:, None, :]).abs() / (1e-6 * ys[:, None, :].abs() + 1e-9)
     assert float(drift.max()) < 1.0
+
+
+def test_knockout_sweep_is_one_batched_launch(engine):
+    """paramest/core.py:144-187: every knockout setting solved in one launch equals the oracle's solve of the
+    same modified parameter vector."""
+    from phoskintime_b200 import knockout
+    rng = np.random.default_rng(5)
+    ns = 3
+    p = rng.uniform(0.2, 2.0, 4 + 2 * ns)
+    y0 = np.asarray(om.initial_condition("distmod", ns))
+    res = knockout.simulate_knockouts(p, y0, ns, T14, model="distmod")
+    assert len(res) == 4 * (ns + 2) and "WT" in res and "Transcription KO_Translation KO_Phospho KO" in res
+    for name, r in res.items():
+        assert r["status"] == 0
+        ex = om.exact_linear("distmod", knockout.apply_knockout(p, r["knockout_setting"], ns), y0, ns, T14)
+        assert _close(r["sol_ko"], np.clip(ex, 0, None), 1e-6, 1e-9).all(), name
+    assert np.allclose(res["Phospho KO"]["sol_ko"][:, 2:], y0[2:] * np.exp(-np.outer(T14, 1.0 + p[4 + ns:])), rtol=1e-6, atol=1e-12)

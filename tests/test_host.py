@@ -125,6 +125,22 @@ def test_multistart_points_follow_normest():
     assert list(best) == [1, 2, 5]
 
 
+def test_knockout_combinations_and_application():
+    """knockout/helper.py:5-62 — order and content of the 4*(ns+2) settings, parameter zeroing."""
+    from phoskintime_b200 import knockout
+    combos = knockout.generate_knockout_combinations(3)
+    assert len(combos) == 4 * (3 + 2) and combos[0] == {"transcription": False, "translation": False, "phosphorylation": False}
+    assert combos[1]["phosphorylation"] is True and combos[2]["phosphorylation"] == [0] and combos[5]["translation"] is True
+    base = np.arange(1.0, 11.0)                                     # A,B,C,D,S1..3,D1..3
+    assert np.array_equal(knockout.apply_knockout(base, combos[0], 3), base)
+    ko = knockout.apply_knockout(base, {"transcription": True, "translation": True, "phosphorylation": [1, 7]}, 3)
+    assert list(ko) == [0, 2, 0, 4, 5, 0, 7, 8, 9, 10] and base[0] == 1.0            # copy, out-of-range site ignored
+    assert list(knockout.apply_knockout(base, {"phosphorylation": True}, 3)[4:7]) == [0, 0, 0]
+    assert knockout.knockout_name(combos[0]) == "WT"
+    assert knockout.knockout_name({"transcription": True, "translation": False, "phosphorylation": [2]}, ["S1", "T5", "Y9"]) \
+        == "Transcription KO_PhosphoSite KO Y9"
+
+
 def test_shard_bounds_cover_and_align():
     for total, world, align in ((11000, 8, 11), (1000, 3, 1), (256000, 8, 256), (7, 8, 1)):
         spans = [parallel.shard_bounds(total, world, r, align) for r in range(world)]
