@@ -59,7 +59,7 @@ typedef struct pk_local_job {
     const double* y0;       /* [n] if y0_stride==0 else [B,n] with row stride y0_stride doubles  */
     int64_t y0_stride;
     const double* t;        /* [T] strictly increasing                                           */
-    double rtol, atol;      /* <=0 -> defaults 1e-7 / 1e-10                                      */
+    double rtol, atol;      /* <=0 -> defaults 2e-6 / 2e-9                                       */
     int32_t max_steps;      /* per system, <=0 -> 100000                                         */
     int32_t normalize;      /* NORMALIZE_MODEL_OUTPUT (models/distmod.py:115-122)                */
     int32_t log_params;     /* 1: params hold log-values, model uses exp(params) (normest.py:54) */

@@ -402,8 +402,8 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     pk::LocalArgs a;
     memset(&a, 0, sizeof(a));
     a.B = j->B; a.T = j->T; a.ns = j->n_sites; a.n = n; a.P = P; a.L = L;
-    a.rtol = j->rtol > 0 ? j->rtol : 1e-7;
-    a.atol = j->atol > 0 ? j->atol : 1e-10;
+    a.rtol = j->rtol > 0 ? j->rtol : 2e-6;      // defaults: DESIGN.md §5 (error <= 0.14 of the parity bound)
+    a.atol = j->atol > 0 ? j->atol : 2e-9;
     if (j->method < 0 || j->method > 2) return fail("unknown method");
     a.m = (j->method == PK_METHOD_RODAS4) ? pk::METHOD_RODAS4 : pk::METHOD_ROS5L;
     a.max_steps = j->max_steps > 0 ? j->max_steps : 100000;

@@ -15,8 +15,10 @@ from . import _lib
 from ._lib import (GLOBAL_METRIC_IDS, METHOD_IDS, MODEL_IDS, PK_DEVICE, PK_HOST, Y_METRIC_IDS, PhoskinError,
                    PkGlobalJob, PkGlobalLossData, PkGlobalTopology, PkLocalJob)
 
-DEFAULT_RTOL = 1e-7
-DEFAULT_ATOL = 1e-10
+# library defaults (all kernels): measured error against the reference's tight solution <= 0.14 (local models) /
+# 0.27 (global network) of the 1e-6 parity bound on every golden — DESIGN.md §5; 1e-7/1e-10 gives 0.007 at 1.65x the steps
+DEFAULT_RTOL = 2e-6
+DEFAULT_ATOL = 2e-9
 
 _engines = {}
 

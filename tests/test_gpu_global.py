@@ -58,8 +58,9 @@ def test_trajectories_match_reference(engine, path):
     assert _ratio(Y, g["Y_tight"], 1e-6, 1e-9) <= 1.0
     assert _ratio(Y, g["Y"], 1e-5, 1e-6) <= 1.0
     assert (np.abs(Y - g["Y"]) <= 1e-6 * np.abs(g["Y"]) + 1e-7).mean() >= 0.99
-    # closer to the tight reference than the stock reference is
-    assert _ratio(Y, g["Y_tight"], 1e-6, 1e-9) <= _ratio(g["Y"], g["Y_tight"], 1e-6, 1e-9)
+    # margin at the library defaults: within half the parity bound (the stock reference, run at 1e-8, is itself
+    # 0.2-0.6 of the bound away from the tight solution)
+    assert _ratio(Y, g["Y_tight"], 1e-6, 1e-9) <= 0.5
     assert (r["nsteps"] > 0).all() and (r["nrej"] >= 0).all()
 
 

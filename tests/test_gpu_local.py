@@ -48,10 +48,9 @@ def test_parity_with_reference_goldens(engine, path):
         float((np.abs(sol - g["sol_tight"]) / (1e-6 * np.abs(g["sol_tight"]) + 1e-9)).max())
     assert _close(sol, g["sol"], 1e-5, 1e-6).all()
     assert _close(sol, g["sol"], 1e-6, 1e-7).mean() >= 0.99
-    # our distance to the tight reference is far below the stock reference's own
-    ours = np.abs(sol - g["sol_tight"]).max()
-    stock = np.abs(g["sol"] - g["sol_tight"]).max()
-    assert ours < 0.1 * stock + 1e-12
+    # margin at the library defaults: within a quarter of the parity bound (the stock reference itself is up to
+    # 14x the bound away from the tight solution)
+    assert float((np.abs(sol - g["sol_tight"]) / (1e-6 * np.abs(g["sol_tight"]) + 1e-9)).max()) <= 0.25
     assert _close(r["flat"], g["flat"], 1e-5, 1e-6).all()
 
 
@@ -313,4 +312,4 @@ def test_knockout_sweep_is_one_batched_launch(engine):
         assert r["status"] == 0
         ex = om.exact_linear("distmod", knockout.apply_knockout(p, r["knockout_setting"], ns), y0, ns, T14)
         assert _close(r["sol_ko"], np.clip(ex, 0, None), 1e-6, 1e-9).all(), name
-    assert np.allclose(res["Phospho KO"]["sol_ko"][:, 2:], y0[2:] * np.exp(-np.outer(T14, 1.0 + p[4 + ns:])), rtol=1e-6, atol=1e-12)
+    assert _close(res["Phospho KO"]["sol_ko"][:, 2:], y0[2:] * np.exp(-np.outer(T14, 1.0 + p[4 + ns:])), 1e-6, 1e-9).all()
