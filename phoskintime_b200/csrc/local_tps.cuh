@@ -177,7 +177,18 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     constexpr int N = M::N, NF = M::NF, P = M::P;
     extern __shared__ double smem[];
     double* tgrid = smem;                                     // [T]
+    short* fmap = (short*)(smem + a.T);                       // [L]: trajectory index (k*N + i) of every flat entry
     for (int i = threadIdx.x; i < a.T; i += TPS_BLOCK) tgrid[i] = a.t[i];
+    {
+        const int rl = a.T > RNA_OFFSET ? a.T - RNA_OFFSET : 0;
+        for (int fi = threadIdx.x; fi < a.L; fi += TPS_BLOCK) {
+            int k, i;
+            if (fi < rl) { k = fi + RNA_OFFSET; i = 0; }
+            else if (fi < rl + a.T) { k = fi - rl; i = 1; }
+            else { const int j = fi - rl - a.T; i = 2 + j / a.T; k = j - (i - 2) * a.T; }
+            fmap[fi] = (short)(k * N + i);
+        }
+    }
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
@@ -336,6 +347,22 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             const double* sg = (want_loss && a.sigma) ? a.sigma + (size_t)g * a.sigma_len : nullptr;
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
             double ssr = 0.0, sr = 0.0, sr2 = 0.0, s1 = 0.0, s2 = 0.0, dyn = 0.0;
+            // Fast path (loss and/or flat only, successful system): walk the L flat entries through the index table —
+            // no (k, i) arithmetic, no per-element validity test, 3 instead of 4 sweeps for 5 sites.
+            const bool fast = fstatus == 0 && !a.out_sol && !want_y && !a.normalize;
+            if (fast) {
+                for (int fi = lane; fi < a.L; fi += 32) {
+                    const double v = fmax(tr[fmap[fi]], 0.0);                 // np.clip(sol, 0, None)
+                    if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
+                    if (want_loss) {
+                        const double dlt = v - __ldg(tg + fi);
+                        const double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                        ssr = fma(w, w, ssr);
+                        sr += fabs(dlt);
+                        sr2 = fma(dlt, dlt, sr2);
+                    }
+                }
+            } else
             for (int idx = lane; idx < TN; idx += 32) {
                 const int k = idx / N, i = idx - k * N;
                 double v = (k < fvalid) ? fmax(tr[idx], 0.0) : qnan;            // np.clip(sol, 0, None)

@@ -160,7 +160,7 @@ constexpr size_t PIPE_MIN_CHUNK = 100000;   // host-path batches >= 2x/4x this a
 
 template <class M>
 cudaError_t launch_tps(pk_handle_s* h, pk::LocalArgs a) {
-    size_t smem = (size_t)a.T * sizeof(double);
+    size_t smem = (size_t)a.T * sizeof(double) + (((size_t)a.L * sizeof(short) + 7) & ~(size_t)7);   // time grid + flat index table
     auto kern = pk::local_tps_kernel<M, tps_min_blocks<M>()>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
