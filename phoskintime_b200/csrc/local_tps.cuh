@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     double t = 0.0;
     StepCtl ctl;
     int kout = 0, nst = 0, nrej = 0, status = 0;
+    double p2own = 0.0;
 
     for (;;) {
         // ------------------------------------------------------------------ refill idle lanes
@@ -231,6 +232,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         for (int i = 0; i < P; ++i) pv[i] = exp(pv[i]);
                     }
                     mdl.load(pv);
+                    p2own = 0.0;                      // |physical params|^2 for score_fit's l2 term
+#pragma unroll
+                    for (int i = 0; i < P; ++i) p2own = fma(pv[i], pv[i], p2own);
                     const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { y[i] = y0[i]; my_traj[i] = y[i]; }
@@ -351,15 +355,28 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             // no (k, i) arithmetic, no per-element validity test, 3 instead of 4 sweeps for 5 sites.
             const bool fast = fstatus == 0 && !a.out_sol && !want_y && !a.normalize;
             if (fast) {
-                for (int fi = lane; fi < a.L; fi += 32) {
-                    const double v = fmax(tr[fmap[fi]], 0.0);                 // np.clip(sol, 0, None)
-                    if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
-                    if (want_loss) {
-                        const double dlt = v - __ldg(tg + fi);
-                        const double w = sg ? dlt / __ldg(sg + fi) : dlt;
-                        ssr = fma(w, w, ssr);
-                        sr += fabs(dlt);
-                        sr2 = fma(dlt, dlt, sr2);
+                for (int base = lane; base < a.L; base += 128) {
+                    // four sweeps' loads are issued back to back (the trajectory slot lives in L2: one latency, not four)
+                    double raw[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int fi = base + 32 * u;
+                        raw[u] = tr[fi < a.L ? fmap[fi] : 0];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int fi = base + 32 * u;
+                        if (fi < a.L) {
+                            const double v = fmax(raw[u], 0.0);                   // np.clip(sol, 0, None)
+                            if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
+                            if (want_loss) {
+                                const double dlt = v - __ldg(tg + fi);
+                                const double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                                ssr = fma(w, w, ssr);
+                                sr += fabs(dlt);
+                                sr2 = fma(dlt, dlt, sr2);
+                            }
+                        }
                     }
                 }
             } else
@@ -390,21 +407,19 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     }
                 }
             }
-            double p2 = 0.0;
+            const double p2 = __shfl_sync(FULL, p2own, f);           // computed by the owner when it loaded the parameters
             if (want_loss) {
-                // |params|^2 for score_fit's l2 term and the lam/P*theta^2 rows of normest's model_func
-                const double* sgr = (sg && a.sigma_len > a.L) ? sg + a.L : nullptr;
-                for (int i = lane; i < P; i += 32) {
-                    const double th = a.params[fsys * P + i];
-                    const double ph = a.log_params ? exp(th) : th;
-                    p2 = fma(ph, ph, p2);
-                    if (a.lam != 0.0) {
+                if (a.lam != 0.0) {
+                    // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423)
+                    const double* sgr = (sg && a.sigma_len > a.L) ? sg + a.L : nullptr;
+                    for (int i = lane; i < P; i += 32) {
+                        const double th = a.params[fsys * P + i];
                         double w = a.lam / (double)P * th * th;
                         if (sgr) w /= __ldg(sgr + i);
                         ssr = fma(w, w, ssr);
                     }
                 }
-                ssr = warp_sum_d(ssr); sr = warp_sum_d(sr); sr2 = warp_sum_d(sr2); p2 = warp_sum_d(p2);
+                ssr = warp_sum_d(ssr); sr = warp_sum_d(sr); sr2 = warp_sum_d(sr2);
             }
             if (want_y) { s1 = warp_sum_d(s1); s2 = warp_sum_d(s2); dyn = warp_sum_d(dyn); }
             if (lane == 0) {
