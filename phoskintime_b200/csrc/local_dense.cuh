@@ -218,8 +218,10 @@ template <int NT>
 __device__ __forceinline__ void dense_apply(int n, int ld, const double* Winv, const double* src, double* dst, int tid) {
     if (NT >= 64 && 2 * (n - 1) <= NT) {                // uniform condition: one lane pair per row 1..n-1
         // row 0 of W is (1 + c B, 0, ..., 0) in every model (mRNA is decoupled), so is row 0 of the inverse
+        // lanes l and l^16 share a row, so the 16 lanes served together by one shared-memory pass all read
+        // different rows at the same column offset: conflict-free with the odd leading dimension
         if (tid == NT - 1) dst[0] = Winv[0] * src[0];
-        const int i = 1 + (tid >> 1), half = tid & 1;
+        const int i = 1 + 16 * (tid >> 5) + (tid & 15), half = (tid >> 4) & 1;
         double acc0 = 0.0, acc1 = 0.0;
         if (i < n) {
             const int mid = (n + 1) >> 1;
@@ -233,7 +235,7 @@ __device__ __forceinline__ void dense_apply(int n, int ld, const double* Winv, c
             if (j < j1) acc0 = fma(row[j], src[j], acc0);
         }
         double acc = acc0 + acc1;
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (i < n && half == 0) dst[i] = acc;
     } else {
         for (int i = tid; i < n; i += NT) {
@@ -291,7 +293,7 @@ __device__ __forceinline__ double dense_max(double v, double* red) {
 }
 
 template <int MODEL, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+__global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     extern __shared__ double smem[];
     __shared__ double red[4];
     __shared__ double coef[48];           // scratch + results of ros5l_coeffs

@@ -14,8 +14,9 @@ for r in rows:
         hdr = r
     elif hdr and r[0].isdigit():
         d = dict(zip(hdr, r))
-        lines.append((cur_file, int(r[0]), r[1].strip(), int(d["Instructions Executed"] or 0), int(d["# Samples"] or 0),
-                      int(d["Thread Instructions Executed"] or 0)))
+        num = lambda k: int(d[k]) if d.get(k, "").strip().lstrip("-").isdigit() else 0
+        lines.append((cur_file, int(r[0]), r[1].strip(), num("Instructions Executed"), num("# Samples"),
+                      num("Thread Instructions Executed")))
 tot_i = sum(l[3] for l in lines) or 1
 tot_s = sum(l[4] for l in lines) or 1
 print(f"total warp instructions {tot_i:.4g}, samples {tot_s}")
