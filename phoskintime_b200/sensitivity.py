@@ -90,16 +90,52 @@ def sensitivity_analysis(popt, time_points, num_psites, init_cond, model, *, pr_
     X = np.ascontiguousarray(X, dtype=np.float64)
     D = problem["num_vars"]
     need_sol = keep_trajectories and pr_data is not None
-    want = ("Y", "sol") if need_sol else ("Y",)
-    res = eng.solve_local_batch(model, X, init_cond, num_psites, time_points, want=want, y_metric=y_metric)
+    T = int(np.asarray(time_points).size)
+    fused = None
+    if need_sol:
+        fused = rmse_target(pr_data, p_data, rna_data, num_psites, T)
+    if need_sol and fused is not None:
+        # The per-trajectory RMSE against the data (analysis.py:277-284) is a weighted residual over the flat
+        # layout, so it rides in the kernel epilogue (8 bytes per row leave HBM instead of the whole trajectory);
+        # only the K closest rows are solved again for their trajectories.
+        target, sigma = fused
+        res = eng.solve_local_batch(model, X, init_cond, num_psites, time_points, want=("Y", "ssr"), y_metric=y_metric,
+                                    target=target, sigma=sigma)
+    else:
+        want = ("Y", "sol") if need_sol else ("Y",)
+        res = eng.solve_local_batch(model, X, init_cond, num_psites, time_points, want=want, y_metric=y_metric)
     Y = np.nan_to_num(res["Y"], nan=0.0, posinf=0.0, neginf=0.0)          # analysis.py:261
     stats = eng.morris_ee(X, Y, num_levels, scaled=scaled)
     Si = {"names": problem["names"], "mu": stats["mu"], "mu_star": stats["mu_star"], "sigma": stats["sigma"],
           "Y": Y, "X": X, "status": res["status"]}
     best = []
-    if need_sol:
+    if need_sol and fused is not None:
+        rmse = np.sqrt(np.asarray(res["ssr"]) / 2.0)
+        rmse = np.where(np.isfinite(rmse), rmse, np.inf)
+        K = int(math.ceil(N * 10 / num_levels))
+        idx = np.argsort(rmse, kind="stable")[:K]
+        sol = eng.solve_local_batch(model, X[idx], init_cond, num_psites, time_points, want=("sol",))["sol"]
+        best = [{"params": X[i], "solution": sol[j], "rmse": float(rmse[i])} for j, i in enumerate(idx)]
+        Si["rmse"] = rmse
+    elif need_sol:
         best = select_closest(res["sol"], X, pr_data, p_data, rna_data, num_psites, N, num_levels)
     return Si, best
+
+
+def rmse_target(pr_data, p_data, rna_data, num_psites, T):
+    """(target[L], sigma[L]) such that the kernel's fused weighted residual `ssr` equals 2*rmse^2 of
+    sensitivity/analysis.py:277-284:  each block's mse = mean((|pred - ref| / ref.size)^2) = sum(d^2) / size^3, so
+    sigma = size^1.5 on that block.  Returns None when the data do not line up with the flat layout
+    [R(t[5:]) | P(t) | sites] (then the trajectories themselves are needed)."""
+    protein_ref = np.asarray(pr_data, dtype=np.float64).reshape(-1)
+    psite_ref = np.asarray(p_data, dtype=np.float64)
+    rna_ref = np.asarray(rna_data, dtype=np.float64).reshape(-1)
+    if rna_ref.size != max(T - 5, 0) or protein_ref.size != T or psite_ref.shape != (num_psites, T):
+        return None
+    target = np.concatenate([rna_ref, protein_ref, psite_ref.reshape(-1)])
+    sigma = np.concatenate([np.full(rna_ref.size, rna_ref.size ** 1.5), np.full(T, protein_ref.size ** 1.5),
+                            np.full(psite_ref.size, psite_ref.size ** 1.5)])
+    return target, sigma
 
 
 def select_closest(sol, X, pr_data, p_data, rna_data, num_psites, N=NUM_TRAJECTORIES, num_levels=PARAMETER_SPACE):

@@ -61,6 +61,17 @@ def test_sensitivity_top_k_selection(engine):
                                                 rna_data=rna, N=N, num_levels=levels, seed=3, engine=engine)
     assert len(best) == int(np.ceil(N * 10 / levels)) and best[0]["rmse"] <= best[-1]["rmse"]
     assert best[0]["solution"].shape == (14, 5)
+    # the fused RMSE (kernel epilogue, weighted residual) equals the reference formula on full trajectories
+    # (sensitivity/analysis.py:277-284) and picks the same rows
+    full = engine.solve_local_batch("distmod", Si["X"], y0, ns, om.TIME_POINTS, want=("sol",))["sol"]
+    host = sensitivity.select_closest(full, Si["X"], pr, p, rna, ns, N, levels)
+    assert [tuple(b["params"]) for b in best] == [tuple(b["params"]) for b in host]
+    assert np.allclose([b["rmse"] for b in best], [b["rmse"] for b in host], rtol=1e-9, atol=1e-15)
+    assert np.array_equal(best[0]["solution"], host[0]["solution"])
+    # data that do not line up with the flat layout fall back to the trajectory path
+    Si2, best2 = sensitivity.sensitivity_analysis(theta, om.TIME_POINTS, ns, y0, "distmod", pr_data=pr, p_data=p,
+                                                  rna_data=sol[-8:, 0], N=4, num_levels=levels, seed=3, engine=engine)
+    assert len(best2) == 1 and "rmse" not in Si2
 
 
 def test_multistart_loss_batch_config4_shape(engine):
