@@ -199,6 +199,10 @@ __device__ __forceinline__ void dense_invert(int n, int ld, double* W, double* c
             if (ukj != 0.0)
                 for (int i = ty; i < n; i += NW) W[i * ld + j] = fma(-colk[i], ukj, W[i * ld + j]);
         }
+        // The sweep above rewrites row k and column k with unchanged values (their multiplier / pivot-row entry is
+        // zero); the write-back below gives them their new values.  With more than one warp per system these must
+        // not interleave — a late "unchanged" store would overwrite a new value — hence the barrier.
+        dsync<NT>();
         // column k <- -col/pivot, row k <- row/pivot, pivot <- 1/pivot
         for (int i = tid; i < n; i += NT) {
             if (i != k) {
