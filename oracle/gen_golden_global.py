@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — writes tests/golden/global_*.npz from the UNMODIFIED reference.
 
-Run in the build container:  python oracle/gen_golden_global.py
-For each kinetic model (0 distributive, 1 sequential, 4 saturating — `MODEL` is an import-time
+Run in the build container:  python oracle/gen_golden_global.py   (or `... only 2` for one kinetic model)
+For each kinetic model (0 distributive, 1 sequential, 2 combinatorial, 4 saturating — `MODEL` is an import-time
 constant of the reference, so each runs in its own subprocess) a REAL `global_model.network.System`
 is constructed around a small synthetic topology (the same arrays `phoskintime_b200.global_model.
 synthetic_system` builds), and the reference's own `simulate_odeint` (LSODA + finite-difference
@@ -23,7 +23,8 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tests", "golden")
 T_EVAL = np.array([0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 15.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])
 CASES = [(0, 10, 5, 3, 11), (0, 36, 12, 4, 12), (1, 14, 6, 4, 13), (4, 14, 6, 3, 14),   # model, N, K, max_sites, seed
-         (0, 120, 40, 4, 5, 2)]     # BASELINE configs[4] shape (state_dim ~ 500), 2 parameter vectors
+         (0, 120, 40, 4, 5, 2),     # BASELINE configs[4] shape (state_dim ~ 500), 2 parameter vectors
+         (2, 10, 5, 3, 21), (2, 24, 8, 4, 22)]   # combinatorial: one state per phosphorylation pattern
 
 
 def stub_modules(model, loss_mode):
@@ -67,14 +68,24 @@ def run_case(model, N, K, max_sites, seed, B=4):
                                 offset_y=s.idx.offset_y.copy(), offset_s=s.idx.offset_s.copy(),
                                 n_sites=s.idx.n_sites.copy(), state_dim=s.idx.state_dim,
                                 total_sites=s.idx.total_sites)
+    if model == 2:
+        idx.n_states = s.idx.n_states.copy()
     W = sparse.csr_matrix((s.W_data, s.W_indices, s.W_indptr), shape=(s.idx.total_sites, K))
     TF = sparse.csr_matrix((s.TF_data, s.TF_indices, s.TF_indptr), shape=(N, N))
     kin = types.SimpleNamespace(grid=s.kin_grid.copy(), Kmat=s.kin_Kmat.copy())
     ref = network.System(idx, W, TF, kin, {**s.defaults}, s.tf_deg.copy())
-    args = ref.odeint_args()
-    assert np.array_equal(args[22], s.driver_map), "driver_map built by the reference differs"
-    for a, b in zip(args, s.odeint_args()):
-        assert np.array_equal(np.asarray(a), np.asarray(b)), "odeint_args wire format mismatch"
+    if model == 2:
+        jac.build_S_cache_into(ref.S_cache, ref.W_indptr, ref.W_indices, ref.W_data, ref.kin_Kmat, ref.c_k)
+        args, mine = ref.odeint_args(ref.S_cache), s.odeint_args(s.build_S_cache())
+        assert len(args) == len(mine) == 27 and np.array_equal(args[24], s.driver_map)
+        assert np.allclose(args[9], mine[9], rtol=1e-14, atol=0.0), "S_cache mismatch"
+        for k, (a, b) in enumerate(zip(args, mine)):
+            assert k == 9 or np.array_equal(np.asarray(a), np.asarray(b)), f"odeint_args wire format mismatch at {k}"
+    else:
+        args = ref.odeint_args()
+        assert np.array_equal(args[22], s.driver_map), "driver_map built by the reference differs"
+        for a, b in zip(args, s.odeint_args()):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), "odeint_args wire format mismatch"
 
     rng = np.random.default_rng(seed + 100)
     P = np.empty((B, s.n_params))
@@ -87,7 +98,7 @@ def run_case(model, N, K, max_sites, seed, B=4):
         P[b] = s.pack_params(p)
         ref.update(**p)
         Ys.append(simulate.simulate_odeint(ref, T_EVAL, rtol=1e-8, atol=1e-8, mxstep=200000))
-        a = ref.odeint_args()
+        a = ref.odeint_args(ref.S_cache) if model == 2 else ref.odeint_args()    # S_cache: refreshed by simulate_odeint
         stops = np.unique(np.concatenate([T_EVAL, s.kin_grid]))
         y = ref.y0()
         rows = {0.0: y.copy()}
@@ -128,10 +139,12 @@ if __name__ == "__main__":
     elif len(sys.argv) > 1 and sys.argv[1] == "loss":
         run_losses(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     else:
+        # `python oracle/gen_golden_global.py only 2` regenerates the cases of one kinetic model
+        keep = (lambda c: c[0] == int(sys.argv[2])) if len(sys.argv) > 2 and sys.argv[1] == "only" else (lambda c: True)
         os.makedirs(OUT, exist_ok=True)
-        for c in CASES:
+        for c in filter(keep, CASES):
             subprocess.run([sys.executable, __file__, "case"] + [str(x) for x in c], check=True)
-        for model, N, *_ in CASES[:1] + CASES[2:3]:
+        for model, N, *_ in filter(keep, CASES[:1] + CASES[2:3] + CASES[5:6]):
             losses = {}
             for mode in (0, 1, 2, 3, 4, 5, 6, -1):
                 subprocess.run([sys.executable, __file__, "loss", str(model), str(N), str(mode)], check=True)

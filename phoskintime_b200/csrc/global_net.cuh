@@ -1,7 +1,8 @@
 // CTA-per-system kernel for the global coupled kinase-TF-protein network
 // (reference: global_model/jacspeedup.py:148-375 RHS wrappers, global_model/models.py:27-306 block
 // kinetics, simulate.py:34-80 integration, lossfn.py:113-246 loss, simulate.py:105-182 +
-// sensitivity.py:106-140 Morris scalar; models 0 distributive, 1 sequential, 4 saturating).
+// sensitivity.py:106-140 Morris scalar; models 0 distributive, 1 sequential, 4 saturating; model 2
+// combinatorial: jacspeedup.py:287-343, models.py:322-485, lossfn.py:248-382, simulate.py:135-158).
 //
 // Structure of the problem (what the design exploits):
 //   * protein i owns the block [mRNA, P0, site_1..site_ns]; phosphorylation rates S = W.(Kmat[:,bucket]*c_k)
@@ -74,7 +75,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int colbuf, rowbuf, bp, partial;  // TILE  > 0: Schur matrix in registers (Gauss-Jordan), exchange buffers
     int tfdata, tfdeg;                // staged topology (doubles)
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
-    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent;
+    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff;
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
 };
 
@@ -97,6 +98,8 @@ struct GlobalArgs {
     double *out_Y, *out_loss, *out_F, *out_metric;
     int *out_status, *out_nsteps, *out_nrej;
     double* traj;                     // [grid][T][n] scratch when out_Y is not requested
+    double* binv;                     // [grid][binv_stride] model 2: inverses of the per-protein pattern blocks
+    long long binv_stride;
     unsigned long long* counter;
 };
 
@@ -188,12 +191,14 @@ __device__ __forceinline__ double loss_atom(int mode, double diff, double obs, d
 __device__ __forceinline__ void loss_sums(const GlobalTopoDev& tp, const double* traj, int n, int mode, double* red,
                                           double& lp, double& lr, double& lph) {
     lp = 0.0; lr = 0.0; lph = 0.0;
+    const bool comb = tp.model == 2;          // lossfn.py:248-382: pattern states instead of [P0, sites]
     for (int k = threadIdx.x; k < tp.n_prot; k += GLOBAL_BLOCK) {
         const int i = tp.p_prot[k], st = tp.offset_y[i], ns = tp.n_sites[i];
         const double* rt = traj + (size_t)tp.t_prot[k] * n + st + 1;
         const double* rb = traj + (size_t)tp.prot_base * n + st + 1;
         double a1 = 0.0, b1 = 0.0;
-        for (int j = 0; j <= ns; ++j) { a1 += rt[j]; b1 += rb[j]; }
+        const int cnt = comb ? (1 << ns) : ns + 1;
+        for (int j = 0; j < cnt; ++j) { a1 += rt[j]; b1 += rb[j]; }
         const double pred = fmax(a1, 1e-9) / fmax(b1, 1e-9), obs = tp.obs_prot[k];
         lp = fma(tp.w_prot[k], loss_atom(mode, obs - pred, obs, pred), lp);
     }
@@ -204,8 +209,20 @@ __device__ __forceinline__ void loss_sums(const GlobalTopoDev& tp, const double*
         lr = fma(tp.w_rna[k], loss_atom(mode, obs - pred, obs, pred), lr);
     }
     for (int k = threadIdx.x; k < tp.n_pho; k += GLOBAL_BLOCK) {
-        const int col = tp.offset_y[tp.p_pho[k]] + 2 + tp.s_pho[k];
-        const double pred = fmax(traj[(size_t)tp.t_pho[k] * n + col], 1e-9) / fmax(traj[(size_t)tp.pho_base * n + col], 1e-9);
+        double a1, b1;
+        if (comb) {                           // site j = sum of the patterns with bit j set
+            const int i = tp.p_pho[k], st = tp.offset_y[i] + 1, nst = 1 << tp.n_sites[i], j = tp.s_pho[k];
+            const double* rt = traj + (size_t)tp.t_pho[k] * n + st;
+            const double* rb = traj + (size_t)tp.pho_base * n + st;
+            a1 = 0.0; b1 = 0.0;
+            for (int m = 0; m < nst; ++m)
+                if ((m >> j) & 1) { a1 += rt[m]; b1 += rb[m]; }
+        } else {
+            const int col = tp.offset_y[tp.p_pho[k]] + 2 + tp.s_pho[k];
+            a1 = traj[(size_t)tp.t_pho[k] * n + col];
+            b1 = traj[(size_t)tp.pho_base * n + col];
+        }
+        const double pred = fmax(a1, 1e-9) / fmax(b1, 1e-9);
         const double obs = tp.obs_pho[k];
         lph = fma(tp.w_pho[k], loss_atom(mode, obs - pred, obs, pred), lph);
     }
@@ -221,6 +238,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
                                                const int* mt_rna, const int* mt_pho, int mb_prot, int mb_rna, int mb_pho,
                                                double* red) {
     const int N = tp.N;
+    const bool comb = tp.model == 2;          // simulate.py:135-158
     double s1 = 0.0, s2 = 0.0;
     const int np_ = N * n_mt_prot, nr_ = N * n_mt_rna;
     for (int k = threadIdx.x; k < np_; k += GLOBAL_BLOCK) {
@@ -229,7 +247,8 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
         const double* rt = traj + (size_t)ti * n + st + 1;
         const double* rb = traj + (size_t)mb_prot * n + st + 1;
         double a1 = 0.0, b1 = 0.0;
-        for (int j = 0; j <= ns; ++j) { a1 += rt[j]; b1 += rb[j]; }
+        const int cnt = comb ? (1 << ns) : ns + 1;
+        for (int j = 0; j < cnt; ++j) { a1 += rt[j]; b1 += rb[j]; }
         const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
         s1 += fc;
         s2 = fma(fc, fc, s2);
@@ -246,8 +265,18 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
             const int st = tp.offset_y[i], ns = tp.n_sites[i];
             for (int k = threadIdx.x; k < ns * n_mt_pho; k += GLOBAL_BLOCK) {
                 const int j = k / n_mt_pho, ti = mt_pho[k - j * n_mt_pho];
-                const int col = st + 2 + j;
-                const double fc = fmax(traj[(size_t)ti * n + col], 1e-12) / fmax(traj[(size_t)mb_pho * n + col], 1e-12);
+                double a1, b1;
+                if (comb) {
+                    const double* rt = traj + (size_t)ti * n + st + 1;
+                    const double* rb = traj + (size_t)mb_pho * n + st + 1;
+                    a1 = 0.0; b1 = 0.0;
+                    for (int m = 0; m < (1 << ns); ++m)
+                        if ((m >> j) & 1) { a1 += rt[m]; b1 += rb[m]; }
+                } else {
+                    a1 = traj[(size_t)ti * n + st + 2 + j];
+                    b1 = traj[(size_t)mb_pho * n + st + 2 + j];
+                }
+                const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
                 s1 += fc;
                 s2 = fma(fc, fc, s2);
             }
@@ -295,13 +324,189 @@ struct GlobalCtx {
     // Gauss-Jordan exchange buffers
     double *colbuf, *rowbuf, *bp, *partial;
     int *piv, *pinv;
+    // model 2: this CTA's block-inverse scratch (global memory, L2 resident) and each protein's offset into it
+    double* binv;
+    const int* boff;
 };
+
+
+// ------------------------------------------------------------------------------------------------
+// Combinatorial model (MODEL 2): protein i owns [mRNA, pattern_0 .. pattern_{2^ns - 1}], pattern m = bitmask
+// of phosphorylated sites (models.py:322-432):
+//   d pattern_m/dt = [m == 0] C R - out_m pattern_m + sum_{j in m} S_j pattern_{m ^ j} + E sum_{j not in m} pattern_{m | j}
+//   out_m = [m == 0] D + sum_{j in m} (E + Dp_j + D) + sum_{j not in m} S_j
+// The wrapper consults no driver map (jacspeedup.py:318-325) and squashes the TF input once, the kernel again.
+// The block Jacobian is a hypercube, not a tree: the 2^ns x 2^ns matrix  M = I - c K_i  of every protein is
+// INVERTED per step by 16 lanes in registers (lane = row, unpivoted Gauss-Jordan: M is strictly column diagonally
+// dominant for non-negative rates) and the inverse is parked in this CTA's L2-resident scratch, stored so that the
+// six stage solves read it coalesced.  Everything around the block (mRNA row, Schur coupling through the
+// transcription gains, unit responses w) is shared with the other kinetic models.
+// ------------------------------------------------------------------------------------------------
+constexpr int COMB_MAX_STATES = 16;   // ns <= 4
+
+__device__ __forceinline__ double comb_state_rhs(const GlobalCtx& cx, const double* src, int i, int m) {
+    const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
+    const double* blk = src + st + 1;
+    const double Di = cx.cD[i], Ei = cx.cE[i];
+    double out = (m == 0) ? Di : 0.0, in = (m == 0) ? cx.cC[i] * src[st] : 0.0;
+    for (int j = 0; j < ns; ++j) {
+        const int bit = 1 << j;
+        const double s = cx.Sall[ss + j];
+        if (m & bit) { out += Ei + cx.cDp[ss + j] + Di; in = fma(s, blk[m ^ bit], in); }
+        else { out += s; in = fma(Ei, blk[m | bit], in); }
+    }
+    return fma(-out, blk[m], in);
+}
+
+// Inverses of all pattern blocks for c = gamma*h, the unit responses w of the pattern states and m_i.
+// Needs facA[st] = 1/(1 + c B) and mult[st+1] = c C (written by eval_rhs_comb) behind a barrier.
+__device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
+    const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const int N = cx.N;
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        const int i = i0 + grp;
+        const bool act = i < N;
+        const int ns = act ? cx.ns[i] : 0, st = act ? cx.offy[i] : 0, ss = act ? cx.offs[i] : 0;
+        const int nst = act ? (1 << ns) : 0;
+        const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));     // the two halves of a warp step together
+        const bool live = r < nst;
+        double a[COMB_MAX_STATES];                                            // row r of M (identity outside the block)
+#pragma unroll
+        for (int q = 0; q < COMB_MAX_STATES; ++q) a[q] = (q == r) ? 1.0 : 0.0;
+        if (live) {
+            const double Di = cx.cD[i], Ei = cx.cE[i];
+            double out = (r == 0) ? Di : 0.0;
+            for (int j = 0; j < ns; ++j) {
+                const int bit = 1 << j;
+                const double s = cx.Sall[ss + j];
+                const bool set = (r & bit) != 0;
+                out += set ? Ei + cx.cDp[ss + j] + Di : s;
+                const int col = r ^ bit;
+                const double v = -c * (set ? s : Ei);
+#pragma unroll
+                for (int q = 0; q < COMB_MAX_STATES; ++q)
+                    if (q == col) a[q] = v;
+            }
+            const double dg = fma(c, out, 1.0);
+#pragma unroll
+            for (int q = 0; q < COMB_MAX_STATES; ++q)
+                if (q == r) a[q] = dg;
+        }
+#pragma unroll
+        for (int k = 0; k < COMB_MAX_STATES; ++k) {
+            if (k < smax) {
+                double prow[COMB_MAX_STATES];
+#pragma unroll
+                for (int q = 0; q < COMB_MAX_STATES; ++q) prow[q] = __shfl_sync(0xffffffffu, a[q], k, 16);
+                const double p = fast_rcp(prow[k]);
+                const bool me = r == k;
+                const double coef = me ? p : -a[k] * p;          // pivot row: row/pivot; other rows: -multiplier
+#pragma unroll
+                for (int q = 0; q < COMB_MAX_STATES; ++q)
+                    if (q != k) a[q] = fma(coef, prow[q], me ? 0.0 : a[q]);
+                a[k] = coef;
+            }
+        }
+        double wr = 0.0;
+        if (live) {
+            double* bi = cx.binv + cx.boff[i];
+#pragma unroll
+            for (int q = 0; q < COMB_MAX_STATES; ++q)
+                if (q < nst) bi[q * nst + r] = a[q];              // element (r, q): lanes r contiguous
+            wr = a[0] * cx.mult[st + 1] * cx.facA[st];            // response of pattern r to a unit mRNA source
+            cx.w[st + 1 + r] = wr;
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) wr += __shfl_xor_sync(0xffffffffu, wr, o);
+        if (act && r == 0) cx.m[i] = wr;
+    }
+}
+
+// x0 = A^-1 b for the combinatorial blocks (in place), z0_i = total-protein part into pvec, z cleared
+__device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x) {
+    const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const int N = cx.N;
+    for (int i0 = 0; i0 < N; i0 += 16) {
+        const int i = i0 + grp;
+        const bool act = i < N;
+        const int st = act ? cx.offy[i] : 0;
+        const int nst = act ? (1 << cx.ns[i]) : 0;
+        const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));
+        const bool live = r < nst;
+        double xr = 0.0, b = 0.0;
+        if (act) {
+            xr = x[st] * cx.facA[st];
+            if (live) b = x[st + 1 + r];
+            if (r == 0) b = fma(cx.mult[st + 1], xr, b);          // translation feeds pattern 0
+        }
+        const double* bi = cx.binv + (act ? cx.boff[i] : 0);
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < COMB_MAX_STATES; ++q) {
+            if (q < smax) {
+                const double bq = __shfl_sync(0xffffffffu, b, q, 16);
+                if (live && q < nst) acc = fma(bi[q * nst + r], bq, acc);
+            }
+        }
+        double zs = live ? acc : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+        if (live) x[st + 1 + r] = acc;
+        if (act && r == 0) {
+            x[st] = xr;
+            cx.pvec[i] = zs;
+            cx.z[i] = 0.0;
+        }
+    }
+}
+
+template <bool FACTOR>
+__device__ __forceinline__ void eval_rhs_comb(const GlobalCtx& cx, const double* src, double* dst, double c) {
+    const int N = cx.N;
+    for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+        const int st = cx.offy[i], nst = 1 << cx.ns[i];
+        double pv = 0.0;
+        for (int m = 0; m < nst; ++m) pv += src[st + 1 + m];
+        cx.pvec[i] = pv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+        const int st = cx.offy[i];
+        double v = 0.0;
+        for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) v = fma(cx.tfdata[q], cx.pvec[cx.tfidx[q]], v);
+        const double itd = cx.tfdeg[i];
+        v *= itd;
+        double synth, dsdv;
+        synth_rate(2, v, cx.cA[i], cx.tfs, synth, dsdv);
+        dst[st] = fma(-cx.cB[i], src[st], synth);
+        if (FACTOR) {
+            cx.g[i] = dsdv * itd;
+            const double iRr = fast_rcp(fma(c, cx.cB[i], 1.0));
+            cx.facA[st] = iRr;
+            cx.w[st] = iRr;
+            cx.mult[st + 1] = c * cx.cC[i];
+        }
+    }
+    for (int s = threadIdx.x; s < cx.n; s += GLOBAL_BLOCK) {
+        const int i = cx.sprot[s], m = s - cx.offy[i] - 1;
+        if (m >= 0) dst[s] = comb_state_rhs(cx, src, i, m);
+    }
+    if (FACTOR) {
+        __syncthreads();
+        comb_factor(cx, c);
+    }
+    __syncthreads();
+}
 
 // f(src) -> dst.  With FACTOR: also the transcription gains g_i, the per-protein tree factorisation of
 // A = I - c J_blk, the unit responses w = A^-1 e_R and m_i.  Two phases, thread per protein.
-template <bool FACTOR>
+template <bool FACTOR, bool COMB>
 __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src, double* dst, double c) {
     const int N = cx.N, model = cx.model;
+    if constexpr (COMB) {
+        eval_rhs_comb<FACTOR>(cx, src, dst, c);
+        return;
+    }
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
         const int d = cx.drv[i];
         double pv;
@@ -693,7 +898,7 @@ __device__ __forceinline__ void lu_apply(const GlobalCtx& cx) {
 }
 
 // x (vector in shared memory, holds the right-hand side b) <- (I - cJ)^-1 b
-template <int TILE>
+template <int TILE, bool COMB>
 __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1]
 #ifdef PK_GLOBAL_TRACE
                                             , long long& ph_last_
@@ -702,6 +907,8 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
     const int N = cx.N;
     const bool chain = cx.model == 1;
     // block solves x0 = A^-1 b and z0 (into pvec)
+    if constexpr (COMB) comb_block_solve(cx, x);
+    else
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
         const int st = cx.offy[i], ns = cx.ns[i];
         const double xr = x[st] * cx.facA[st];
@@ -744,8 +951,9 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
     PH(12);
 }
 
-template <int TILE>
-__global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1) global_net_kernel(const GlobalArgs a) {
+// COMB: the combinatorial kinetic model (its own instantiation, so that the other models compile exactly as without it)
+template <int TILE, bool COMB>
+__global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB) ? 2 : 1) global_net_kernel(const GlobalArgs a) {
     extern __shared__ double smem[];
     const GlobalTopoDev& tp = a.tp;
     const GlobalSmem& L = a.sm;
@@ -761,7 +969,8 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                  ismem + L.i_offy, ismem + L.i_offs, ismem + L.i_ns, ismem + L.i_drv, ismem + L.i_tfptr, ismem + L.i_tfidx,
                  ismem + L.i_qlist, ismem + L.i_qpos, ismem + L.i_sprot, (const unsigned char*)(ismem + L.i_ent),
                  smem + L.tfdata, smem + L.tfdeg,
-                 smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv};
+                 smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
+                 a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff};
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
     cx.cC = cx.cB + N;
@@ -794,7 +1003,12 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
         for (int q = threadIdx.x; q < tp.nQ; q += GLOBAL_BLOCK) ismem[L.i_qlist + q] = tp.qlist[q];
         for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {          // state -> protein map
             const int st = tp.offset_y[i], ns = tp.n_sites[i];
-            for (int j = 0; j < 2 + ns; ++j) ismem[L.i_sprot + st + j] = i;
+            const int bl = tp.model == 2 ? 1 + (1 << ns) : 2 + ns;
+            for (int j = 0; j < bl; ++j) ismem[L.i_sprot + st + j] = i;
+            int bo = 0;                                                // model 2: offset of the block inverse (4^ns each)
+            if (tp.model == 2)
+                for (int k = 0; k < i; ++k) bo += 1 << (2 * tp.n_sites[k]);
+            ismem[L.i_boff + i] = bo;
         }
         if constexpr (TILE > 0) {
             // static sparsity of the Schur block as seen by this thread's tile (see gj_assemble); rows of the uploaded
@@ -880,7 +1094,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
             }
             if (si == 0) {
                 // initial step: 1% of the error-weighted time scale |y|/|f|
-                eval_rhs<false>(cx, y, arg, 0.0);
+                eval_rhs<false, COMB>(cx, y, arg, 0.0);
                 float d0 = 0.f, d1 = 0.f;
                 for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
                     const double sc = 1.0 / fma(a.rtol, fabs(y[i]), a.atol);
@@ -914,7 +1128,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
 
                 // stage 1: f(y), Jacobian pieces, factorisation
                 PH(0);
-                eval_rhs<true>(cx, y, U, STEP_C);
+                eval_rhs<true, COMB>(cx, y, U, STEP_C);
                 PH(1);
                 if (cx.nQ > 0) {
                     if constexpr (TILE > 0) {
@@ -932,7 +1146,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                 }
                 __syncthreads();
                 PH(4);
-                schur_solve<TILE>(cx, U, STEP_C, A PH_ARG);
+                schur_solve<TILE, COMB>(cx, U, STEP_C, A PH_ARG);
                 // stages 2..6:  (I - cJ) U_s = c ( f(y + sum a_sj U_j) + sum c_sj/h U_j )
 #pragma unroll 1
                 for (int s = 1; s < 6; ++s) {
@@ -951,7 +1165,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                     __syncthreads();
                     PH(5);
                     double* Us = U + s * n;
-                    eval_rhs<false>(cx, arg, Us, 0.0);
+                    eval_rhs<false, COMB>(cx, arg, Us, 0.0);
                     PH(6);
                     dispatch_uniform<1, 6>(s, [&](auto S) {
                         constexpr int sc = decltype(S)::value;
@@ -965,7 +1179,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6) ? 2 : 1
                     });
                     __syncthreads();
                     PH(7);
-                    schur_solve<TILE>(cx, Us, STEP_C, A PH_ARG);
+                    schur_solve<TILE, COMB>(cx, Us, STEP_C, A PH_ARG);
                 }
                 // y_new = arg_6 + U_6, err = U_6
                 float err = 0.f;

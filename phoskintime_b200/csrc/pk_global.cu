@@ -24,6 +24,7 @@ struct GlobalTopoHost {
     std::vector<double> kin_grid;
     bool has_loss = false;
     int T_loss_max = -1;              // largest time index the loss tables reference
+    size_t binv_elems = 0;            // model 2: block-inverse scratch per resident system (doubles)
 
     static void free_list(std::vector<void*>& v) {
         for (void* p : v) cudaFree(p);
@@ -131,19 +132,27 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     L.i_pinv = itake(16 * pk::GJ_MAX_TILE);
     L.i_sprot = itake(n);
     L.i_ent = itake(L.tile * L.tile * pk::GLOBAL_BLOCK / 4);    // one byte per tile slot and thread
+    L.i_boff = itake(N);
     o += (io + 1) / 2;
     L.total = o;
     th->smem_bytes = (size_t)o * sizeof(double);
 }
 
 typedef void (*global_kernel_t)(const pk::GlobalArgs);
-global_kernel_t kernel_for_tile(int tile) {
+global_kernel_t kernel_for_tile(int tile, bool comb) {
+    if (comb) switch (tile) {
+        case 2: return pk::global_net_kernel<2, true>;
+        case 4: return pk::global_net_kernel<4, true>;
+        case 6: return pk::global_net_kernel<6, true>;
+        case 8: return pk::global_net_kernel<8, true>;
+        default: return pk::global_net_kernel<0, true>;
+    }
     switch (tile) {
-        case 2: return pk::global_net_kernel<2>;
-        case 4: return pk::global_net_kernel<4>;
-        case 6: return pk::global_net_kernel<6>;
-        case 8: return pk::global_net_kernel<8>;
-        default: return pk::global_net_kernel<0>;
+        case 2: return pk::global_net_kernel<2, false>;
+        case 4: return pk::global_net_kernel<4, false>;
+        case 6: return pk::global_net_kernel<6, false>;
+        case 8: return pk::global_net_kernel<8, false>;
+        default: return pk::global_net_kernel<0, false>;
     }
 }
 
@@ -157,9 +166,10 @@ extern "C" {
 
 int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_id) {
     if (!h || !tp || !topo_id) return fail("pk_global_upload: null argument");
-    if (tp->model != 0 && tp->model != 1 && tp->model != 4)
-        return fail("pk_global_upload: kinetic model must be 0 (distributive), 1 (sequential) or 4 (saturating); "
-                    "the combinatorial model 2 is not supported");
+    if (tp->model != 0 && tp->model != 1 && tp->model != 2 && tp->model != 4)
+        return fail("pk_global_upload: kinetic model must be 0 (distributive), 1 (sequential), 2 (combinatorial) or "
+                    "4 (saturating)");
+    const bool comb = tp->model == 2;
     const int N = tp->N, K = tp->K, nb = tp->n_bins;
     if (N < 1 || K < 1 || nb < 1) return fail("pk_global_upload: N, K and n_bins must be positive");
     if (!tp->n_sites || !tp->W_indptr || !tp->TF_indptr || !tp->kin_grid || !tp->kin_Kmat || !tp->tf_deg ||
@@ -167,12 +177,17 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         return fail("pk_global_upload: missing array");
     std::vector<int> off_y(N), off_s(N);
     int n = 0, S = 0;
+    size_t binv_elems = 0;            // model 2: doubles of block-inverse scratch per resident system
     for (int i = 0; i < N; ++i) {
         if (tp->n_sites[i] < 0) return fail("pk_global_upload: negative n_sites");
+        if (comb && tp->n_sites[i] > 4)
+            return fail("pk_global_upload: the combinatorial model supports at most 4 sites per protein (16 pattern states)");
         off_y[i] = n;
         off_s[i] = S;
-        n += 2 + tp->n_sites[i];
+        // network.py:144-149: combinatorial block = mRNA + 2^ns pattern states, otherwise mRNA + P0 + ns sites
+        n += comb ? 1 + (1 << tp->n_sites[i]) : 2 + tp->n_sites[i];
         S += tp->n_sites[i];
+        binv_elems += comb ? (size_t)1 << (2 * tp->n_sites[i]) : 0;
     }
     if (tp->W_indptr[0] != 0 || tp->TF_indptr[0] != 0) return fail("pk_global_upload: indptr must start at 0");
     for (int s = 0; s < S; ++s)
@@ -193,6 +208,9 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     for (int b = 1; b < nb; ++b)
         if (!(tp->kin_grid[b] > tp->kin_grid[b - 1])) return fail("pk_global_upload: kin_grid must be strictly increasing");
     CK(cudaSetDevice(h->device));
+    // The combinatorial wrapper never consults the driver map (jacspeedup.py:318-325)
+    std::vector<int> drv(tp->driver_map, tp->driver_map + N);
+    if (comb) std::fill(drv.begin(), drv.end(), -1);
 
     // canonical TF rows for the device: column indices sorted and unique (duplicates summed) — the kernel's static
     // sparsity table of the Schur block needs at most one entry per (gene, regulator)
@@ -218,7 +236,7 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         for (int q = 0; q < nnzC; ++q)
             if (tf_val[q] != 0.0) used[tf_idx[q]] = 1;
         for (int i = 0; i < N; ++i)
-            if (used[i] && tp->driver_map[i] < 0) {
+            if (used[i] && drv[i] < 0) {
                 qpos[i] = (int)qlist.size();
                 qlist.push_back(i);
             }
@@ -229,6 +247,7 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     pk::GlobalTopoDev& d = th->dev;
     d.model = tp->model; d.N = N; d.K = K; d.nb = nb; d.n = n; d.S = S; d.nQ = (int)qlist.size();
     th->P = K + 5 * N + S + 1;
+    th->binv_elems = binv_elems;
     th->kin_grid.assign(tp->kin_grid, tp->kin_grid + nb);
     cudaError_t e = cudaSuccess;
 #define UP(field, src, count)                                                     \
@@ -245,7 +264,7 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     UP(kin_grid, tp->kin_grid, nb);
     UP(kin_Kmat, tp->kin_Kmat, (size_t)K * nb);
     UP(tf_deg, tp->tf_deg, N);
-    UP(driver_map, tp->driver_map, N);
+    UP(driver_map, drv.data(), N);
     UP(qlist, qlist.data(), qlist.size());
     UP(qpos, qpos.data(), N);
 #undef UP
@@ -452,7 +471,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     a.y0_stride = j->y0_stride;
     a.counter = h->counter;
 
-    const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile);
+    const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile, d.model == 2);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th->smem_bytes));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pk::GLOBAL_BLOCK, th->smem_bytes));
@@ -486,6 +505,11 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     if (!a.out_Y) {                                   // per-CTA trajectory slot (reused for every system of that CTA)
         CK(h->g_traj.ensure((size_t)grid * TN * sizeof(double)));
         a.traj = (double*)h->g_traj.p;
+    }
+    if (th->binv_elems) {                             // model 2: per-CTA block inverses (rewritten every step)
+        CK(h->g_binv.ensure((size_t)grid * th->binv_elems * sizeof(double)));
+        a.binv = (double*)h->g_binv.p;
+        a.binv_stride = (long long)th->binv_elems;
     }
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(h->ev0, st));

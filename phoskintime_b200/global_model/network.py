@@ -5,13 +5,17 @@ kinase->site matrix W and the TF->gene matrix, the kinase step-input table and `
 — the 23-tuple that is the wire format into its Numba kernels (network.py:508-526).  Building the
 topology from CSV/XLSX files (Index, buildmat, io) is out of scope: a
 `GlobalSystem` is constructed from the already-indexed arrays, which is exactly what crosses the
-boundary.  The combinatorial model (MODEL 2) is not supported.
+boundary.  The combinatorial model (MODEL 2: one state per phosphorylation pattern, block
+`[mRNA, mask_0 .. mask_{2^ns-1}]`, network.py:131-146) has its own 27-tuple (network.py:471-505) with the
+per-bucket rate table `S_cache` (jacspeedup.py:114-145) and the hypercube transition lists (models.py:435-485).
 """
 from types import SimpleNamespace
 
 import numpy as np
 
-MODEL_IDS = {"distributive": 0, "sequential": 1, "saturating": 4, "saturation": 4, 0: 0, 1: 1, 4: 4}
+MODEL_IDS = {"distributive": 0, "sequential": 1, "combinatorial": 2, "saturating": 4, "saturation": 4,
+             0: 0, 1: 1, 2: 2, 4: 4}
+MAX_COMB_SITES = 4          # combinatorial blocks are inverted by 16 lanes in registers (csrc/global_net.cuh)
 PARAM_KEYS = ("c_k", "A_i", "B_i", "C_i", "D_i", "Dp_i", "E_i")
 
 
@@ -34,10 +38,20 @@ class GlobalSystem:
         N = n_sites.size
         offset_y = np.zeros(N, np.int32)
         offset_s = np.zeros(N, np.int32)
-        offset_y[1:] = np.cumsum(2 + n_sites)[:-1]
+        if self.model == 2:
+            if n_sites.size and int(n_sites.max()) > MAX_COMB_SITES:
+                raise ValueError(f"combinatorial model: at most {MAX_COMB_SITES} sites per protein")
+            n_states = (1 << n_sites).astype(np.int32)          # network.py:131-132
+            block = 1 + n_states
+        else:
+            n_states = None
+            block = 2 + n_sites
+        offset_y[1:] = np.cumsum(block)[:-1]
         offset_s[1:] = np.cumsum(n_sites)[:-1]
         self.idx = SimpleNamespace(N=N, n_sites=n_sites, offset_y=offset_y, offset_s=offset_s,
-                                   state_dim=int((2 + n_sites).sum()), total_sites=int(n_sites.sum()))
+                                   state_dim=int(block.sum()), total_sites=int(n_sites.sum()))
+        if n_states is not None:
+            self.idx.n_states = n_states
         self.W_indptr, self.W_indices, self.W_data = i32(W_indptr), i32(W_indices), f64(W_data)
         self.TF_indptr, self.TF_indices, self.TF_data = i32(TF_indptr), i32(TF_indices), f64(TF_data)
         self.n_W_rows, self.n_TF_rows = self.W_indptr.size - 1, self.TF_indptr.size - 1
@@ -54,6 +68,12 @@ class GlobalSystem:
             setattr(self, k, self.defaults[k].copy())
         self.tf_scale = self.defaults["tf_scale"]
         self.custom_y0 = None if y0 is None else f64(y0).copy()
+        if self.model == 2:
+            # network.py:278-291: work buffers, per-bucket rate table and the hypercube transition lists
+            self.P_vec_work = np.zeros(self.n_TF_rows)
+            self.TF_in_work = np.zeros(self.n_TF_rows)
+            self.S_cache = np.zeros((self.n_W_rows, self.kin_Kmat.shape[1]))
+            (self.trans_from, self.trans_to, self.trans_site, self.trans_off, self.trans_n) = comb_transitions(n_sites)
         self._topo_id = {}          # engine id -> uploaded topology id
         self._loss_key = {}         # engine id -> loss-table dict currently installed
 
@@ -70,18 +90,37 @@ class GlobalSystem:
         self.tf_scale = float(tf_scale)
 
     def y0(self):
-        """network.py:421-441: custom y0 if set, else mRNA = P0 = 1 and 0.01 per site."""
+        """network.py:421-441: custom y0 if set, else mRNA = P0 = 1 and 0.01 per site (model 2: per
+        phosphorylated pattern)."""
         if self.custom_y0 is not None:
             return self.custom_y0.copy()
         y = np.zeros(self.idx.state_dim)
         for i in range(self.idx.N):
             st = self.idx.offset_y[i]
             y[st] = y[st + 1] = 1.0
-            y[st + 2:st + 2 + self.idx.n_sites[i]] = 0.01
+            extra = self.idx.n_states[i] - 1 if self.model == 2 else self.idx.n_sites[i]
+            y[st + 2:st + 2 + extra] = 0.01
         return y
 
-    def odeint_args(self):
-        """The reference's 23-tuple (network.py:508-526)."""
+    def build_S_cache(self):
+        """jacspeedup.py:114-145: S_cache[site, bucket] = sum_k W[site,k] * Kmat[k,bucket] * c_k (host, once per
+        parameter set; a few thousand flops of argument packing)."""
+        Kc = self.kin_Kmat * self.c_k[:, None]
+        for i in range(self.n_W_rows):
+            q = slice(self.W_indptr[i], self.W_indptr[i + 1])
+            self.S_cache[i, :] = self.W_data[q] @ Kc[self.W_indices[q], :]
+        return self.S_cache
+
+    def odeint_args(self, S_cache=None):
+        """The reference's 23-tuple (network.py:508-526); model 2: the 27-tuple of network.py:471-505."""
+        if self.model == 2:
+            if S_cache is None:
+                raise ValueError("MODEL==2 requires S_cache (total_sites x n_timebins).")
+            return (self.c_k, self.A_i, self.B_i, self.C_i, self.D_i, self.Dp_i, self.E_i, float(self.tf_scale),
+                    self.kin_grid, S_cache, self.TF_indptr, self.TF_indices, self.TF_data, int(self.n_TF_rows),
+                    self.idx.offset_y, self.idx.offset_s, self.idx.n_sites, self.idx.n_states,
+                    self.trans_from, self.trans_to, self.trans_site, self.trans_off, self.trans_n,
+                    self.tf_deg, self.driver_map, self.P_vec_work, self.TF_in_work)
         return (self.c_k, self.A_i, self.B_i, self.C_i, self.D_i, self.Dp_i, self.E_i, float(self.tf_scale),
                 self.kin_grid, self.kin_Kmat, self.W_indptr, self.W_indices, self.W_data, int(self.n_W_rows),
                 self.TF_indptr, self.TF_indices, self.TF_data, int(self.n_TF_rows),
@@ -117,8 +156,29 @@ class GlobalSystem:
                 "W_indptr": self.W_indptr, "W_indices": self.W_indices, "W_data": self.W_data,
                 "n_W_rows": self.n_W_rows, "TF_indptr": self.TF_indptr, "TF_indices": self.TF_indices,
                 "TF_data": self.TF_data, "kin_grid": self.kin_grid, "kin_Kmat": self.kin_Kmat,
-                "tf_deg": self.tf_deg, "driver_map": self.driver_map, "y0": self.y0(),
+                "tf_deg": self.tf_deg, "driver_map": self.driver_map, "y0": self.y0(), "model": self.model,
                 "defaults": {**{k: self.defaults[k].copy() for k in PARAM_KEYS}, "tf_scale": self.defaults["tf_scale"]}}
+
+
+def comb_transitions(n_sites):
+    """Forward (phosphorylation) edges of every protein's pattern hypercube, flattened — the arrays
+    models.py:435-485 hands to the Numba kernel: edge m -> m | (1 << j) for every unset bit j, patterns in
+    ascending order, sites in ascending order inside a pattern."""
+    frm, to, site = [], [], []
+    off = np.zeros(len(n_sites), np.int32)
+    cnt = np.zeros(len(n_sites), np.int32)
+    for i, ns in enumerate(np.asarray(n_sites, int)):
+        off[i] = len(frm)
+        if ns > 0:
+            m = np.repeat(np.arange(1 << ns), ns)
+            j = np.tile(np.arange(ns), 1 << ns)
+            free = (m >> j) & 1 == 0
+            frm.extend(m[free].tolist())
+            to.extend((m[free] | (1 << j[free])).tolist())
+            site.extend(j[free].tolist())
+        cnt[i] = len(frm) - off[i]
+    i32 = lambda a: np.asarray(a, dtype=np.int32)
+    return i32(frm), i32(to), i32(site), off, cnt
 
 
 def synthetic_system(seed=0, N=120, K=40, max_sites=4, w_density=0.08, tf_density=0.03, n_driven=None,
@@ -173,7 +233,8 @@ def synthetic_loss_data(sys_, time_grid, seed=0, frac=0.5):
     rng = np.random.default_rng(seed)
     tg = np.asarray(time_grid, float)
     idx = sys_.idx
-    prot_map = np.stack([idx.offset_y, idx.n_sites], axis=1).astype(np.int32)
+    # cache.py:138-145: second column = n_states for the combinatorial model, n_sites otherwise
+    prot_map = np.stack([idx.offset_y, idx.n_states if sys_.model == 2 else idx.n_sites], axis=1).astype(np.int32)
     base = {"prot_base_idx": int(np.argmin(np.abs(tg - 0.0))), "rna_base_idx": int(np.argmin(np.abs(tg - 4.0))),
             "pho_base_idx": int(np.argmin(np.abs(tg - 0.0)))}
     t_all = np.arange(tg.size)

@@ -77,27 +77,37 @@ def metric_time_indices(times, t_points_p, t_points_r, t_points_pho):
 
 
 def LOSS_FN(Y, p_prot, t_prot, obs_prot, w_prot, p_rna, t_rna, obs_rna, w_rna, p_pho, s_pho, t_pho, obs_pho, w_pho,
-            prot_map, prot_base_idx, rna_base_idx, pho_base_idx, *, loss_mode=0, engine=None):
-    """Reference signature of `LOSS_FN` (global_model/lossfn.py:113-121, :386) for models 0/1/4:
-    one trajectory Y[T, state_dim] -> (loss_p, loss_r, loss_ph).  `prot_map[i] = (offset_y, n_sites)`
-    (cache.py:128-139) is all the topology the loss needs, so a loss-only topology is uploaded per
-    distinct prot_map and cached."""
+            prot_map, prot_base_idx, rna_base_idx, pho_base_idx, *, loss_mode=0, model=0, engine=None):
+    """Reference signature of `LOSS_FN` (global_model/lossfn.py:113-121, :386): one trajectory
+    Y[T, state_dim] -> (loss_p, loss_r, loss_ph).  The reference binds `loss_function_comb` for MODEL 2 and
+    `loss_function_noncomb` otherwise at import time (lossfn.py:386); here `model` selects.
+    `prot_map[i] = (offset_y, n_sites)` — `(offset_y, n_states)` for the combinatorial model (cache.py:138-145) —
+    is all the topology the loss needs, so a loss-only topology is uploaded per distinct prot_map and cached."""
     eng = engine or get_engine()
     prot_map = np.ascontiguousarray(prot_map, dtype=np.int32)
-    key = (id(eng), prot_map.tobytes())
+    comb = int(model) == 2
+    key = (id(eng), comb, prot_map.tobytes())
     topo = _LOSS_TOPOS.get(key)
     if topo is None:
         from .network import GlobalSystem
-        n_sites = prot_map[:, 1]
+        if comb:
+            n_states = prot_map[:, 1]
+            n_sites = np.round(np.log2(np.maximum(n_states, 1))).astype(np.int32)
+            if not np.array_equal(1 << n_sites, n_states):
+                raise ValueError("combinatorial prot_map: second column must be 2**n_sites (cache.py:145)")
+            block = 1 + n_states
+        else:
+            n_sites = prot_map[:, 1]
+            block = 2 + n_sites
         N, S = n_sites.size, int(n_sites.sum())
-        if not np.array_equal(prot_map[:, 0], np.concatenate([[0], np.cumsum(2 + n_sites)[:-1]])):
-            raise ValueError("prot_map offsets must be the packed [mRNA, P0, sites...] layout (network.py:28-167)")
+        if not np.array_equal(prot_map[:, 0], np.concatenate([[0], np.cumsum(block)[:-1]])):
+            raise ValueError("prot_map offsets must be the packed per-protein block layout (network.py:28-167)")
         z = np.zeros(N)
         shell = GlobalSystem(n_sites=n_sites, W_indptr=np.zeros(S + 1, np.int32), W_indices=[], W_data=[],
                              TF_indptr=np.zeros(N + 1, np.int32), TF_indices=[], TF_data=[], kin_grid=[0.0],
                              kin_Kmat=np.ones((1, 1)), tf_deg=np.ones(N), driver_map=np.full(N, -1),
                              defaults={"c_k": [1.0], "A_i": z, "B_i": z, "C_i": z, "D_i": z, "Dp_i": np.zeros(S), "E_i": z,
-                                       "tf_scale": 0.0})
+                                       "tf_scale": 0.0}, model=2 if comb else 0)
         topo = _LOSS_TOPOS[key] = eng.global_upload(shell)
     eng.global_set_loss_data(topo, dict(p_prot=p_prot, t_prot=t_prot, obs_prot=obs_prot, w_prot=w_prot, p_rna=p_rna,
                                         t_rna=t_rna, obs_rna=obs_rna, w_rna=w_rna, p_pho=p_pho, s_pho=s_pho, t_pho=t_pho,

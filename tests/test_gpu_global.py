@@ -94,7 +94,7 @@ def test_fused_loss_objectives_metric(engine, path):
                                loss_mode=mode, metric=metric, metric_times=mt, lambdas=lambdas, lambda_prior=lam_prior,
                                engine=engine)
             for b in range(g["params"].shape[0]):
-                ref = np.array(og.loss_noncomb(r["Y"][b], ld, mode if mode < 7 else -1))
+                ref = np.array(og.loss(s.model, r["Y"][b], ld, mode if mode < 7 else -1))
                 assert np.allclose(r["loss"][b], ref, rtol=1e-11, atol=1e-13), (mode, b)
                 F = og.objectives(ref, ld, og.unpack_params(g["params"][b], net), net["defaults"], lambdas, lam_prior)
                 assert np.allclose(r["F"][b], F, rtol=1e-11, atol=1e-13), (mode, b)
@@ -125,7 +125,7 @@ def test_loss_fn_on_reference_trajectories(engine, path):
             mine = np.array(LOSS_FN(g["Y"][b], ld["p_prot"], ld["t_prot"], ld["obs_prot"], ld["w_prot"], ld["p_rna"],
                                     ld["t_rna"], ld["obs_rna"], ld["w_rna"], ld["p_pho"], ld["s_pho"], ld["t_pho"],
                                     ld["obs_pho"], ld["w_pho"], ld["prot_map"], ld["prot_base_idx"], ld["rna_base_idx"],
-                                    ld["pho_base_idx"], loss_mode=mode, engine=engine))
+                                    ld["pho_base_idx"], loss_mode=mode, model=int(g["model"]), engine=engine))
             both_nan = np.isnan(mine) & np.isnan(ref[b])        # mode 2 is NaN by design
             assert np.all(both_nan | (np.abs(mine - ref[b]) <= 1e-11 * np.abs(ref[b]) + 1e-13)), (mode, b, mine, ref[b])
 
@@ -191,7 +191,7 @@ def test_time_grid_subsets(engine):
 def test_unsupported_model_and_bad_inputs(engine):
     from phoskintime_b200 import PhoskinError
     s = synthetic_system(seed=1, N=6, K=3, max_sites=2, model=0)
-    s.model = 2
+    s.model = 3
     with pytest.raises(PhoskinError):
         engine.global_upload(s)
     s.model = 0
@@ -216,6 +216,28 @@ def test_full_size_network_sanity(engine):
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert np.isfinite(a["Y"]).all() and (a["Y"] > -1e-9).all()
     assert _ratio(a["Y"], b["Y"], 1e-6, 1e-9) <= 1.0
+
+
+def test_combinatorial_full_size_and_uncoupled(engine):
+    """MODEL 2 at the BASELINE configs[4] network size (N = 120, ~1000 pattern states): every system integrates,
+    a tighter tolerance agrees to 1e-6, the shared-memory LU fallback agrees; and a network without TF edges (no
+    Schur block) matches the oracle's tight solution block by block."""
+    s = synthetic_system(seed=5, N=120, K=40, max_sites=4, model=2)
+    assert s.idx.state_dim == int((1 + (1 << s.idx.n_sites)).sum())
+    rng = np.random.default_rng(0)
+    base = s.pack_params()
+    P = base[None, :] * np.exp(0.05 * rng.standard_normal((8, base.size)))
+    t = np.array([0.0, 0.5, 1.0, 4.0, 15.0, 16.0, 60.0, 240.0, 960.0])
+    a = simulate_batch(s, P, t, ("Y",), engine=engine)
+    b = simulate_batch(s, P, t, ("Y",), rtol=1e-8, atol=1e-11, engine=engine)
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert np.isfinite(a["Y"]).all() and (a["Y"] > -1e-9).all()
+    assert _ratio(a["Y"], b["Y"], 1e-6, 1e-9) <= 1.0
+    u = synthetic_system(seed=8, N=6, K=3, max_sites=4, tf_density=0.0, model=2)
+    tu = np.array([0.0, 0.5, 1.0, 4.0, 16.0, 60.0, 960.0])
+    r = simulate_batch(u, u.pack_params()[None, :], tu, ("Y",), engine=engine)
+    assert r["status"][0] == 0 and engine.global_dims(u._topo_id[id(engine)])["n_reg"] == 0
+    assert _ratio(r["Y"][0], og.simulate_exact_buckets(2, u.as_dict(), tu), 1e-6, 1e-9) <= 1.0
 
 
 def test_solve_custom_signature(engine):

@@ -50,7 +50,36 @@ def test_system_layout_and_argument_packing():
     s.update(**p)
     assert np.array_equal(s.pack_params(), v * 2.0)           # write-through (network.py:293-302)
     with pytest.raises(KeyError):
-        synthetic_system(seed=1, N=6, K=3, model="combinatorial")
+        synthetic_system(seed=1, N=6, K=3, model="michaelis")
+
+
+def test_combinatorial_layout_and_27_tuple():
+    """MODEL 2 mirror: block [mRNA, 2^ns patterns] (network.py:131-149), y0 (network.py:431-436), the 27-tuple of
+    network.py:471-505 and the hypercube edge lists (models.py:435-485, restated independently in the oracle)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import global_models as og
+    s = synthetic_system(seed=4, N=9, K=4, max_sites=3, model="combinatorial")
+    idx = s.idx
+    assert s.model == 2 and np.array_equal(idx.n_states, 1 << idx.n_sites)
+    assert idx.state_dim == int((1 + idx.n_states).sum())
+    assert np.array_equal(np.diff(idx.offset_y), 1 + idx.n_states[:-1])
+    y0 = s.y0()
+    for i in range(idx.N):
+        st = idx.offset_y[i]
+        assert y0[st] == 1.0 and y0[st + 1] == 1.0 and np.all(y0[st + 2:st + 1 + idx.n_states[i]] == 0.01)
+    with pytest.raises(ValueError):
+        s.odeint_args()
+    args = s.odeint_args(s.build_S_cache())
+    assert len(args) == 27 and args[9].shape == (idx.total_sites, s.kin_grid.size)
+    assert np.allclose(args[9], og.s_cache(s.as_dict(), s.c_k), rtol=1e-14, atol=0.0)
+    for mine, ref in zip(args[18:23], og.comb_tables(idx.n_sites)):
+        assert mine.dtype == np.int32 and np.array_equal(mine, ref)
+    # every pattern has one forward edge per unset bit
+    assert args[22].sum() == sum(ns * (1 << ns) // 2 for ns in idx.n_sites)
+    ld = synthetic_loss_data(s, T15, seed=1)
+    assert np.array_equal(ld["prot_map"][:, 1], idx.n_states)
+    with pytest.raises(ValueError):
+        synthetic_system(seed=4, N=9, K=4, max_sites=6, model=2)
 
 
 def test_raw_parameter_transform_roundtrip():

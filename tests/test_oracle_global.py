@@ -30,7 +30,7 @@ def load_case(path):
 
 
 def test_goldens_present():
-    assert len(FILES) == 5
+    assert len(FILES) == 7
 
 
 @pytest.mark.parametrize("path", FILES, ids=IDS)
@@ -63,7 +63,7 @@ def test_losses_match_reference(path):
     for mode in (0, 1, 2, 3, 4, 5, 6, -1):
         ref = g[f"loss_mode{mode}"]
         for b in range(ref.shape[0]):
-            mine = np.array(og.loss_noncomb(g["Y"][b], ld, mode))
+            mine = np.array(og.loss(int(g["model"]), g["Y"][b], ld, mode))
             both_nan = np.isnan(mine) & np.isnan(ref[b])       # mode 2 is NaN by design
             assert np.all(both_nan | (np.abs(mine - ref[b]) <= 1e-10 * np.abs(ref[b]) + 1e-12)), (mode, b)
 
