@@ -135,6 +135,59 @@ int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, doubl
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched bounded non-linear least squares over the local models.
+ *
+ *   pk_local_nlls_batch  <- a loop of scipy.optimize.curve_fit(model_func, time_points, target_fit, p0=p0_try,
+ *                           bounds=free_bounds, sigma=sigma, x_scale='jac') calls: the multistart loop
+ *                           paramest/normest.py:274-316 (one call per start), the lambda scan :79-89 and the
+ *                           sequential / bootstrap fits :494-509 — with the residual model of normest.py:403-423
+ *                              r(theta) = ([flat(solve_ode(theta or exp theta)) | lam/P*theta^2] - [target | 0]) / sigma
+ *                           Every problem (one start of one protein) is a row of theta[B,P]; group[b] selects its
+ *                           target / sigma row.  On return theta holds the minimiser, out_cost = 0.5*sum(r^2) there and
+ *                           out_score = score_fit(theta, target, flat) (config/config.py:176-226), the quantity
+ *                           normest.py:293-306 ranks the starts by.
+ * The optimiser is a projected Levenberg-Marquardt with MINPACK column scaling (SciPy's TRF is policy, outside the
+ * parity contract); Jacobians are forward differences, B*(P+1) solves in ONE launch per iteration.
+ * out_status: 1 gtol, 2 ftol, 3 xtol, 4 max_iter reached, -1 numerical failure (integrator failed / non-finite).
+ * -----------------------------------------------------------------------------------------------*/
+typedef struct pk_nlls_job {
+    int32_t model;          /* pk_model                                                          */
+    int32_t n_sites;
+    int64_t B;              /* problems                                                          */
+    int32_t T;
+    int32_t memspace;       /* of theta, y0, target, sigma, group, out_*; t, lb, ub are HOST     */
+    double* theta;          /* [B,P] in: start points (clipped into the box), out: minimisers    */
+    const double* y0;       /* [n] (y0_stride 0) or [B, y0_stride]                               */
+    int64_t y0_stride;
+    const double* t;        /* [T] HOST                                                          */
+    const double* lb;       /* [P] HOST, finite                                                  */
+    const double* ub;       /* [P] HOST, finite                                                  */
+    const double* target;   /* [G,L]                                                             */
+    const double* sigma;    /* NULL or [G,sigma_len], sigma_len in {L, L+P}                      */
+    const int32_t* group;   /* NULL or [B]                                                       */
+    int32_t n_groups;
+    int32_t sigma_len;
+    double lam;             /* regularisation lambda (normest.py:56, 421)                        */
+    int32_t log_params;     /* 1: model uses exp(theta) (randmod, normest.py:54)                 */
+    int32_t max_iter;       /* Jacobian evaluations per problem                                  */
+    double ftol, xtol, gtol;/* curve_fit defaults 1e-8                                           */
+    double fd_rel;          /* forward-difference step relative to max(1,|theta_j|), default 1e-4 */
+    double mu0;             /* initial damping (<=0 -> 1e-3)                                     */
+    double rtol, atol;      /* integrator tolerances, defaults 2e-7 / 2e-10                      */
+    int32_t max_steps;
+    int32_t method;         /* pk_method                                                         */
+    double score_w[5];
+    double* out_cost;       /* [B]                                                               */
+    double* out_score;      /* [B]                                                               */
+    int32_t* out_status;    /* [B]                                                               */
+    int32_t* out_iters;     /* [B]                                                               */
+    int32_t* out_nfev;      /* [B] ODE solves spent on the problem                               */
+} pk_nlls_job;
+void pk_nlls_job_init(pk_nlls_job* job);
+int pk_sizeof_nlls_job(void);
+int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* job);
+
+/* ------------------------------------------------------------------------------------------------
  * Global coupled kinase-TF-protein network (reference: global_model/)
  *
  *   pk_global_upload        <- the static array part of System.odeint_args()  global_model/network.py:508-526
@@ -148,15 +201,17 @@ int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, doubl
  *                              GlobalODE_MOO._evaluate (optproblem.py:87-160) and the Morris scalar of
  *                              global_model/sensitivity.py:106-140 over simulate_and_measure's fold changes
  *                              (simulate.py:105-182).
- * Kinetic models: 0 distributive, 1 sequential, 4 saturating (global_model/models.py); the combinatorial
- * model 2 is not supported (pk_global_upload returns an error).
+ * Kinetic models (global_model/models.py): 0 distributive, 1 sequential, 4 saturating with the block
+ * [mRNA, P0, site_1..site_ns]; 2 combinatorial with the block [mRNA, pattern_0 .. pattern_{2^ns-1}]
+ * (network.py:131-149; at most 4 sites per protein; driver_map is ignored as in jacspeedup.py:318-325; the
+ * reference's per-bucket rate table S_cache, jacspeedup.py:114-145, is recomputed on the device).
  * -----------------------------------------------------------------------------------------------*/
 typedef struct pk_global_topology {
-    int32_t model;               /* 0, 1 or 4                                                      */
+    int32_t model;               /* 0, 1, 2 or 4                                                    */
     int32_t N;                   /* proteins                                                        */
     int32_t K;                   /* kinases                                                         */
     int32_t n_bins;              /* kinase-grid points                                              */
-    const int32_t* n_sites;      /* [N]; block of protein i = [mRNA, P0, site_1..site_ns]           */
+    const int32_t* n_sites;      /* [N]; block of protein i = [mRNA, P0, site_1..site_ns] (model 2: patterns) */
     const int32_t* W_indptr;     /* CSR [total_sites, K]: site <- kinase weights                    */
     const int32_t* W_indices;
     const double* W_data;

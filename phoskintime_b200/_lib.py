@@ -39,6 +39,26 @@ class PkLocalJob(C.Structure):
     ]
 
 
+class PkNllsJob(C.Structure):
+    """Mirror of `struct pk_nlls_job` — one batched call replacing a loop of curve_fit
+    (reference paramest/normest.py:79-89, 278-290, 494-509)."""
+    _fields_ = [
+        ("model", C.c_int32), ("n_sites", C.c_int32), ("B", C.c_int64), ("T", C.c_int32), ("memspace", C.c_int32),
+        ("theta", C.c_void_p), ("y0", C.c_void_p), ("y0_stride", C.c_int64), ("t", C.c_void_p),
+        ("lb", C.c_void_p), ("ub", C.c_void_p), ("target", C.c_void_p), ("sigma", C.c_void_p), ("group", C.c_void_p),
+        ("n_groups", C.c_int32), ("sigma_len", C.c_int32), ("lam", C.c_double),
+        ("log_params", C.c_int32), ("max_iter", C.c_int32),
+        ("ftol", C.c_double), ("xtol", C.c_double), ("gtol", C.c_double), ("fd_rel", C.c_double), ("mu0", C.c_double),
+        ("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("method", C.c_int32),
+        ("score_w", C.c_double * 5),
+        ("out_cost", C.c_void_p), ("out_score", C.c_void_p), ("out_status", C.c_void_p), ("out_iters", C.c_void_p),
+        ("out_nfev", C.c_void_p),
+    ]
+
+
+NLLS_STATUS_NAMES = {1: "gtol", 2: "ftol", 3: "xtol", 4: "max_iter", -1: "failed"}
+
+
 class PkGlobalTopology(C.Structure):
     """Mirror of `struct pk_global_topology` — the static arrays of System.odeint_args()
     (reference global_model/network.py:508-526)."""
@@ -109,6 +129,9 @@ SYMBOLS = {
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pk_nlls_job_init": (None, [C.POINTER(PkNllsJob)]),
+    "pk_sizeof_nlls_job": (C.c_int, []),
+    "pk_local_nlls_batch": (C.c_int, [C.c_void_p, C.POINTER(PkNllsJob)]),
     "pk_global_upload": (C.c_int, [C.c_void_p, C.POINTER(PkGlobalTopology), C.POINTER(C.c_int32)]),
     "pk_global_set_loss_data": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(PkGlobalLossData)]),
     "pk_global_set_prior": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
@@ -148,6 +171,8 @@ def load():
         raise PhoskinError("libphoskin_b200.so ABI version mismatch")
     if lib.pk_sizeof_local_job() != C.sizeof(PkLocalJob):
         raise PhoskinError("pk_local_job layout mismatch between header and ctypes mirror")
+    if lib.pk_sizeof_nlls_job() != C.sizeof(PkNllsJob):
+        raise PhoskinError("pk_nlls_job layout mismatch between header and ctypes mirror")
     if lib.pk_sizeof_global_job() != C.sizeof(PkGlobalJob):
         raise PhoskinError("pk_global_job layout mismatch between header and ctypes mirror")
     _lib = lib

@@ -192,6 +192,87 @@ class Engine:
         del keep
         return res
 
+    # ------------------------------------------------------------------------------ nlls
+    def nlls_local_batch(self, model, theta0, init_cond, num_psites, t, target, lb, ub, *, sigma=None, group=None,
+                         lam=0.0, log_params=False, max_iter=100, ftol=1e-8, xtol=1e-8, gtol=1e-8, fd_rel=None,
+                         rtol=None, atol=None, max_steps=0, method=None, score_weights=(1.0, 1.0, 1.0, 1.0, 1.0)):
+        """B bounded least-squares problems in one call (`pk_local_nlls_batch`): the batched form of
+        `curve_fit(model_func, time_points, target_fit, p0, bounds=free_bounds, sigma=sigma, x_scale='jac')`
+        (paramest/normest.py:278-290) with the residual model of normest.py:403-423.
+
+        theta0 [B,P] start points; target [L] or [G,L]; sigma None, [L]/[L+P] or [G,.]; group [B] rows of target;
+        lb/ub [P] finite.  Returns dict(theta[B,P], cost[B] = 0.5*sum(r^2), score[B] = score_fit at the optimum,
+        status[B] (1 gtol, 2 ftol, 3 xtol, 4 max_iter, -1 failed), iters[B], nfev[B])."""
+        dev = _is_torch(theta0)
+        xp = _TorchOps(theta0.device) if dev else _NumpyOps()
+        theta = xp.f64(theta0)
+        theta = (theta.reshape(1, -1) if theta.ndim == 1 else theta)
+        theta = theta.clone() if dev else theta.copy()
+        B = int(theta.shape[0])
+        t_arr = np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(-1))
+        T = int(t_arr.shape[0])
+        n, P, L = local_dims(model, num_psites, T)
+        if theta.shape[1] != P:
+            raise ValueError(f"{model} with {num_psites} sites takes {P} parameters, got {theta.shape[1]}")
+        lb = np.ascontiguousarray(np.broadcast_to(np.asarray(lb, dtype=np.float64), (P,)))
+        ub = np.ascontiguousarray(np.broadcast_to(np.asarray(ub, dtype=np.float64), (P,)))
+        y0 = xp.f64(init_cond)
+        if y0.ndim == 1:
+            if y0.shape[0] != n:
+                raise ValueError(f"init_cond must have {n} entries")
+            y0_stride = 0
+        else:
+            if tuple(y0.shape) != (B, n):
+                raise ValueError(f"init_cond must be [{n}] or [{B},{n}]")
+            y0_stride = n
+        tg = xp.f64(target)
+        tg = tg.reshape(1, -1) if tg.ndim == 1 else tg
+        if tg.shape[1] != L:
+            raise ValueError(f"target must have {L} columns")
+        G = int(tg.shape[0])
+        job = _lib.PkNllsJob()
+        self.lib.pk_nlls_job_init(C.byref(job))
+        job.model, job.n_sites, job.B, job.T = MODEL_IDS[model], int(num_psites), B, T
+        job.memspace = PK_DEVICE if dev else PK_HOST
+        job.theta, job.y0, job.y0_stride, job.t = xp.ptr(theta), xp.ptr(y0), y0_stride, t_arr.ctypes.data
+        job.lb, job.ub, job.target, job.n_groups = lb.ctypes.data, ub.ctypes.data, xp.ptr(tg), G
+        keep = [theta, y0, t_arr, lb, ub, tg]
+        if sigma is not None:
+            sg = xp.f64(sigma)
+            sg = sg.reshape(1, -1) if sg.ndim == 1 else sg
+            if sg.shape[0] != G or sg.shape[1] not in (L, L + P):
+                raise ValueError(f"sigma must be [{G},{L}] or [{G},{L + P}]")
+            job.sigma, job.sigma_len = xp.ptr(sg), int(sg.shape[1])
+            keep.append(sg)
+        if group is not None:
+            gr = xp.i32(group).reshape(-1)
+            if gr.shape[0] != B:
+                raise ValueError("group must have B entries")
+            job.group = xp.ptr(gr)
+            keep.append(gr)
+        elif G != 1:
+            raise ValueError("several target rows need `group`")
+        job.lam, job.log_params, job.max_iter = float(lam), int(bool(log_params)), int(max_iter)
+        job.ftol, job.xtol, job.gtol = float(ftol), float(xtol), float(gtol)
+        if fd_rel is not None:
+            job.fd_rel = float(fd_rel)
+        if rtol is not None:
+            job.rtol = float(rtol)
+        if atol is not None:
+            job.atol = float(atol)
+        job.max_steps, job.method = int(max_steps), METHOD_IDS[method]
+        for i, w in enumerate(score_weights):
+            job.score_w[i] = float(w)
+        res = {"theta": theta, "cost": xp.empty((B,), "f64"), "score": xp.empty((B,), "f64"),
+               "status": xp.empty((B,), "i32"), "iters": xp.empty((B,), "i32"), "nfev": xp.empty((B,), "i32")}
+        job.out_cost, job.out_score = xp.ptr(res["cost"]), xp.ptr(res["score"])
+        job.out_status, job.out_iters, job.out_nfev = xp.ptr(res["status"]), xp.ptr(res["iters"]), xp.ptr(res["nfev"])
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_local_nlls_batch(self._h, C.byref(job)))
+        del keep
+        return res
+
     # ---------------------------------------------------------------------------- morris
     def morris_ee(self, X, Y, num_levels, scaled=False, want_ee=False):
         """mu, mu*, sigma (and optionally the EE matrix) from trajectories X[N(D+1),D], Y[N(D+1)]

@@ -4,8 +4,12 @@
 The reference runs its 48 starts sequentially (normest.py:274-316); each start is a SciPy
 `curve_fit` whose every residual evaluation is one `solve_ode` (normest.py:403-423).  The part
 of that loop that is data-parallel — "given many parameter vectors for many proteins, return the
-regularised weighted residual cost and the score_fit of each" — is one kernel launch here.  The
-optimiser policy (TRF) stays with the caller (SURVEY.md §8(f) row 1 is the follow-up).
+regularised weighted residual cost and the score_fit of each" — is one kernel launch here
+(`evaluate_starts`).  `fit_multistart` runs the whole multistart fit on the device: every start of every
+protein is one row of `pk_local_nlls_batch` (bounded Levenberg-Marquardt, forward-difference Jacobians
+as B*(P+1) solves per launch), and the best start per protein is picked by `score_fit` exactly as
+normest.py:293-306 does.  SciPy's TRF itself is optimiser policy outside the parity contract
+(SURVEY.md §8(c)); tests compare the minima found with SciPy's on the same residual.
 """
 import numpy as np
 
@@ -47,6 +51,36 @@ def evaluate_starts(model, starts, init_cond, num_psites, time_points, targets, 
     return eng.solve_local_batch(model, starts, init_cond, num_psites, time_points, want=want,
                                  target=targets, sigma=sigma, group=group, lam=lam,
                                  log_params=(model == "randmod"), **kw)
+
+
+def fit_multistart(model, base_p0, lb, ub, init_cond, num_psites, time_points, targets, *, genes=None, sigma=None,
+                   lam=0.0, n_starts=48, jitter_frac=0.10, seed=42, engine=None, **nlls_kw):
+    """`_curve_fit_multistart` (normest.py:167-326) for G proteins at once.
+
+    targets[G,L] one row per protein; base_p0 [P] or [G,P]; genes: names used for the per-gene seed
+    (normest.py:222-223).  Returns dict(popt[G,P], best_score[G], best_start[G], n_ok[G], n_fail[G]) plus the
+    per-start arrays (`theta`, `score`, `cost`, `status`, `group`)."""
+    eng = engine or get_engine()
+    targets = np.atleast_2d(np.asarray(targets, dtype=float))
+    G = targets.shape[0]
+    lb = np.asarray(lb, dtype=float)
+    ub = np.asarray(ub, dtype=float)
+    base = np.broadcast_to(np.asarray(base_p0, dtype=float), (G, lb.size))
+    genes = [""] * G if genes is None else list(genes)
+    starts = np.concatenate([multistart_points(base[p], lb, ub, n_starts, jitter_frac, seed, genes[p]) for p in range(G)])
+    per = starts.shape[0] // G
+    group = np.repeat(np.arange(G, dtype=np.int32), per)
+    res = eng.nlls_local_batch(model, starts, init_cond, num_psites, time_points, targets, lb, ub, sigma=sigma,
+                               group=group, lam=lam, log_params=(model == "randmod"), **nlls_kw)
+    ok = (res["status"] > 0) & np.isfinite(res["score"])            # a failed start is skipped (normest.py:312-316)
+    score = np.where(ok, res["score"], np.inf)
+    best = best_per_group(score, group, G)
+    n_ok = np.bincount(group[ok], minlength=G)
+    if (n_ok == 0).any():
+        raise RuntimeError(f"multistart fit: all starts failed for proteins {np.flatnonzero(n_ok == 0).tolist()}")
+    return {"popt": res["theta"][best], "best_score": score[best], "best_start": best - np.arange(G) * per,
+            "n_ok": n_ok, "n_fail": per - n_ok, "theta": res["theta"], "score": res["score"], "cost": res["cost"],
+            "status": res["status"], "iters": res["iters"], "nfev": res["nfev"], "group": group}
 
 
 def best_per_group(values, group, n_groups):
