@@ -3,3 +3,4 @@ from .network import GlobalSystem, synthetic_system, synthetic_loss_data  # noqa
 from .simulate import LOSS_FN, metric_time_indices, simulate_batch, simulate_odeint, solve_custom  # noqa: F401
 from .optproblem import GlobalODE_MOO, init_raw_params, unpack_params  # noqa: F401
 from .sensitivity import compute_bounds, run_sensitivity_analysis  # noqa: F401
+from .analysis import final_rate_of_change, simulate_until_steady, steady_check_batch, steady_time_grid  # noqa: F401

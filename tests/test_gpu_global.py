@@ -240,6 +240,24 @@ def test_combinatorial_full_size_and_uncoupled(engine):
     assert _ratio(r["Y"][0], og.simulate_exact_buckets(2, u.as_dict(), tu), 1e-6, 1e-9) <= 1.0
 
 
+def test_simulate_until_steady_long_log_grid(engine):
+    """analysis.py:29-67: 1000 log-spaced outputs over 24 h (beyond the last kinase-grid point): every output is hit
+    exactly; a sample of rows is compared with the oracle's tight solution, the convergence rate with its definition."""
+    from phoskintime_b200.global_model import final_rate_of_change, simulate_until_steady, steady_check_batch
+    g, s, _ = load_case(FILES[0])
+    s.update(**s.unpack_params(g["params"][1]))
+    t, Y = simulate_until_steady(s, t_max=1440.0, n_points=1000)
+    assert t.shape == (1000,) and t[0] == 0.0 and np.isclose(t[1], 1e-3) and np.isclose(t[-1], 1440.0)
+    assert Y.shape == (1000, s.idx.state_dim) and np.isfinite(Y).all()
+    rows = np.array([0, 1, 150, 400, 555, 700, 850, 930, 999])
+    ref = og.simulate_exact_buckets(int(g["model"]), s.as_dict(), t[rows], params=s.unpack_params(g["params"][1]))
+    assert _ratio(Y[rows], ref, 1e-6, 1e-9) <= 1.0
+    rate = final_rate_of_change(t, Y)
+    assert np.isclose(rate, np.linalg.norm(Y[-1] - Y[-2]) / (t[-1] - t[-2])) and rate < 1e-3
+    tb, Yb, rb, st = steady_check_batch(s, g["params"], engine=engine)
+    assert (st == 0).all() and np.array_equal(Yb[1], Y) and np.isclose(rb[1], rate)
+
+
 def test_solve_custom_signature(engine):
     g, s, _ = load_case(FILES[2])
     s.update(**s.unpack_params(g["params"][2]))
