@@ -7,6 +7,8 @@
 // Here every start of every protein is one row of a batch and an iteration is
 //     perturb (this file)  ->  ONE launch of the ODE kernel over B*(P+1) systems (flat + ssr)
 //     lm_step  (this file)  ->  ONE launch of the ODE kernel over the B trial points (ssr)  ->  lm_accept (this file)
+// Only problems that are still running take part: lm_accept appends the survivors to a compact index list, the next
+// iteration's batches hold nA*(P+1) and nA systems (nA = survivors), so converged starts cost nothing further.
 // The optimiser POLICY is a projected Levenberg-Marquardt (Nielsen damping, Jacobian column scaling as MINPACK's
 // x_scale='jac'), not a transcription of SciPy's TRF: SURVEY.md section 8(c) places the optimiser outside the parity
 // contract; what is checked is that the minima found agree with SciPy's on the same residual (tests/test_gpu_nlls.py).
@@ -45,6 +47,16 @@ struct NllsArgs {
     const int* trial_status; // [B]
     NllsState* st;           // [B]
     int* n_running;          // device counter of problems still running (written by lm_accept)
+    // compaction: row a of the perturbed / trial batches belongs to problem idx[a], a < nA
+    long long nA;
+    const int* idx;          // [nA] problems still running, this iteration
+    int* idx_next;           // [<=nA] survivors, written by lm_accept
+    int* trial_group;        // [nA] or nullptr
+    const double* y0;        // per-problem initial conditions [B, y0_stride] (y0_stride > 0) ...
+    long long y0_stride;
+    int n;
+    double* y0_pert;         // ... gathered to [nA*(P+1), n]
+    double* y0_trial;        // ... and to [nA, n]
 };
 
 // theta -> the P+1 parameter rows of the forward-difference Jacobian.  Step: fd_rel * max(1, |theta_j|), flipped when it
@@ -52,13 +64,16 @@ struct NllsArgs {
 __global__ void nlls_perturb_kernel(const NllsArgs a) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int P = a.P;
-    if (idx >= a.B * (P + 1)) return;
-    const long long b = idx / (P + 1);
-    const int k = (int)(idx - b * (P + 1));
+    if (idx >= a.nA * (P + 1)) return;
+    const long long ai = idx / (P + 1);
+    const long long b = a.idx[ai];
+    const int k = (int)(idx - ai * (P + 1));
     const double* th = a.theta + b * P;
     double* row = a.pert + idx * P;
     for (int j = 0; j < P; ++j) row[j] = th[j];
     if (a.pert_group) a.pert_group[idx] = a.group[b];
+    if (a.y0_pert)
+        for (int i = 0; i < a.n; ++i) a.y0_pert[idx * a.n + i] = a.y0[b * a.y0_stride + i];
     if (k > 0) {
         const int j = k - 1;
         double h = a.fd_rel * fmax(1.0, fabs(th[j]));
@@ -78,16 +93,16 @@ __device__ __forceinline__ double nlls_warp_sum(double v) {
 __global__ void nlls_step_kernel(const NllsArgs a, int warps_per_cta, int Lp) {
     extern __shared__ double nsm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long b = blockIdx.x * (long long)warps_per_cta + wid;
-    if (b >= a.B) return;
+    const long long ai = blockIdx.x * (long long)warps_per_cta + wid;
+    if (ai >= a.nA) return;
+    const long long b = a.idx[ai];
     NllsState& S = a.st[b];
     const int P = a.P, L = a.L;
     double* th = a.theta + b * P;
-    double* tr = a.trial + b * P;
-    if (S.status != 0) {                      // finished earlier: the trial row stays a valid parameter set
-        for (int j = lane; j < P; j += 32) tr[j] = th[j];
-        return;
-    }
+    double* tr = a.trial + ai * P;
+    if (lane == 0 && a.trial_group) a.trial_group[ai] = a.group[b];
+    if (a.y0_trial)
+        for (int i = lane; i < a.n; i += 32) a.y0_trial[ai * a.n + i] = a.y0[b * a.y0_stride + i];
     const size_t per_warp = (size_t)P * Lp + L + (size_t)P * P + 4 * (size_t)P;
     double* J = nsm + wid * per_warp;
     double* r = J + (size_t)P * Lp;
@@ -96,7 +111,7 @@ __global__ void nlls_step_kernel(const NllsArgs a, int warps_per_cta, int Lp) {
     double* dsc = g + P;
     double* dl = dsc + P;
     double* act = dl + P;
-    const long long row0 = b * (P + 1);
+    const long long row0 = ai * (P + 1);
     const int grp = a.group ? a.group[b] : 0;
     const double* tg = a.target + (size_t)grp * L;
     const double* sg = a.sigma ? a.sigma + (size_t)grp * a.sigma_len : nullptr;
@@ -252,18 +267,19 @@ __global__ void nlls_step_kernel(const NllsArgs a, int warps_per_cta, int Lp) {
 
 // Gain ratio, acceptance, damping update (Nielsen 1999) and the ftol / xtol tests; one thread per problem.
 __global__ void nlls_accept_kernel(const NllsArgs a, int last_iter) {
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    const long long ai = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (ai >= a.nA) return;
+    const long long b = a.idx[ai];
     NllsState& S = a.st[b];
-    if (S.status != 0) return;
+    if (S.status != 0) return;                // finished inside lm_step (gtol / numerical failure)
     const int P = a.P;
-    const double ct = 0.5 * a.trial_ssr[b];
-    const bool ok = a.trial_status[b] == 0 && ct == ct && S.pred > 0.0;
+    const double ct = 0.5 * a.trial_ssr[ai];
+    const bool ok = a.trial_status[ai] == 0 && ct == ct && S.pred > 0.0;
     ++S.nfev;
     const double rho = ok ? (S.cost - ct) / S.pred : -1.0;
     if (ok && rho > 1e-4 && ct < S.cost) {
         const double dc = S.cost - ct;
-        for (int j = 0; j < P; ++j) a.theta[b * P + j] = a.trial[b * P + j];
+        for (int j = 0; j < P; ++j) a.theta[b * P + j] = a.trial[ai * P + j];
         const double f = 2.0 * rho - 1.0;
         S.mu *= fmax(1.0 / 3.0, 1.0 - f * f * f);
         S.nu = 2.0;
@@ -277,12 +293,13 @@ __global__ void nlls_accept_kernel(const NllsArgs a, int last_iter) {
         if (!(S.mu < 1e30)) S.status = 3;
     }
     if (S.status == 0 && last_iter) S.status = 4;
-    if (S.status == 0) atomicAdd(a.n_running, 1);
+    if (S.status == 0) a.idx_next[atomicAdd(a.n_running, 1)] = (int)b;
 }
 
-__global__ void nlls_init_kernel(const NllsArgs a, double mu0) {
+__global__ void nlls_init_kernel(const NllsArgs a, double mu0, int* idx0) {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= a.B) return;
+    idx0[b] = (int)b;
     NllsState& S = a.st[b];
     S.mu = mu0; S.nu = 2.0; S.cost = 0.0; S.pred = 0.0; S.snorm = 0.0; S.xnorm = 0.0;
     S.status = 0; S.iters = 0; S.nfev = 0; S.pad = 0;

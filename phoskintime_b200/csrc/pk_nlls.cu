@@ -2,7 +2,8 @@
 // Replaces a loop of scipy.optimize.curve_fit calls (paramest/normest.py:79-89, 278-290, 494-509), each of which
 // evaluates its residual model (normest.py:403-423) and a 2-point Jacobian one solve_ode at a time.
 // The iteration loop lives here (C++), every solve is pk_local_solve_batch on device buffers, the linear algebra
-// of a step is nlls_step_kernel (csrc/nlls.cuh).  Per iteration 2 ODE launches + 3 small kernels, 4 bytes to the host.
+// of a step is nlls_step_kernel (csrc/nlls.cuh).  Per iteration 2 ODE launches + 3 small kernels, 4 bytes to the host
+// (the number of problems still running, which sizes the next iteration's batches).
 #include <algorithm>
 #include <cmath>
 
@@ -88,13 +89,15 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     a.ftol = j->ftol; a.xtol = j->xtol; a.gtol = j->gtol;
     double *d_lb, *d_ub, *d_t, *d_y0, *d_target, *d_sigma = nullptr, *d_theta, *d_pert, *d_h, *d_flat, *d_ssr, *d_dscale,
            *d_trial, *d_tssr, *d_score = nullptr;
-    int *d_group = nullptr, *d_pgroup = nullptr, *d_sstat, *d_tstat, *d_run;
+    int *d_group = nullptr, *d_pgroup = nullptr, *d_tgroup = nullptr, *d_sstat, *d_tstat, *d_run, *d_idx[2];
     pk::NllsState* d_state;
     CK(ws.get(&d_lb, P)); CK(ws.get(&d_ub, P)); CK(ws.get(&d_pert, R * P)); CK(ws.get(&d_h, B * P));
     CK(ws.get(&d_flat, R * L)); CK(ws.get(&d_ssr, R)); CK(ws.get(&d_dscale, B * P)); CK(ws.get(&d_trial, B * P));
     CK(ws.get(&d_tssr, B)); CK(ws.get(&d_sstat, R)); CK(ws.get(&d_tstat, B)); CK(ws.get(&d_run, 1));
     CK(ws.get(&d_state, B));
-    if (j->group) CK(ws.get(&d_pgroup, R));
+    if (j->group) { CK(ws.get(&d_pgroup, R)); CK(ws.get(&d_tgroup, B)); }
+    CK(ws.get(&d_idx[0], B)); CK(ws.get(&d_idx[1], B));
+    if (B > 0x7fffffffull / (size_t)(P + 1)) return fail("pk_local_nlls_batch: B*(P+1) exceeds 2^31");
     CK(cudaMemcpyAsync(d_lb, j->lb, P * sizeof(double), cudaMemcpyHostToDevice, st));      // lb/ub/t: always host
     CK(cudaMemcpyAsync(d_ub, j->ub, P * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(ws.get(&d_t, j->T));
@@ -117,19 +120,17 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
         d_theta = j->theta; d_y0 = (double*)j->y0; d_target = (double*)j->target; d_sigma = (double*)j->sigma;
         d_group = (int*)j->group; d_score = j->out_score;
     }
-    // per-system y0 rows must follow their problem into the perturbed batch
-    double* d_y0p = nullptr;
+    // per-system y0 rows follow their problem into the (compacted) perturbed and trial batches
+    double *d_y0p = nullptr, *d_y0t = nullptr;
     if (j->y0_stride) {
         CK(ws.get(&d_y0p, R * (size_t)n));
-        for (size_t b = 0; b < B; ++b)
-            for (int k = 0; k <= P; ++k)
-                CK(cudaMemcpyAsync(d_y0p + (b * (P + 1) + k) * n, d_y0 + b * (size_t)j->y0_stride, n * sizeof(double),
-                                   cudaMemcpyDeviceToDevice, st));
+        CK(ws.get(&d_y0t, B * (size_t)n));
     }
     a.lb = d_lb; a.ub = d_ub; a.target = d_target; a.sigma = d_sigma; a.group = d_group;
     a.theta = d_theta; a.pert = d_pert; a.pert_group = d_pgroup; a.hstep = d_h; a.flat = d_flat; a.ssr = d_ssr;
     a.solve_status = d_sstat; a.dscale = d_dscale; a.trial = d_trial; a.trial_ssr = d_tssr; a.trial_status = d_tstat;
     a.st = d_state; a.n_running = d_run;
+    a.trial_group = d_tgroup; a.y0 = d_y0; a.y0_stride = j->y0_stride; a.n = n; a.y0_pert = d_y0p; a.y0_trial = d_y0t;
 
     pk_local_job base;
     pk_local_job_init(&base);
@@ -144,31 +145,37 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, st));
-    pk::nlls_init_kernel<<<gB, TB, 0, st>>>(a, j->mu0 > 0 ? j->mu0 : 1e-3);
+    pk::nlls_init_kernel<<<gB, TB, 0, st>>>(a, j->mu0 > 0 ? j->mu0 : 1e-3, d_idx[0]);
     int launches = 1, iters_done = 0;
     int rc = 0;
+    size_t nA = B;                                    // problems still running
+    (void)gR;
     for (int it = 0; it < j->max_iter; ++it) {
-        pk::nlls_perturb_kernel<<<gR, TB, 0, st>>>(a);
+        const size_t RA = nA * (size_t)(P + 1);
+        a.nA = (long long)nA; a.idx = d_idx[it & 1]; a.idx_next = d_idx[(it + 1) & 1];
+        pk::nlls_perturb_kernel<<<(unsigned)((RA + TB - 1) / TB), TB, 0, st>>>(a);
         pk_local_job jj = base;
-        jj.B = (int64_t)R; jj.params = d_pert; jj.group = d_pgroup;
+        jj.B = (int64_t)RA; jj.params = d_pert; jj.group = d_pgroup;
         jj.y0 = j->y0_stride ? d_y0p : d_y0; jj.y0_stride = j->y0_stride ? n : 0;
         jj.out_flat = d_flat; jj.out_ssr = d_ssr; jj.out_status = d_sstat;
         if ((rc = pk_local_solve_batch(h, &jj)) != 0) break;
         launches += 1 + h->last_launches;
-        pk::nlls_step_kernel<<<(unsigned)((B + wpc - 1) / wpc), wpc * 32, wpc * per_warp, st>>>(a, wpc, Lp);
+        pk::nlls_step_kernel<<<(unsigned)((nA + wpc - 1) / wpc), wpc * 32, wpc * per_warp, st>>>(a, wpc, Lp);
         pk_local_job jt = base;
-        jt.B = j->B; jt.params = d_trial; jt.group = d_group; jt.y0 = d_y0; jt.y0_stride = j->y0_stride;
+        jt.B = (int64_t)nA; jt.params = d_trial; jt.group = d_tgroup;
+        jt.y0 = j->y0_stride ? d_y0t : d_y0; jt.y0_stride = j->y0_stride ? n : 0;
         jt.out_ssr = d_tssr; jt.out_status = d_tstat;
         if ((rc = pk_local_solve_batch(h, &jt)) != 0) break;
         launches += 1 + h->last_launches;
         CK(cudaMemsetAsync(d_run, 0, sizeof(int), st));
-        pk::nlls_accept_kernel<<<gB, TB, 0, st>>>(a, it + 1 == j->max_iter);
+        pk::nlls_accept_kernel<<<(unsigned)((nA + TB - 1) / TB), TB, 0, st>>>(a, it + 1 == j->max_iter);
         ++launches;
         int running = 0;
         CK(cudaMemcpyAsync(&running, d_run, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         iters_done = it + 1;
-        if (running == 0) break;
+        nA = (size_t)running;
+        if (nA == 0) break;
     }
     if (rc != 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     // final evaluation at the optimum: cost and score_fit (normest.py:293-306 ranks the starts by score_fit)

@@ -79,6 +79,10 @@ def test_exact_data_is_recovered_and_bounds_hold(engine):
     assert (res["status"] > 0).all()
     c0 = np.array([0.5 * np.sum((om.flat_from_sol(model, om.exact_linear(model, s, y0, ns, T), ns) - target) ** 2) for s in starts])
     assert (res["cost"] <= 1e-6 * c0).mean() >= 0.9 and res["cost"].min() < 1e-12
+    # per-problem initial conditions travel with their problem through the compacted batches
+    res_y = engine.nlls_local_batch(model, starts, np.repeat(y0[None, :], starts.shape[0], axis=0), ns, T, target, lb, ub,
+                                    max_iter=200)
+    assert np.allclose(res_y["theta"], res["theta"], rtol=1e-9, atol=1e-12) and np.array_equal(res_y["status"], res["status"])
     ub2 = ub.copy()
     ub2[2] = 0.5 * th_true[2]
     res2 = engine.nlls_local_batch(model, starts, y0, ns, T, target, lb, ub2, max_iter=200)
