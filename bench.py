@@ -30,15 +30,18 @@ def workload_config(n_gpus, b_per_gpu):
     return {"workload": f"{MODEL} ns={NS} (7 states, 14 params), {b_per_gpu} parameter sets/GPU ~U(0.05,3), "
                         f"14 output times 0..960 min, fused ssr+score_fit epilogue",
             "batch_per_gpu": b_per_gpu, "global_batch": b_per_gpu * n_gpus, "parallelism": f"shard{n_gpus}",
-            "integrator": "ROS5L order 5(4) Rosenbrock, rtol=2e-6 atol=2e-9 (library defaults: error <= 0.14 of the "
+            "integrator": "ROS6L order 6(5) Rosenbrock, 7 solves/step, rtol=2e-5 atol=2e-9 (library defaults: error <= 0.15 of the "
                           "1e-6 parity bound vs the reference's tight solution)",
             "l2": "256 MiB written between timed steps (flush), excluded from the step timing"}
 
 
 # ------------------------------------------------------------------ algorithmic work per step
-def flops_per_step(model, ns):
+def flops_per_step(model, ns, nsol=None):
     """FP64 operations of ONE integrator step attempt as the kernels perform them (FMA = 2,
-    add/mul/div/max = 1) — DESIGN.md §Kernels derives each term."""
+    add/mul/div/max = 1) — DESIGN.md §Kernels derives each term.  nsol = solves per step: 7 for ROS6L (default of the
+    thread-per-system kernels: dist/succ up to 8 sites), 6 for ROS5L / RODAS4 (dense kernel)."""
+    if nsol is None:
+        nsol = 7 if model in ("distmod", "succmod") and ns <= 8 else 6
     n = 2 + ns
     if model == "distmod":
         factor, rhs, solve = 10 * ns + 16, 4 * ns + 5, 4 * ns + 6
@@ -48,8 +51,8 @@ def flops_per_step(model, ns):
         n = 2 + (1 << ns) - 1
         nnz = 3 + ns + ((1 << ns) - 1) * (ns + 1)          # non-zeros of the transition-rate matrix
         factor, rhs, solve = (2 * n ** 3) // 3, 2 * nnz + n, 2 * n * n
-    # v0 = h f (n) ; 6 solves ; y_new/err accumulation 21 n ; error ratio 9 n ; finite check n ; controller 20
-    return factor + rhs + n + 6 * solve + 21 * n + 9 * n + n + 20
+    # v0 = h f (n) ; nsol solves ; y_new/err accumulation (4 nsol - 3) n ; error ratio 9 n ; finite check n ; controller 20
+    return factor + rhs + n + nsol * solve + (4 * nsol - 3) * n + 9 * n + n + 20
 
 
 def bytes_per_solve(model, ns):

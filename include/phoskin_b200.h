@@ -43,9 +43,10 @@ enum pk_memspace { PK_HOST = 0, PK_DEVICE = 1 };
 /* sensitivity/analysis.py:114-176 */
 enum pk_y_metric { PK_Y_NONE = -1, PK_Y_TOTAL_SIGNAL = 0, PK_Y_MEAN_ACTIVITY = 1, PK_Y_VARIANCE = 2,
                    PK_Y_DYNAMICS = 3, PK_Y_L2_NORM = 4 };
-/* integrator coefficient set: ROS5L = 6-solve order-5(4) Rosenbrock for linear systems (default),
+/* integrator coefficient set: ROS6L = 7-solve order-6(5) Rosenbrock for linear systems (default of the
+ * thread-per-system kernels: dist/succ up to 8 sites), ROS5L = 6-solve order-5(4) (default of the dense kernel),
  * RODAS4 = Hairer-Wanner order-4(3); see DESIGN.md section 2 */
-enum pk_method { PK_METHOD_DEFAULT = 0, PK_METHOD_RODAS4 = 1, PK_METHOD_ROS5L = 2 };
+enum pk_method { PK_METHOD_DEFAULT = 0, PK_METHOD_RODAS4 = 1, PK_METHOD_ROS5L = 2, PK_METHOD_ROS6L = 3 };
 enum pk_status { PK_OK = 0, PK_MAX_STEPS = 1, PK_STEP_UNDERFLOW = 2, PK_NON_FINITE = 3 };
 
 /* One batched call of solve_ode(params[b], init_cond, num_psites, t) for b in [0,B). */
@@ -59,7 +60,7 @@ typedef struct pk_local_job {
     const double* y0;       /* [n] if y0_stride==0 else [B,n] with row stride y0_stride doubles  */
     int64_t y0_stride;
     const double* t;        /* [T] strictly increasing                                           */
-    double rtol, atol;      /* <=0 -> defaults 2e-6 / 2e-9                                       */
+    double rtol, atol;      /* <=0 -> defaults of the method: ROS6L 2e-5 / 2e-9, ROS5L and RODAS4 2e-6 / 2e-9 */
     int32_t max_steps;      /* per system, <=0 -> 100000                                         */
     int32_t normalize;      /* NORMALIZE_MODEL_OUTPUT (models/distmod.py:115-122)                */
     int32_t log_params;     /* 1: params hold log-values, model uses exp(params) (normest.py:54) */

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PHOSKIN_LIB") or os.path.join(_HERE, "libphoskin_b200
 PK_HOST, PK_DEVICE = 0, 1
 MODEL_IDS = {"distmod": 0, "succmod": 1, "randmod": 2}
 Y_METRIC_IDS = {"total_signal": 0, "mean_activity": 1, "variance": 2, "dynamics": 3, "l2_norm": 4}
-METHOD_IDS = {None: 0, "default": 0, "rodas4": 1, "ros5l": 2}
+METHOD_IDS = {None: 0, "default": 0, "rodas4": 1, "ros5l": 2, "ros6l": 3}
 STATUS_NAMES = {0: "ok", 1: "max_steps", 2: "step_underflow", 3: "non_finite"}
 
 c_double_p = C.POINTER(C.c_double)

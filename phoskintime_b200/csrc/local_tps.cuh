@@ -297,13 +297,18 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[4], v[i], yn[i]); er[i] = fma(a.m.eps[4], v[i], er[i]); }
                     mdl.solve(F, v);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[5], v[i], yn[i]); er[i] = fma(a.m.eps[5], v[i], er[i]); }
+                    if (a.m.nsol > 6) {                    // ROS6L: seventh solve (uniform over the grid)
+                        mdl.solve(F, v);
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[6], v[i], yn[i]); er[i] = fma(a.m.eps[6], v[i], er[i]); }
+                    }
                     float err = 0.0f;
                     double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        yn[i] = fma(a.m.mu[5], v[i], yn[i]);
-                        er[i] = fma(a.m.eps[5], v[i], er[i]);
-                        err = fmaxf(err, err_ratio(er[i], y[i], yn[i], a.rtol, a.atol));
+                        err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], a.rtol, a.rtol_floor, a.kappa, a.atol));
                         chk += yn[i];
                     }
                     if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {

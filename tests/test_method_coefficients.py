@@ -14,12 +14,16 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 def _parse_methods():
     text = open(os.path.join(ROOT, "phoskintime_b200", "csrc", "pk_common.cuh")).read()
     out = {}
-    for name in ("METHOD_RODAS4", "METHOD_ROS5L"):
+    for name in ("METHOD_RODAS4", "METHOD_ROS5L", "METHOD_ROS6L"):
         body = text[text.index(f"constexpr Method {name}"):]
         body = body[body.index("{") + 1:body.index("};")]
+        nsol = int(re.findall(r",\s*(\d+)\s*$", body)[0])                       # last field: solves per step
+        body = body.replace("1.0f / 6.0f", repr(1.0 / 6.0))
         nums = [float(x.rstrip("f")) for x in re.findall(r"-?\d+\.\d+(?:e[+-]\d+)?f?", body)]
-        assert len(nums) == 14, (name, nums)
-        out[name] = {"gamma": nums[0], "mu": np.array(nums[1:7]), "eps": np.array(nums[7:13]), "expo": nums[13]}
+        assert len(nums) == 16, (name, nums)                                     # gamma, mu[7], eps[7], expo
+        assert np.all(np.array(nums[1:8])[nsol:] == 0.0) and np.all(np.array(nums[8:15])[nsol:] == 0.0)
+        out[name] = {"gamma": nums[0], "mu": np.array(nums[1:1 + nsol]), "eps": np.array(nums[8:8 + nsol]),
+                     "expo": nums[15], "nsol": nsol}
     return out
 
 
@@ -35,6 +39,12 @@ def test_coefficients_match_derivation_scripts():
     assert np.allclose(m["METHOD_ROS5L"]["mu"], [float(x) for x in mu], rtol=0, atol=1e-16)
     assert np.allclose(m["METHOD_ROS5L"]["eps"], [float(x) for x in eps], rtol=0, atol=1e-15)
     assert m["METHOD_ROS5L"]["gamma"] == float(derive_ros5l.GAMMA) and abs(m["METHOD_ROS5L"]["expo"] - 0.2) < 1e-7
+    import derive_ros6l
+    mu6, eps6, _ = derive_ros6l.design()
+    assert m["METHOD_ROS6L"]["nsol"] == 7 and m["METHOD_ROS6L"]["gamma"] == float(derive_ros6l.GAMMA)
+    assert np.allclose(m["METHOD_ROS6L"]["mu"], [float(x) for x in mu6], rtol=0, atol=2e-15)
+    assert np.allclose(m["METHOD_ROS6L"]["eps"], [float(x) for x in eps6], rtol=0, atol=2e-14)
+    assert abs(m["METHOD_ROS6L"]["expo"] - 1.0 / 6.0) < 1e-7
     import derive_rodas4_linear
     mu4, eps4 = derive_rodas4_linear.derive()
     assert np.allclose(m["METHOD_RODAS4"]["mu"], [float(x) for x in mu4[1:]], rtol=0, atol=1e-16)
@@ -42,14 +52,20 @@ def test_coefficients_match_derivation_scripts():
 
 
 def test_order_and_stability_of_compiled_coefficients():
-    for name, order in (("METHOD_RODAS4", 4), ("METHOD_ROS5L", 5)):
+    for name, order in (("METHOD_RODAS4", 4), ("METHOD_ROS5L", 5), ("METHOD_ROS6L", 6)):
         c = _parse_methods()[name]
         g, mu, eps = c["gamma"], c["mu"], c["eps"]
         assert mu[0] == g and eps[0] == 0.0                        # L-stable main and embedded solutions
         # order: R(z) - exp(z) = O(z^(order+1)), estimator = O(z^order)
-        e1 = abs(_R(mu, g, 0.02) - np.exp(0.02))
-        e2 = abs(_R(mu, g, 0.04) - np.exp(0.04))
-        assert abs(np.log2(e2 / e1) - (order + 1)) < 0.1
+        # (ROS6L sits next to the member of its family whose z^7 error coefficient vanishes: C7 = 1.1e-6, so at a
+        #  testable z the observed slope is between 7 and 8 — checked as "at least order 6")
+        za, zb = (0.02, 0.04) if order < 6 else (0.1, 0.2)
+        e1 = abs(_R(mu, g, za) - np.exp(za))
+        e2 = abs(_R(mu, g, zb) - np.exp(zb))
+        if order < 6:
+            assert abs(np.log2(e2 / e1) - (order + 1)) < 0.1
+        else:
+            assert order + 0.9 < np.log2(e2 / e1) < order + 2.1
         s1 = abs(0.02 * sum(e * (1 / (1 - g * 0.02)) ** (k + 1) for k, e in enumerate(eps)))
         s2 = abs(0.04 * sum(e * (1 / (1 - g * 0.04)) ** (k + 1) for k, e in enumerate(eps)))
         assert abs(np.log2(s2 / s1) - order) < 0.1
