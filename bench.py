@@ -328,10 +328,10 @@ def run_ours(args):
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp64_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, one
-                         # `ncu --set full` capture (profiles/r1_succ5_e_ros5l.txt: 116.7 MB + 124.9 MB); the
+                         # `ncu --set full` capture (profiles/r1_succ5_g_ros6l.txt: 116.4 MB + 129.3 MB); the
                          # algorithmic bytes are 140 MB (bytes_per_solve x B): the rest is write-back of the
                          # L2-resident trajectory slots
-                         "traffic": 241.6e6 if (B == B_PER_GPU and world == 1) else None,
+                         "traffic": 245.6e6 if (B == B_PER_GPU and world == 1) else None,
                          "peak_source": "pk_measure_fp64_peak (register-resident DFMA probe, this run); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_step": flops_per_step(MODEL, NS),
