@@ -267,6 +267,9 @@ typedef struct pk_global_job {
     int32_t* out_status;         /* [B] pk_status                                                   */
     int32_t* out_nsteps;
     int32_t* out_nrej;
+    double* out_fc;              /* [B, n_fc] or NULL: the fold changes simulate_and_measure tabulates
+                                  * (global_model/simulate.py:105-182, floors 1e-12, bases mb_*), n_fc =
+                                  * N*n_mt_prot + N*n_mt_rna + total_sites*n_mt_pho, protein-major then (site,) time */
 } pk_global_job;
 
 int pk_global_upload(pk_handle_t h, const pk_global_topology* topo, int32_t* topo_id);
@@ -276,6 +279,8 @@ int pk_global_release(pk_handle_t h, int32_t topo_id);
 /* state_dim, number of parameters P, size of the regulator set (dense Schur block), shared memory bytes per CTA */
 int pk_global_dims(pk_handle_t h, int32_t topo_id, int32_t* state_dim, int32_t* n_params, int32_t* n_reg,
                    int32_t* smem_bytes);
+/* proteins, kinases and total phosphorylation sites of an uploaded network */
+int pk_global_counts(pk_handle_t h, int32_t topo_id, int32_t* n_proteins, int32_t* n_kinases, int32_t* total_sites);
 void pk_global_job_init(pk_global_job* job);
 int pk_sizeof_global_job(void);
 int pk_global_solve_batch(pk_handle_t h, const pk_global_job* job);

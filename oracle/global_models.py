@@ -458,6 +458,24 @@ def scalar_metric(Y, net, obs, metric="total_signal"):
     return _reduce_metric(np.concatenate(vals), metric)
 
 
+def fc_tables(Y, net, obs):
+    """The fold-change values of simulate_and_measure (simulate.py:105-182) as three arrays
+    (fc_prot[N, len(t_prot)], fc_rna[N, len(t_rna)], fc_pho[total_sites, len(t_pho)])."""
+    fl = lambda a: np.maximum(a, 1e-12)
+    comb = int(net.get("model", 0)) == 2
+    P, R, PH = [], [], []
+    for i in range(net["N"]):
+        st, ns = int(net["offset_y"][i]), int(net["n_sites"][i])
+        tot = Y[:, st + 1:st + 1 + (1 << ns)].sum(axis=1) if comb else Y[:, st + 1:st + 2 + ns].sum(axis=1)
+        P.append(fl(tot[obs["t_prot"]]) / fl(tot[obs["prot_b"]]))
+        Rv = Y[:, st]
+        R.append(fl(Rv[obs["t_rna"]]) / fl(Rv[obs["rna_b"]]))
+        for j in range(ns):
+            ph = (Y[:, st + 1 + np.flatnonzero((np.arange(1 << ns) >> j) & 1)].sum(axis=1) if comb else Y[:, st + 2 + j])
+            PH.append(fl(ph[obs["t_pho"]]) / fl(ph[obs["pho_b"]]))
+    return np.array(P), np.array(R), np.array(PH).reshape(-1, len(obs["t_pho"]))
+
+
 def _reduce_metric(c, metric):
     if metric == "mean":
         return float(np.mean(c))

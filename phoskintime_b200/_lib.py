@@ -98,7 +98,7 @@ class PkGlobalJob(C.Structure):
         ("mb_prot", C.c_int32), ("mb_rna", C.c_int32), ("mb_pho", C.c_int32), ("reserved0", C.c_int32),
         ("lambdas", C.c_double * 3), ("lambda_prior", C.c_double),
         ("out_Y", C.c_void_p), ("out_loss", C.c_void_p), ("out_F", C.c_void_p), ("out_metric", C.c_void_p),
-        ("out_status", C.c_void_p), ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p),
+        ("out_status", C.c_void_p), ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p), ("out_fc", C.c_void_p),
     ]
 
 
@@ -138,6 +138,7 @@ SYMBOLS = {
     "pk_global_release": (C.c_int, [C.c_void_p, C.c_int32]),
     "pk_global_dims": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pk_global_counts": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pk_global_job_init": (None, [C.POINTER(PkGlobalJob)]),
     "pk_sizeof_global_job": (C.c_int, []),
     "pk_global_solve_batch": (C.c_int, [C.c_void_p, C.POINTER(PkGlobalJob)]),

@@ -96,6 +96,7 @@ struct GlobalArgs {
     const int *mt_prot, *mt_rna, *mt_pho;
     double lam[3], lam_prior;
     double *out_Y, *out_loss, *out_F, *out_metric;
+    double* out_fc;                   // [B][n_fc] fold-change table (simulate.py:105-182) or nullptr
     int *out_status, *out_nsteps, *out_nrej;
     double* traj;                     // [grid][T][n] scratch when out_Y is not requested
     double* binv;                     // [grid][binv_stride] model 2: inverses of the per-protein pattern blocks
@@ -233,10 +234,12 @@ __device__ __forceinline__ void loss_sums(const GlobalTopoDev& tp, const double*
 
 // Morris scalar of the global path: fold changes (floor 1e-12) of every protein / mRNA / site at the
 // requested time indices (simulate.py:105-182) reduced as sensitivity.py:106-140.
+// fc (optional): the fold changes themselves, [N*n_mt_prot | N*n_mt_rna | total_sites*n_mt_pho] — protein-major, then
+// (site,) time, the row order of simulate_and_measure's three tables after its time filter (simulate.py:184-200).
 __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const double* traj, int n, int metric,
                                                int n_mt_prot, int n_mt_rna, int n_mt_pho, const int* mt_prot,
                                                const int* mt_rna, const int* mt_pho, int mb_prot, int mb_rna, int mb_pho,
-                                               double* red) {
+                                               double* red, double* fc_out = nullptr) {
     const int N = tp.N;
     const bool comb = tp.model == 2;          // simulate.py:135-158
     double s1 = 0.0, s2 = 0.0;
@@ -250,6 +253,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
         const int cnt = comb ? (1 << ns) : ns + 1;
         for (int j = 0; j < cnt; ++j) { a1 += rt[j]; b1 += rb[j]; }
         const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
+        if (fc_out) fc_out[k] = fc;
         s1 += fc;
         s2 = fma(fc, fc, s2);
     }
@@ -257,6 +261,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
         const int i = k / n_mt_rna, ti = mt_rna[k - i * n_mt_rna];
         const int st = tp.offset_y[i];
         const double fc = fmax(traj[(size_t)ti * n + st], 1e-12) / fmax(traj[(size_t)mb_rna * n + st], 1e-12);
+        if (fc_out) fc_out[np_ + k] = fc;
         s1 += fc;
         s2 = fma(fc, fc, s2);
     }
@@ -277,6 +282,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
                     b1 = traj[(size_t)mb_pho * n + st + 2 + j];
                 }
                 const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
+                if (fc_out) fc_out[np_ + nr_ + tp.offset_s[i] * n_mt_pho + k] = fc;
                 s1 += fc;
                 s2 = fma(fc, fc, s2);
             }
@@ -1284,10 +1290,12 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                 }
             }
         }
-        if (a.out_metric) {
+        if (a.out_metric || a.out_fc) {
+            const size_t nfc = (size_t)N * (a.n_mt_prot + a.n_mt_rna) + (size_t)S * a.n_mt_pho;
             const double mv = metric_value(tp, traj, n, a.metric, a.n_mt_prot, a.n_mt_rna, a.n_mt_pho, a.mt_prot, a.mt_rna,
-                                           a.mt_pho, a.mb_prot, a.mb_rna, a.mb_pho, cx.red);
-            if (threadIdx.x == 0) a.out_metric[sys] = mv;
+                                           a.mt_pho, a.mb_prot, a.mb_rna, a.mb_pho, cx.red,
+                                           a.out_fc ? a.out_fc + (size_t)sys * nfc : nullptr);
+            if (threadIdx.x == 0 && a.out_metric) a.out_metric[sys] = mv;
         }
     }
 }

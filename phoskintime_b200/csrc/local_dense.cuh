@@ -147,12 +147,10 @@ __device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double*
     dsync<NT>();
 }
 
-constexpr int DENSE_HQ = 1;       // step-size grid: 2^(j/DENSE_HQ)
-
-// largest grid value <= h
-__device__ __forceinline__ double dense_quantize_h(double h) {
+// largest value of the step-size grid 2^(j*lg), j integer, that is <= h
+__device__ __forceinline__ double dense_quantize_h(double h, double lg) {
     if (!(h > 0.0) || !(h < 1.0e300)) return h;
-    return exp2(floor(log2(h) * (double)DENSE_HQ) * (1.0 / (double)DENSE_HQ));
+    return exp2(floor(log2(h) / lg) * lg);
 }
 
 // In-place inverse by Gauss-Jordan elimination without pivoting.  Thread (tx, ty) = (tid & 31, tid >> 5) updates
@@ -387,7 +385,7 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
         d0 = dense_max<NT>(d0, red);
         d1 = dense_max<NT>(d1, red);
         const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        StepCtl ctl{dense_quantize_h(h0), (float)h0, 1.0f, 0, 0};
+        StepCtl ctl{dense_quantize_h(h0, a.hgrid_log2), (float)h0, 1.0f, 0, 0};
         emit(0, y);
 
         // ---------------------------------------------------------------------- time loop
@@ -463,7 +461,7 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
                 const double hprop = ctl.h;
                 const double hnew = ctl_accept(ctl, hh, err, a.m.expo);
                 const double hp = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
-                double hq = dense_quantize_h(hp);
+                double hq = dense_quantize_h(hp, a.hgrid_log2);
                 // hysteresis: a proposal only slightly below the current grid step keeps it (the proposal already
                 // carries the 0.9 safety factor), so the controller does not flip between two neighbouring levels
                 if (hq < hprop && hp >= 0.85 * hprop) hq = hprop;
@@ -474,7 +472,7 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
                 else t += hh;
             } else {
                 ++nrej;
-                ctl.h = dense_quantize_h(ctl_reject(ctl, hh, err, a.m.expo));
+                ctl.h = dense_quantize_h(ctl_reject(ctl, hh, err, a.m.expo), a.hgrid_log2);
                 if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
             }
             if (status == 0 && kout < T && nst + nrej >= a.max_steps) status = 1;

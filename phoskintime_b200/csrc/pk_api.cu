@@ -308,7 +308,7 @@ int pk_destroy(pk_handle_t h) {
                       &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
-                       &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv};
+                       &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
     for (DevBuf* b : gbufs) b->release();
     pkh::release_global_topologies(h);
     if (h->counter) cudaFree(h->counter);
@@ -421,6 +421,10 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     // 1.25 / 0.82 / 0.33 of the parity bound at (1e-2, 1/10) / (4e-3, 1/10) / (4e-3, 1/20); ROS5L at 2e-6: 0.55.
     a.rtol_floor = ros6 ? 0.05 * a.rtol : a.rtol;
     a.kappa = ros6 ? 4e-3 : 0.0;
+    // dense kernel: power-of-two step grid.  Measured (tools/dense_grid_scan.py, rand-6): ratio 2 -> 1.68e5 solves/s at 85 steps,
+    // ratio 4 -> 1.76e5 at 119 steps (inversions saved ~ mat-vecs added), ratio 2.83 -> 1.67e5; ratios above the
+    // controller's growth limit (6) stall.
+    a.hgrid_log2 = 1.0;
     a.max_steps = j->max_steps > 0 ? j->max_steps : 100000;
     a.normalize = j->normalize; a.log_params = j->log_params;
     a.y_metric = j->out_Y ? j->y_metric : -1;

@@ -370,6 +370,15 @@ int pk_global_dims(pk_handle_t h, int32_t topo_id, int32_t* state_dim, int32_t* 
     return 0;
 }
 
+int pk_global_counts(pk_handle_t h, int32_t topo_id, int32_t* n_proteins, int32_t* n_kinases, int32_t* total_sites) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_counts: bad handle or topology id");
+    if (n_proteins) *n_proteins = th->dev.N;
+    if (n_kinases) *n_kinases = th->dev.K;
+    if (total_sites) *total_sites = th->dev.S;
+    return 0;
+}
+
 void pk_global_job_init(pk_global_job* job) {
     memset(job, 0, sizeof(*job));
     job->metric = PK_GM_NONE;
@@ -392,8 +401,8 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     if (want_loss && !th->has_loss) return fail("out_loss/out_F need pk_global_set_loss_data");
     if (want_loss && th->T_loss_max >= j->T) return fail("loss tables reference a time index >= T");
     if (want_loss && (j->loss_mode < -1 || j->loss_mode > 7)) return fail("loss_mode out of range");
-    if (j->out_metric) {
-        if (j->metric < 0 || j->metric > 3) return fail("out_metric needs a valid metric id");
+    if (j->out_metric || j->out_fc) {
+        if (j->out_metric && (j->metric < 0 || j->metric > 3)) return fail("out_metric needs a valid metric id");
         if (j->n_mt_prot < 0 || j->n_mt_rna < 0 || j->n_mt_pho < 0) return fail("negative metric time count");
         const int32_t* lists[3] = {j->mt_prot, j->mt_rna, j->mt_pho};
         const int cnt[3] = {j->n_mt_prot, j->n_mt_rna, j->n_mt_pho};
@@ -427,7 +436,9 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
         if (o < T && stops[k] == j->t_eval[o]) s_out[k] = o++;
         s_bucket[k] = pkh::bucket_of(k + 1 < ns ? 0.5 * (stops[k] + stops[k + 1]) : stops[k], th->kin_grid);
     }
-    const int n_mt = j->out_metric ? j->n_mt_prot + j->n_mt_rna + j->n_mt_pho : 0;
+    const bool want_fc_tab = j->out_metric || j->out_fc;
+    const int n_mt = want_fc_tab ? j->n_mt_prot + j->n_mt_rna + j->n_mt_pho : 0;
+    const size_t nfc = want_fc_tab ? (size_t)d.N * (j->n_mt_prot + j->n_mt_rna) + (size_t)d.S * j->n_mt_pho : 0;
     const size_t stop_bytes = (size_t)ns * sizeof(double) + (size_t)(2 * ns + n_mt) * sizeof(int);
     CK(h->g_stops.ensure(stop_bytes));
     {
@@ -484,6 +495,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
         a.params = j->params; a.y0 = j->y0;
         a.out_Y = j->out_Y; a.out_loss = j->out_loss; a.out_F = j->out_F; a.out_metric = j->out_metric;
         a.out_status = j->out_status; a.out_nsteps = j->out_nsteps; a.out_nrej = j->out_nrej;
+        a.out_fc = j->out_fc;
     } else {
 #define WS(buf, need, bytes, dstfield)                                                        \
     do {                                                                                      \
@@ -495,6 +507,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
         WS(g_loss, j->out_loss, B * 3 * sizeof(double), a.out_loss);
         WS(g_F, j->out_F, B * 3 * sizeof(double), a.out_F);
         WS(g_metric, j->out_metric, B * sizeof(double), a.out_metric);
+        WS(g_fc, j->out_fc, B * nfc * sizeof(double), a.out_fc);
         WS(g_status, j->out_status, B * sizeof(int32_t), a.out_status);
         WS(g_nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
         WS(g_nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
@@ -527,6 +540,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
         BACK(j->out_loss, a.out_loss, B * 3 * sizeof(double));
         BACK(j->out_F, a.out_F, B * 3 * sizeof(double));
         BACK(j->out_metric, a.out_metric, B * sizeof(double));
+        BACK(j->out_fc, a.out_fc, B * nfc * sizeof(double));
         BACK(j->out_status, a.out_status, B * sizeof(int32_t));
         BACK(j->out_nsteps, a.out_nsteps, B * sizeof(int32_t));
         BACK(j->out_nrej, a.out_nrej, B * sizeof(int32_t));

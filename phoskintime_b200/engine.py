@@ -323,7 +323,10 @@ class Engine:
     def global_dims(self, topo):
         v = [C.c_int32() for _ in range(4)]
         _lib.check(self.lib.pk_global_dims(self._h, int(topo), *[C.byref(x) for x in v]))
-        return {"state_dim": v[0].value, "n_params": v[1].value, "n_reg": v[2].value, "smem_bytes": v[3].value}
+        c = [C.c_int32() for _ in range(3)]
+        _lib.check(self.lib.pk_global_counts(self._h, int(topo), *[C.byref(x) for x in c]))
+        return {"state_dim": v[0].value, "n_params": v[1].value, "n_reg": v[2].value, "smem_bytes": v[3].value,
+                "n_proteins": c[0].value, "n_kinases": c[1].value, "total_sites": c[2].value}
 
     def global_set_loss_data(self, topo, ld):
         """Install the observation tables of LOSS_FN (global_model/lossfn.py:113-121; built by
@@ -356,7 +359,9 @@ class Engine:
                            theta_mode=False, loss_mode=0, metric="total_signal", metric_times=None,
                            lambdas=(1.0, 1.0, 1.0), lambda_prior=0.0, out=None):
         """Integrate B parameter vectors of one uploaded network.  Returns a dict with the requested
-        keys among Y[B,T,state_dim], loss[B,3], F[B,3], metric[B] plus status/nsteps/nrej[B].
+        keys among Y[B,T,state_dim], loss[B,3], F[B,3], metric[B], fc[B,n_fc] plus status/nsteps/nrej[B].
+        fc = the fold-change table of simulate_and_measure (simulate.py:105-182): [N*len(t_prot) | N*len(t_rna) |
+        total_sites*len(t_pho)], protein-major then (site,) time.
 
         params : [B,P] physical values (or raw theta with theta_mode=True: softplus is applied on the
                  device, global_model/params.py:106-132), order c_k|A|B|C|D|Dp|E|tf_scale
@@ -364,7 +369,7 @@ class Engine:
                  t_eval simulate_and_measure tabulates (global_model/simulate.py:105-182)
         """
         want = tuple(want)
-        unknown = set(want) - {"Y", "loss", "F", "metric"}
+        unknown = set(want) - {"Y", "loss", "F", "metric", "fc"}
         if unknown:
             raise ValueError(f"unknown outputs {sorted(unknown)}")
         dev = _is_torch(params)
@@ -415,9 +420,9 @@ class Engine:
             job.out_loss = alloc("loss", (B, 3))
         if "F" in want:
             job.out_F = alloc("F", (B, 3))
-        if "metric" in want:
+        if "metric" in want or "fc" in want:
             if metric_times is None:
-                raise ValueError("metric needs metric_times")
+                raise ValueError("metric / fc need metric_times")
             job.metric = GLOBAL_METRIC_IDS[metric]
             for name, key in (("prot", "t_prot"), ("rna", "t_rna"), ("pho", "t_pho")):
                 a = np.ascontiguousarray(metric_times[key], dtype=np.int32).reshape(-1)
@@ -426,7 +431,11 @@ class Engine:
                 setattr(job, "mt_" + name, a.ctypes.data)
             job.mb_prot, job.mb_rna, job.mb_pho = (int(metric_times["prot_b"]), int(metric_times["rna_b"]),
                                                    int(metric_times["pho_b"]))
-            job.out_metric = alloc("metric", (B,))
+            if "metric" in want:
+                job.out_metric = alloc("metric", (B,))
+            if "fc" in want:
+                n_fc = dims["n_proteins"] * (job.n_mt_prot + job.n_mt_rna) + dims["total_sites"] * job.n_mt_pho
+                job.out_fc = alloc("fc", (B, n_fc))
         job.out_status = alloc("status", (B,), "i32")
         job.out_nsteps = alloc("nsteps", (B,), "i32")
         job.out_nrej = alloc("nrej", (B,), "i32")

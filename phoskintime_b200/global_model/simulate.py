@@ -76,6 +76,45 @@ def metric_time_indices(times, t_points_p, t_points_r, t_points_pho):
             "prot_b": bidx(METRIC_BASE_TIMES[0]), "rna_b": bidx(METRIC_BASE_TIMES[1]), "pho_b": bidx(METRIC_BASE_TIMES[2])}
 
 
+def fold_change_tables(sys_, params, t_points_p, t_points_r, t_points_pho, *, rtol=1e-5, atol=1e-7, mxstep=5000, engine=None):
+    """The three fold-change tables of `simulate_and_measure` (simulate.py:105-182) for B parameter vectors, computed
+    in the solve kernel's epilogue: returns dict(times, fc_prot[B,N,len(tp)], fc_rna[B,N,len(tr)], fc_pho[B,total_sites,
+    len(tph)], status) — rows in the reference's order (protein-major, sites in block order, times ascending), floors
+    1e-12, baselines t=0 / t=4 / t=0, tolerances of simulate.py:109."""
+    times = np.unique(np.concatenate([t_points_p, t_points_r, t_points_pho]).astype(np.float64))
+    mt = metric_time_indices(times, t_points_p, t_points_r, t_points_pho)
+    params = np.atleast_2d(params) if isinstance(params, np.ndarray) else params
+    r = simulate_batch(sys_, params, times, ("fc",), rtol=rtol, atol=atol, mxstep=mxstep, metric_times=mt, engine=engine)
+    fc = r["fc"]
+    B, N, S = fc.shape[0], sys_.idx.N, sys_.idx.total_sites
+    np_, nr_, nph = mt["t_prot"].size, mt["t_rna"].size, mt["t_pho"].size
+    return {"times": times, "t_prot": times[mt["t_prot"]], "t_rna": times[mt["t_rna"]], "t_pho": times[mt["t_pho"]],
+            "fc_prot": fc[:, :N * np_].reshape(B, N, np_), "fc_rna": fc[:, N * np_:N * (np_ + nr_)].reshape(B, N, nr_),
+            "fc_pho": fc[:, N * (np_ + nr_):].reshape(B, S, nph), "status": r["status"]}
+
+
+def simulate_and_measure(sys, idx, t_points_p, t_points_r, t_points_pho):
+    """Reference signature (global_model/simulate.py:83): current parameters of `sys` -> (df_prot, df_rna, df_phos)
+    with columns [protein, time, pred_fc] / [protein, psite, time, pred_fc].  `idx` supplies the names
+    (`idx.proteins`, `idx.sites`); pass None for integer labels.  Needs pandas, like the reference."""
+    import pandas as pd
+    tab = fold_change_tables(sys, sys.pack_params()[None, :], t_points_p, t_points_r, t_points_pho)
+    N = sys.idx.N
+    names = list(idx.proteins) if idx is not None and hasattr(idx, "proteins") else list(range(N))
+    sites = (idx.sites if idx is not None and hasattr(idx, "sites") else
+             [list(range(int(k))) for k in sys.idx.n_sites])
+    mk = lambda fc, t: pd.DataFrame({"protein": np.repeat(np.asarray(names, dtype=object), t.size),
+                                     "time": np.tile(t, N), "pred_fc": fc.reshape(-1)})
+    df_p, df_r = mk(tab["fc_prot"][0], tab["t_prot"]), mk(tab["fc_rna"][0], tab["t_rna"])
+    prot_col = [names[i] for i in range(N) for _ in sites[i]]
+    site_col = [s for i in range(N) for s in sites[i]]
+    t = tab["t_pho"]
+    df_ph = pd.DataFrame({"protein": np.repeat(np.asarray(prot_col, dtype=object), t.size),
+                          "psite": np.repeat(np.asarray(site_col, dtype=object), t.size),
+                          "time": np.tile(t, len(site_col)), "pred_fc": tab["fc_pho"][0].reshape(-1)})
+    return df_p, df_r, df_ph
+
+
 def LOSS_FN(Y, p_prot, t_prot, obs_prot, w_prot, p_rna, t_rna, obs_rna, w_rna, p_pho, s_pho, t_pho, obs_pho, w_pho,
             prot_map, prot_base_idx, rna_base_idx, pho_base_idx, *, loss_mode=0, model=0, engine=None):
     """Reference signature of `LOSS_FN` (global_model/lossfn.py:113-121, :386): one trajectory

@@ -23,7 +23,8 @@ from conftest import GOLDEN, ROOT
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import global_models as og  # noqa: E402
 from phoskintime_b200.global_model import (LOSS_FN, GlobalODE_MOO, init_raw_params, metric_time_indices,  # noqa: E402
-                                           run_sensitivity_analysis, simulate_batch, simulate_odeint, solve_custom,
+                                           run_sensitivity_analysis, simulate_batch, simulate_odeint, solve_custom, fold_change_tables,
+                                           simulate_and_measure,
                                            synthetic_loss_data, synthetic_system, unpack_params)
 import morris as omorris  # noqa: E402
 
@@ -256,6 +257,29 @@ def test_simulate_until_steady_long_log_grid(engine):
     assert np.isclose(rate, np.linalg.norm(Y[-1] - Y[-2]) / (t[-1] - t[-2])) and rate < 1e-3
     tb, Yb, rb, st = steady_check_batch(s, g["params"], engine=engine)
     assert (st == 0).all() and np.array_equal(Yb[1], Y) and np.isclose(rb[1], rate)
+
+
+@pytest.mark.parametrize("path", [FILES[0], FILES[4]], ids=[IDS[0], IDS[4]])
+def test_fold_change_tables_match_oracle(engine, path):
+    """simulate_and_measure's three tables (simulate.py:105-182) from the kernel epilogue vs the oracle's tabulation of
+    the same trajectories; the reference-signature wrapper returns the same numbers as DataFrames."""
+    g, s, _ = load_case(path)
+    net = s.as_dict()
+    tab = fold_change_tables(s, g["params"], T_PROT, T_RNA, T_PROT, engine=engine)
+    assert (tab["status"] == 0).all() and np.array_equal(tab["times"], np.unique(np.concatenate([T_PROT, T_RNA])))
+    mt = metric_time_indices(tab["times"], T_PROT, T_RNA, T_PROT)
+    Y = simulate_batch(s, g["params"], tab["times"], ("Y",), rtol=1e-5, atol=1e-7, mxstep=5000, engine=engine)["Y"]
+    for b in range(g["params"].shape[0]):
+        P, R, PH = og.fc_tables(Y[b], net, mt)
+        assert np.allclose(tab["fc_prot"][b], P, rtol=1e-12, atol=0) and np.allclose(tab["fc_rna"][b], R, rtol=1e-12, atol=0)
+        assert np.allclose(tab["fc_pho"][b], PH, rtol=1e-12, atol=0)
+    s.update(**s.unpack_params(g["params"][1]))
+    df_p, df_r, df_ph = simulate_and_measure(s, None, T_PROT, T_RNA, T_PROT)
+    assert list(df_p.columns) == ["protein", "time", "pred_fc"] and list(df_ph.columns) == ["protein", "psite", "time", "pred_fc"]
+    assert len(df_p) == s.idx.N * len(T_PROT) and len(df_r) == s.idx.N * len(T_RNA) and len(df_ph) == s.idx.total_sites * len(T_PROT)
+    assert np.array_equal(df_p["pred_fc"].to_numpy(), tab["fc_prot"][1].reshape(-1))
+    assert np.array_equal(df_r["time"].to_numpy()[:len(T_RNA)], np.asarray(T_RNA))
+    assert (df_p["pred_fc"].to_numpy()[::len(T_PROT)] == 1.0).all()          # every protein's t = 0 row is its own baseline
 
 
 def test_solve_custom_signature(engine):
