@@ -95,7 +95,7 @@ struct DistModel {
 
 template <int NS_>
 struct SuccModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 3 * NS_ + 3;
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4;
     // d[0] = D + S_0 (protein), d[1+i] = 1 + Dr_i + S_{i+1} (site i; no S term for the last site)
     double A, Bm, C, S[NS], d[NS + 1];
     __device__ __forceinline__ void load(const double* p) {
@@ -120,7 +120,7 @@ struct SuccModel {
     // Continuants theta_j = a_j theta_{j-1} - (c S_{j-1}) c theta_{j-2} give the Thomas pivots
     // p_j = theta_j / theta_{j-1} without a sequential chain of divisions (no pivoting needed: the
     // block is strictly column diagonally dominant for non-negative rates).
-    // F = [1/q0, cC, 1/p_j (NS+1), l_j = c S_{j-1}/p_{j-1} (NS), c/p_j (NS)]
+    // F = [1/q0, cC, 1/p_j (NS+1), l_j = c S_{j-1}/p_{j-1} (NS), c]
     __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
         double th[NS + 2];                       // th[0] = q0, th[1+j] = theta_j
         th[0] = fma(c, Bm, 1.0);
@@ -142,8 +142,7 @@ struct SuccModel {
         for (int j = 1; j <= NS; ++j) F[2 + j] = th[j] * inv[1 + j];   // theta_{j-1} / theta_j
 #pragma unroll
         for (int j = 1; j <= NS; ++j) F[2 + NS + j] = cs[j - 1] * F[1 + j];       // l_j
-#pragma unroll
-        for (int j = 0; j < NS; ++j) F[3 + 2 * NS + j] = c * F[2 + j];            // c / p_j
+        F[3 + 2 * NS] = c;
     }
     __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
         x[0] *= F[0];
@@ -152,7 +151,7 @@ struct SuccModel {
         for (int j = 1; j <= NS; ++j) x[1 + j] = fma(F[2 + NS + j], x[j], x[1 + j]);        // forward
         x[1 + NS] *= F[2 + NS];
 #pragma unroll
-        for (int j = NS - 1; j >= 0; --j) x[1 + j] = fma(F[3 + 2 * NS + j], x[2 + j], x[1 + j] * F[2 + j]);
+        for (int j = NS - 1; j >= 0; --j) x[1 + j] = fma(F[3 + 2 * NS], x[2 + j], x[1 + j]) * F[2 + j];   // (x_j + c x_{j+1}) / p_j
     }
 };
 
@@ -306,9 +305,10 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     }
                     float err = 0.0f;
                     double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
+                    const float rtolf = (float)a.rtol, floorf_ = (float)a.rtol_floor, kapf = (float)a.kappa, atolf = (float)a.atol;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], a.rtol, a.rtol_floor, a.kappa, a.atol));
+                        err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], rtolf, floorf_, kapf, atolf));
                         chk += yn[i];
                     }
                     if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
