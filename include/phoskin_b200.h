@@ -130,6 +130,12 @@ int pk_measure_fp64_peak(pk_handle_t h, double* tflops, float* ms);
  * for steps that reuse an inverse computed for a larger step; exported for verification (host arithmetic). */
 int pk_ros5l_coeffs(double gamma, double* mu6, double* eps6);
 
+/* The solve fused with the path's one collective: the batch is integrated in `chunks` pieces (<=0 -> 4) and the
+ * all-gather of piece c's per-sample output (which: 0 out_score, 1 out_ssr, 2 out_Y; must be requested in the job)
+ * runs on a second, high-priority stream while piece c+1 integrates — only the last piece's gather is exposed.
+ * recv_dev [world*B] is filled rank-major (the layout pk_allgather_f64 produces).  Device buffers only. */
+int pk_local_solve_allgather(pk_handle_t h, const pk_local_job* job, int32_t which, int32_t chunks, double* recv_dev);
+
 int pk_nccl_unique_id(char* out128);
 int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank);
 int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev);

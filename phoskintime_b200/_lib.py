@@ -128,6 +128,7 @@ SYMBOLS = {
     "pk_ros5l_coeffs": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "pk_local_solve_allgather": (C.c_int, [C.c_void_p, C.POINTER(PkLocalJob), C.c_int32, C.c_int32, C.c_void_p]),
     "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pk_nlls_job_init": (None, [C.POINTER(PkNllsJob)]),
     "pk_sizeof_nlls_job": (C.c_int, []),

@@ -286,7 +286,12 @@ int pk_create(int device, pk_handle_t* out) {
     snprintf(h->name, sizeof(h->name), "%.127s", prop.name);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    {   // copy-out / collective stream at the highest priority: a collective that becomes runnable together with the
+        // next piece's persistent compute grid must get its SM slots first (pk_local_solve_allgather)
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->s_out, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < pk_handle_s::MAX_CHUNKS; ++i) {
         CK(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
@@ -305,7 +310,7 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
                        &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
@@ -454,12 +459,54 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
         a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
         a.out_nrej = j->out_nrej;
-        CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+        // pk_local_solve_allgather: integrate in pieces; the all-gather of piece c (copy stream) overlaps piece c+1
+        double* const ag = h->ag_recv;
+        int nch = ag ? std::min(h->ag_chunks, PIPE_MAX_CHUNKS) : 1;
+        if ((size_t)nch > B) nch = (int)B;
+        if (nch < 1) nch = 1;
+        const size_t W = (size_t)h->world;
+        if (ag && W > 1) CK(h->ag_stage.ensure(W * B * sizeof(double)));
         CK(cudaEventRecord(h->ev0, st));
-        cudaError_t e = launch(a);
-        if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+        for (int c = 0; c < nch; ++c) {
+            const size_t o = B * (size_t)c / nch, cnt = B * (size_t)(c + 1) / nch - o;
+            pk::LocalArgs ac = a;
+            ac.B = (long long)cnt;
+            ac.params += o * P;
+            if (j->y0_stride) ac.y0 += o * j->y0_stride;
+            if (ac.group) ac.group += o;
+            if (ac.out_sol) ac.out_sol += o * TN;
+            if (ac.out_flat) ac.out_flat += o * L;
+            if (ac.out_Y) ac.out_Y += o;
+            if (ac.out_ssr) ac.out_ssr += o;
+            if (ac.out_score) ac.out_score += o;
+            if (ac.out_status) ac.out_status += o;
+            if (ac.out_nsteps) ac.out_nsteps += o;
+            if (ac.out_nrej) ac.out_nrej += o;
+            CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
+            cudaError_t e = launch(ac);
+            if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
+            h->last_launches++;
+            if (ag) {
+                const double* src = h->ag_which == 0 ? ac.out_score : (h->ag_which == 1 ? ac.out_ssr : ac.out_Y);
+                CK(cudaEventRecord(h->ev_k[c], st));
+                CK(cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+                if (W == 1) {
+                    CK(cudaMemcpyAsync(ag + o, src, cnt * sizeof(double), cudaMemcpyDeviceToDevice, h->s_out));
+                } else {
+                    double* stage = (double*)h->ag_stage.p + W * o;            // [world][cnt]
+                    int r = g_nccl.AllGather(src, stage, cnt, NCCL_FLOAT64, h->comm, h->s_out);
+                    if (r != 0) return fail(std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+                    // rank-major placement: row r of the landing area goes to recv[r*B + o .. + cnt)
+                    CK(cudaMemcpy2DAsync(ag + o, B * sizeof(double), stage, cnt * sizeof(double), cnt * sizeof(double), W,
+                                         cudaMemcpyDeviceToDevice, h->s_out));
+                }
+            }
+        }
         CK(cudaEventRecord(h->ev1, st));
-        h->last_launches = 1;
+        if (ag) {                                   // join the collective stream back into the compute stream
+            CK(cudaEventRecord(h->ev_in[0], h->s_out));
+            CK(cudaStreamWaitEvent(st, h->ev_in[0], 0));
+        }
         CK(cudaStreamSynchronize(st));
         CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
         return 0;
@@ -663,6 +710,21 @@ int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank) {
     int r = g_nccl.CommInitRank(&h->comm, world, id, rank);
     if (r != 0) return fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
     return 0;
+}
+
+int pk_local_solve_allgather(pk_handle_t h, const pk_local_job* job, int32_t which, int32_t chunks, double* recv_dev) {
+    if (!h || !job || !recv_dev) return fail("pk_local_solve_allgather: null argument");
+    if (job->memspace != PK_DEVICE) return fail("pk_local_solve_allgather needs device buffers");
+    if (which < 0 || which > 2) return fail("pk_local_solve_allgather: which must be 0 (score), 1 (ssr) or 2 (Y)");
+    if ((which == 0 && !job->out_score) || (which == 1 && !job->out_ssr) || (which == 2 && !job->out_Y))
+        return fail("pk_local_solve_allgather: the gathered output must be requested in the job");
+    if (h->world > 1 && !h->comm) return fail("pk_nccl_init was not called");
+    h->ag_recv = recv_dev;
+    h->ag_which = which;
+    h->ag_chunks = chunks > 0 ? chunks : 4;
+    const int rc = pk_local_solve_batch(h, job);
+    h->ag_recv = nullptr;
+    return rc;
 }
 
 int pk_allgather_f64(pk_handle_t h, const double* send_dev, int64_t count, double* recv_dev) {

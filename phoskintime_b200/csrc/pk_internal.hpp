@@ -66,6 +66,9 @@ struct pk_handle_s {
     unsigned long long* counter = nullptr;
     int last_launches = 0;
     float last_ms = 0.f;
+    pkh::DevBuf ag_stage;                      // pk_local_solve_allgather: [world][chunk] landing area of one piece
+    double* ag_recv = nullptr;                 // set for the duration of one pk_local_solve_allgather call
+    int ag_which = 0, ag_chunks = 1;
     pkh::ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
     std::vector<pkh::GlobalTopoHost*> topos;   // uploaded global networks (index = topology id)

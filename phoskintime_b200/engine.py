@@ -86,7 +86,7 @@ class Engine:
     def solve_local_batch(self, model, params, init_cond, num_psites, t, want=("sol", "flat"), *,
                           target=None, sigma=None, group=None, lam=0.0, y_metric="total_signal",
                           rtol=None, atol=None, max_steps=0, normalize=False, log_params=False,
-                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True, method=None):
+                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True, method=None, gather=None):
         """Solve B systems.  Returns a dict with the requested keys among
         sol[B,T,n], flat[B,L], Y[B], ssr[B], score[B] plus status/nsteps/nrej[B] (int32).
 
@@ -96,7 +96,11 @@ class Engine:
             [G,·]; group [B] int32 indices into G (None = all 0)
         out : optional dict of preallocated outputs (same kind as params) to fill
         counters : also return accepted/rejected step counts per system (nsteps, nrej)
-        method : None/'ros5l' (order 5(4), default) or 'rodas4' (order 4(3)) — DESIGN.md §2
+        method : None (library default: 'ros6l' on the thread-per-system kernels, 'ros5l' on the dense kernel),
+            'ros6l', 'ros5l' or 'rodas4' — DESIGN.md §2
+        gather : (key, recv, chunks) — fuse the solve with the NCCL all-gather of the per-sample output `key`
+            ('score', 'ssr' or 'Y'; torch CUDA path only): the batch is integrated in `chunks` pieces and piece c's
+            gather overlaps piece c+1 (`pk_local_solve_allgather`); recv [world*B] comes back rank-major
         """
         want = tuple(want)
         unknown = set(want) - {"sol", "flat", "Y", "ssr", "score"}
@@ -190,7 +194,15 @@ class Engine:
 
         if dev:
             xp.sync()          # inputs produced on torch's stream must be visible to ours
-        _lib.check(self.lib.pk_local_solve_batch(self._h, C.byref(job)))
+        if gather is not None:
+            key, recv, chunks = gather
+            if not dev or key not in res or key not in ("score", "ssr", "Y"):
+                raise ValueError("gather needs torch CUDA buffers and a requested per-sample output (score, ssr or Y)")
+            _lib.check(self.lib.pk_local_solve_allgather(self._h, C.byref(job), {"score": 0, "ssr": 1, "Y": 2}[key],
+                                                         int(chunks), recv.data_ptr()))
+            res["gathered"] = recv
+        else:
+            _lib.check(self.lib.pk_local_solve_batch(self._h, C.byref(job)))
         del keep
         return res
 

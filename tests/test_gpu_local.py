@@ -253,6 +253,28 @@ def test_pipelined_host_path_equals_device_path(engine):
     assert engine.last_launch_info()[0] == 1
 
 
+def test_fused_gather_single_rank(engine):
+    """pk_local_solve_allgather at world 1: the batch is integrated in pieces, every output equals the one-launch
+    result bit for bit and the gathered buffer equals the requested per-sample output."""
+    import torch
+    B = 50_003
+    rng = np.random.default_rng(9)
+    p = torch.from_numpy(rng.uniform(0.05, 3.0, (B, 14))).cuda()
+    y0 = torch.from_numpy(rng.uniform(0.1, 1.0, (B, 7))).cuda()
+    t = torch.from_numpy(T14).cuda()
+    tg = torch.from_numpy(rng.random(93)).cuda()
+    a = engine.solve_local_batch("succmod", p, y0, 5, t, want=("flat", "ssr", "score", "Y"), target=tg)
+    assert engine.last_launch_info()[0] == 1
+    for key in ("score", "ssr", "Y"):
+        recv = torch.full((B,), -1.0, dtype=torch.float64, device="cuda")
+        b = engine.solve_local_batch("succmod", p, y0, 5, t, want=("flat", "ssr", "score", "Y"), target=tg,
+                                     gather=(key, recv, 3))
+        assert engine.last_launch_info()[0] == 3
+        for k in ("flat", "ssr", "score", "Y", "status", "nsteps", "nrej"):
+            assert torch.equal(a[k], b[k]), k
+        assert torch.equal(b["gathered"], a[key])
+
+
 def test_large_batch_properties(engine):
     """Size-independent checks at bench scale (2^18 systems): steady states stay put, the flow is
     a semigroup (solve to t1 then on to t2 == solve to t2), and the map is affine in (A, y0)."""
