@@ -123,11 +123,26 @@ __global__ void nlls_step_kernel(const NllsArgs a, int warps_per_cta, int Lp) {
         for (int j = lane; j < P; j += 32) tr[j] = th[j];
         return;
     }
-    for (int l = lane; l < L; l += 32) {
-        const double is = sg ? 1.0 / sg[l] : 1.0;
-        const double base = f0[l];
-        r[l] = (base - tg[l]) * is;
-        for (int j = 0; j < P; ++j) J[(size_t)j * Lp + l] = (a.flat[(row0 + 1 + j) * L + l] - base) * is / a.hstep[b * P + j];
+    // reciprocal forward-difference steps once per problem (dl is free until the normal equations are damped)
+    for (int j = lane; j < P; j += 32) dl[j] = 1.0 / a.hstep[b * P + j];
+    __syncwarp();
+    {
+        const double* __restrict__ fl = a.flat + (row0 + 1) * L;     // the P perturbed rows, [P][L]
+        for (int l = lane; l < L; l += 32) {
+            const double is = sg ? 1.0 / sg[l] : 1.0;
+            const double base = f0[l];
+            r[l] = (base - tg[l]) * is;
+            int j = 0;
+            for (; j + 4 <= P; j += 4) {                              // four independent loads in flight per lane
+                const double v0 = fl[(size_t)j * L + l], v1 = fl[(size_t)(j + 1) * L + l];
+                const double v2 = fl[(size_t)(j + 2) * L + l], v3 = fl[(size_t)(j + 3) * L + l];
+                J[(size_t)j * Lp + l] = (v0 - base) * is * dl[j];
+                J[(size_t)(j + 1) * Lp + l] = (v1 - base) * is * dl[j + 1];
+                J[(size_t)(j + 2) * Lp + l] = (v2 - base) * is * dl[j + 2];
+                J[(size_t)(j + 3) * Lp + l] = (v3 - base) * is * dl[j + 3];
+            }
+            for (; j < P; ++j) J[(size_t)j * Lp + l] = (fl[(size_t)j * L + l] - base) * is * dl[j];
+        }
     }
     __syncwarp();
     // A = J^T J, g = J^T r  (+ the diagonal regularisation rows lam/P*theta_j^2 / sigma_{L+j})
