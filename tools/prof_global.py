@@ -18,4 +18,4 @@ mt = {"t_prot": np.arange(15), "t_rna": np.arange(5, 15), "t_pho": np.arange(15)
 for _ in range(reps):
     r = simulate_batch(s, P, t, ("metric",), engine=eng, metric_times=mt)
     ms = eng.last_launch_info()[1]
-    print(f"model {model} N={N} B={B}: kernel {ms:.1f} ms -> {B / ms * 1e3:.0f} solves/s steps {r['nsteps'].mean():.0f}", flush=True)
+    print(f"model {model} N={N} B={B}: kernel {ms:.1f} ms -> {B / ms * 1e3:.0f} solves/s steps {r['nsteps'].mean():.0f} rejected {r['nrej'].mean():.1f}", flush=True)
