@@ -44,8 +44,8 @@ enum pk_memspace { PK_HOST = 0, PK_DEVICE = 1 };
 enum pk_y_metric { PK_Y_NONE = -1, PK_Y_TOTAL_SIGNAL = 0, PK_Y_MEAN_ACTIVITY = 1, PK_Y_VARIANCE = 2,
                    PK_Y_DYNAMICS = 3, PK_Y_L2_NORM = 4 };
 /* integrator coefficient set: ROS6L = 7-solve order-6(5) Rosenbrock for linear systems (default of the
- * thread-per-system kernels: dist/succ up to 8 sites), ROS5L = 6-solve order-5(4) (default of the dense kernel),
- * RODAS4 = Hairer-Wanner order-4(3); see DESIGN.md section 2 */
+ * thread-per-system kernels: dist/succ up to 8 sites; selectable on the dense kernel), ROS5L = 6-solve order-5(4)
+ * (default of the dense kernel), RODAS4 = Hairer-Wanner order-4(3); see DESIGN.md section 2 */
 enum pk_method { PK_METHOD_DEFAULT = 0, PK_METHOD_RODAS4 = 1, PK_METHOD_ROS5L = 2, PK_METHOD_ROS6L = 3 };
 enum pk_status { PK_OK = 0, PK_MAX_STEPS = 1, PK_STEP_UNDERFLOW = 2, PK_NON_FINITE = 3 };
 
@@ -129,6 +129,7 @@ int pk_measure_fp64_peak(pk_handle_t h, double* tflops, float* ms);
 /* Coefficients MU[6], EPS[6] of the ROS5L(gamma) member: the dense kernel derives them at run time
  * for steps that reuse an inverse computed for a larger step; exported for verification (host arithmetic). */
 int pk_ros5l_coeffs(double gamma, double* mu6, double* eps6);
+int pk_ros6l_coeffs(double gamma, double* mu7, double* eps7);   /* the seven-solve family (ROS6L) */
 
 /* The solve fused with the path's one collective: the batch is integrated in `chunks` pieces (<=0 -> 4) and the
  * all-gather of piece c's per-sample output (which: 0 out_score, 1 out_ssr, 2 out_Y; must be requested in the job)

@@ -126,6 +126,7 @@ SYMBOLS = {
     "pk_host_free": (C.c_int, [C.c_void_p]),
     "pk_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "pk_ros5l_coeffs": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pk_ros6l_coeffs": (C.c_int, [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pk_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "pk_local_solve_allgather": (C.c_int, [C.c_void_p, C.POINTER(PkLocalJob), C.c_int32, C.c_int32, C.c_void_p]),

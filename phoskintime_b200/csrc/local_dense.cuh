@@ -298,7 +298,7 @@ template <int MODEL, int NT>
 __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     extern __shared__ double smem[];
     __shared__ double red[4];
-    __shared__ double coef[48];           // scratch + results of ros5l_coeffs
+    __shared__ double coef[64];           // scratch + results of rosl_coeffs<6|7>
     __shared__ unsigned long long s_idx;
     const int lane = threadIdx.x;                 // thread index inside the group that owns one system
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
@@ -401,9 +401,10 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
             // step SHORTENED by the output grid (landing / halving) uses it too, as the ROS5L member with
             // gamma' = gamma*h_inv/hh (pk_common.cuh: ros5l_coeffs) — so inversions only happen when the controller
             // moves to another level of the step-size grid.
-            double mu[6], eps[6];
+            double mu[7], eps[7];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { mu[k] = a.m.mu[k]; eps[k] = a.m.eps[k]; }
+            for (int k = 0; k < 7; ++k) { mu[k] = a.m.mu[k]; eps[k] = a.m.eps[k]; }
+            const bool seven = a.m.nsol > 6;          // ROS6L: seven solves per step
             const bool forced = hh != ctl.h;          // hh was set by the output grid, not by the controller
             bool reuse = hh == h_inv;
             if (!reuse && a.m.family == 1 && forced && h_inv > 0.0 && hh <= 1.03 * h_inv && hh * 16.0 >= h_inv) reuse = true;
@@ -418,10 +419,18 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
 #endif
             }
             if (hh != h_inv) {                      // uniform over the system's threads
-                if (lane == 0) ros5l_coeffs(a.m.gamma * h_inv / hh, coef);
+                if (lane == 0) {
+                    if (seven) rosl_coeffs<7>(a.m.gamma * h_inv / hh, coef);
+                    else rosl_coeffs<6>(a.m.gamma * h_inv / hh, coef);
+                }
                 dsync<NT>();
+                if (seven) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { mu[k] = coef[36 + k]; eps[k] = coef[42 + k]; }
+                    for (int k = 0; k < 7; ++k) { mu[k] = coef[48 + k]; eps[k] = coef[55 + k]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { mu[k] = coef[36 + k]; eps[k] = coef[42 + k]; }
+                }
                 dsync<NT>();
             }
 
@@ -440,14 +449,22 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
             dense_apply<NT>(n, ld, W, v2, v, lane);
             for (int i = lane; i < n; i += NT) { w[i] = fma(mu[4], v[i], w[i]); E[i] = fma(eps[4], v[i], E[i]); }
             dense_apply<NT>(n, ld, W, v, v2, lane);
+            const double* vl = v2;                    // last Krylov vector and its coefficients
+            double mul = mu[5], epl = eps[5];
+            if (seven) {
+                for (int i = lane; i < n; i += NT) { w[i] = fma(mu[5], v2[i], w[i]); E[i] = fma(eps[5], v2[i], E[i]); }
+                dense_apply<NT>(n, ld, W, v2, v, lane);
+                vl = v; mul = mu[6]; epl = eps[6];
+            }
             float err = 0.0f;
             bool bad = false;
+            const float rtolf = (float)a.rtol, floorf_ = (float)a.rtol_floor, kapf = (float)a.kappa, atolf = (float)a.atol;
             for (int i = lane; i < n; i += NT) {
-                const double yn = fma(mu[5], v2[i], w[i]);
-                const double ei = fma(eps[5], v2[i], E[i]);
+                const double yn = fma(mul, vl[i], w[i]);
+                const double ei = fma(epl, vl[i], E[i]);
                 w[i] = yn;
-                const float q = err_ratio(ei, y[i], yn, a.rtol, a.atol);
-                bad |= !(q < 3.0e38f) || !(fabs(yn) < 1.0e300);
+                const float q = err_ratio_inc(ei, y[i], yn, rtolf, floorf_, kapf, atolf);
+                bad |= !(q < 3.0e38f) || !(fabs(yn) < 3.0e38);          // NaN/inf, or beyond the FP32 range of the error scale
                 err = fmaxf(err, q);
             }
             if (bad) err = __int_as_float(0x7f800000);

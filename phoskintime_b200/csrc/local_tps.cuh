@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], rtolf, floorf_, kapf, atolf));
                         chk += yn[i];
                     }
-                    if (!(fabs(chk) < 1.0e300) || !(err < 3.0e38f)) {
+                    if (!(fabs(chk) < 3.0e38) || !(err < 3.0e38f)) {     // NaN/inf, or beyond the FP32 range of the error scale
                         status = 3;
                     } else if (err <= 1.0f) {
                         ++nst;

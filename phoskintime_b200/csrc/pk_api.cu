@@ -254,6 +254,13 @@ extern "C" {
 int pk_abi_version(void) { return PK_ABI_VERSION; }
 
 // host evaluation of the run-time ROS5L(gamma) coefficient construction the dense kernel uses (for tests)
+int pk_ros6l_coeffs(double gamma, double* mu7, double* eps7) {
+    if (!(gamma > 0.0) || !mu7 || !eps7) return fail("pk_ros6l_coeffs: bad arguments");
+    double scratch[64];
+    pk::rosl_coeffs<7>(gamma, scratch);
+    for (int k = 0; k < 7; ++k) { mu7[k] = scratch[48 + k]; eps7[k] = scratch[55 + k]; }
+    return 0;
+}
 int pk_ros5l_coeffs(double gamma, double* mu6, double* eps6) {
     if (!(gamma > 0.0) || !mu6 || !eps6) return fail("pk_ros5l_coeffs: bad arguments");
     double scratch[48];
@@ -410,10 +417,10 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     if (j->method < 0 || j->method > 3) return fail("unknown method");
     const bool tps_path = (j->model == PK_DISTMOD && j->n_sites <= TPS_MAX_NS_DIST) ||
                           (j->model == PK_SUCCMOD && j->n_sites <= TPS_MAX_NS_SUCC);
-    // default method: ROS6L (7 solves, order 6(5)) on the thread-per-system kernels, ROS5L (whose inverse-reuse
-    // family the dense kernel exploits) elsewhere
-    if (j->method == PK_METHOD_ROS6L && !tps_path)
-        return fail("PK_METHOD_ROS6L is implemented for the thread-per-system kernels (dist/succ up to 8 sites)");
+    // default method: ROS6L (7 solves, order 6(5)) on the thread-per-system kernels.  The dense kernel supports it too
+    // (run-time ROS6L(gamma') family, rosl_coeffs<7>) but keeps ROS5L as its default: measured on rand-6 the 31 % fewer
+    // steps buy +5 % (U draws) to +33 % (harsh draws) throughput — inversions, not mat-vecs, dominate there — at 0.16-0.22
+    // instead of 0.04-0.10 of the parity bound (tools/dense_method_scan.py).
     const bool ros6 = j->method == PK_METHOD_ROS6L || (j->method == PK_METHOD_DEFAULT && tps_path);
     a.m = (j->method == PK_METHOD_RODAS4) ? pk::METHOD_RODAS4 : (ros6 ? pk::METHOD_ROS6L : pk::METHOD_ROS5L);
     // default tolerances: chosen per method from the measured error against the reference's tight

@@ -253,6 +253,32 @@ def test_pipelined_host_path_equals_device_path(engine):
     assert engine.last_launch_info()[0] == 1
 
 
+@pytest.mark.parametrize("ns", [3, 4, 6])
+def test_dense_kernel_ros6l_option_matches_goldens(engine, ns):
+    """The seven-solve family on the dense kernel (method='ros6l': run-time ROS6L(gamma') coefficients for steps that
+    reuse an inverse) against the reference goldens of the random model; fewer steps than the default ROS5L."""
+    g = np.load(os.path.join(GOLDEN, f"local_randmod_ns{ns}.npz"))
+    a = engine.solve_local_batch("randmod", g["params"], g["y0"], ns, g["t"], want=("sol",), method="ros6l")
+    b = engine.solve_local_batch("randmod", g["params"], g["y0"], ns, g["t"], want=("sol",))
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    tight = g["sol_tight"]
+    assert float((np.abs(a["sol"] - tight) / (1e-6 * np.abs(tight) + 1e-9)).max()) <= 0.5
+    assert a["nsteps"].mean() < 0.85 * b["nsteps"].mean()
+
+
+def test_states_beyond_fp32_range_are_flagged(engine):
+    """The ROS6L error scale is evaluated in FP32: a state beyond 3.4e38 must end as status 3 with NaN outputs, never as
+    an accepted step with "zero" error; its neighbours in the batch are unaffected."""
+    rng = np.random.default_rng(4)
+    p = rng.uniform(0.05, 3.0, (8, 10))
+    y0 = np.repeat(rng.uniform(0.1, 1.0, (1, 5)), 8, axis=0)
+    y0[3, 1] = 1e39
+    r = engine.solve_local_batch("distmod", p, y0, 3, T14, want=("sol",))
+    assert r["status"][3] == 3 and np.isnan(r["sol"][3, 1:]).all()
+    ok = np.delete(np.arange(8), 3)
+    assert (r["status"][ok] == 0).all() and np.isfinite(r["sol"][ok]).all()
+
+
 def test_fused_gather_single_rank(engine):
     """pk_local_solve_allgather at world 1: the batch is integrated in pieces, every output equals the one-launch
     result bit for bit and the gathered buffer equals the requested per-sample output."""

@@ -119,3 +119,37 @@ def test_runtime_ros5l_family_matches_design_and_stays_stable():
         assert rel <= 1.5 and (g < 0.3 or rel < 0.7)
     with np.errstate(all="ignore"):
         assert lib.pk_ros5l_coeffs(-1.0, (C.c_double * 6)(), (C.c_double * 6)()) != 0
+
+
+def test_runtime_ros6l_family_matches_design_and_stays_stable():
+    """`rosl_coeffs<7>` (the dense kernel re-derives ROS6L(gamma') for steps that reuse an inverse) through its host export
+    `pk_ros6l_coeffs`: at gamma = 0.205 it reproduces the compiled ROS6L constants; every member the kernel can request
+    (0.205/1.03 .. 0.205*16) has MU[0] = gamma' (L-stable), EPS[0] = 0, an order-5 embedded solution (estimate O(z^6)),
+    order >= 6, and is stable on the negative real axis and in the 60-degree sector."""
+    import ctypes as C
+    from phoskintime_b200 import _lib
+    lib = _lib.load()
+
+    def coeffs(g):
+        mu, eps = (C.c_double * 7)(), (C.c_double * 7)()
+        assert lib.pk_ros6l_coeffs(g, mu, eps) == 0
+        return np.array(mu[:]), np.array(eps[:])
+
+    ref = _parse_methods()["METHOD_ROS6L"]
+    mu0, eps0 = coeffs(0.205)
+    assert np.allclose(mu0, ref["mu"], rtol=1e-9, atol=1e-10) and np.allclose(eps0, ref["eps"], rtol=1e-8, atol=1e-9)
+    x = -np.logspace(-3, 8, 3000)
+    sector = np.logspace(-3, 8, 3000) * np.exp(1j * (np.pi - np.pi / 3))
+    for g in (0.205 / 1.03, 0.21, 0.25, 0.3, 0.41, 0.5, 0.82, 1.0, 1.64, 3.28):
+        mu, eps = coeffs(g)
+        assert mu[0] == g and eps[0] == 0.0
+        z1 = 0.05 / max(1.0, g / 0.3)
+        z2 = 2.0 * z1
+        e1, e2 = abs(_R(mu, g, 4 * z1) - np.exp(4 * z1)), abs(_R(mu, g, 4 * z2) - np.exp(4 * z2))
+        assert np.log2(e2 / e1) > 6.7, (g, np.log2(e2 / e1))                  # local error O(z^7) or better
+        s1 = abs(z1 * sum(e * (1 / (1 - g * z1)) ** (k + 1) for k, e in enumerate(eps)))
+        s2 = abs(z2 * sum(e * (1 / (1 - g * z2)) ** (k + 1) for k, e in enumerate(eps)))
+        assert abs(np.log2(s2 / s1) - 6) < 0.3, (g, np.log2(s2 / s1))
+        assert np.abs(_R(mu, g, x)).max() < 1.0 and abs(_R(mu, g, -1e8)) < 1e-6
+        assert np.abs(_R(mu, g, sector)).max() <= 1.0 + 1e-12
+    assert lib.pk_ros6l_coeffs(-1.0, (C.c_double * 7)(), (C.c_double * 7)()) != 0
