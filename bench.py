@@ -237,7 +237,7 @@ def run_ours(args):
     gathered = torch.empty(world * B, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    gather_chunks = args.gather_chunks if args.gather_chunks >= 0 else (2 if world >= 4 else 0)
+    gather_chunks = args.gather_chunks if args.gather_chunks >= 0 else (2 if world >= 8 else 0)
 
     def step_device():
         # world > 1: the one collective of the path, the all-gather of the per-sample losses.  --gather-chunks K > 0
@@ -389,8 +389,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather-chunks", type=int, default=-1,
                     help="N>1: fuse the all-gather with the solve in this many pieces (0 = one launch + one all-gather; "
-                         "-1 = auto: 2 pieces from 4 GPUs on, where the collective is long enough to be worth a second "
-                         "launch tail — measured 3.50 -> 3.05 ms per step at 8 GPUs, 2.78 -> 2.97 at 2 GPUs with 4 pieces)")
+                         "-1 = auto: 2 pieces at 8 GPUs, where the collective is long enough to be worth a second launch "
+                         "tail — measured 3.50 -> 3.05 ms per step at 8 GPUs, 2.87 -> 2.94 at 4, 2.78 -> 2.97 at 2 (4 pieces))")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
