@@ -474,8 +474,23 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         const size_t W = (size_t)h->world;
         if (ag && W > 1) CK(h->ag_stage.ensure(W * B * sizeof(double)));
         CK(cudaEventRecord(h->ev0, st));
+        // piece boundaries: equal pieces for a plain solve; for the fused gather every piece is half the previous one
+        // (2/3 + 1/3 for two pieces), so that the exposed gather of the LAST piece is short while the earlier, larger
+        // gathers hide behind the following pieces' integration
+        size_t bound[PIPE_MAX_CHUNKS + 1];
+        bound[0] = 0;
+        {
+            const double total = ag ? (double)((1u << nch) - 1u) : (double)nch;
+            double acc = 0.0;
+            for (int c = 0; c < nch; ++c) {
+                acc += ag ? (double)(1u << (nch - 1 - c)) : 1.0;
+                bound[c + 1] = (c + 1 == nch) ? B : std::min(B, (size_t)((double)B * acc / total));
+                if (bound[c + 1] <= bound[c] && bound[c] < B) bound[c + 1] = bound[c] + 1;   // no empty piece
+            }
+        }
         for (int c = 0; c < nch; ++c) {
-            const size_t o = B * (size_t)c / nch, cnt = B * (size_t)(c + 1) / nch - o;
+            const size_t o = bound[c], cnt = bound[c + 1] - bound[c];
+            if (cnt == 0) continue;
             pk::LocalArgs ac = a;
             ac.B = (long long)cnt;
             ac.params += o * P;

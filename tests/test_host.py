@@ -40,6 +40,19 @@ def test_abi_version_and_struct_layout():
     assert job.y_metric == -1 and job.n_groups == 1 and list(job.score_w) == [1.0] * 5
 
 
+def test_nlls_job_defaults_and_layout():
+    """pk_nlls_job_init: curve_fit's default tolerances (ftol = xtol = gtol = 1e-8), the struct mirrors the header."""
+    import ctypes as C
+    lib = _lib.load()
+    assert lib.pk_sizeof_nlls_job() == C.sizeof(_lib.PkNllsJob)
+    job = _lib.PkNllsJob()
+    lib.pk_nlls_job_init(C.byref(job))
+    assert (job.ftol, job.xtol, job.gtol) == (1e-8, 1e-8, 1e-8) and job.max_iter == 100 and job.n_groups == 1
+    assert job.fd_rel == 1e-4 and job.rtol == 2e-7 and job.atol == 2e-10 and list(job.score_w) == [1.0] * 5
+    # (the defaults written by the C side land in the right ctypes fields: offsets agree, not just the size)
+    assert job.mu0 == 0.0 and job.lam == 0.0 and job.max_steps == 0 and job.method == 0 and job.log_params == 0
+
+
 def test_local_dims_follow_reference_layout():
     assert pk.local_dims("distmod", 3, 14) == (5, 10, 65)      # L = 9 + 14 + 3*14
     assert pk.local_dims("distmod", 4, 14) == (6, 12, 79)
