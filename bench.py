@@ -390,7 +390,7 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=-1,
                     help="N>1: fuse the all-gather with the solve in this many pieces (0 = one launch + one all-gather; "
                          "-1 = auto: 2 pieces at 8 GPUs, where the collective is long enough to be worth a second launch "
-                         "tail — measured 3.50 -> 3.05 ms per step at 8 GPUs, 2.87 -> 2.94 at 4, 2.78 -> 2.97 at 2 (4 pieces))")
+                         "tail — measured 3.50 -> 2.97 ms per step at 8 GPUs (pieces of 2/3 + 1/3), 2.87 -> 2.94 at 4, 2.78 -> 2.97 at 2 (4 pieces))")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
