@@ -326,6 +326,25 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_single(args.cpu_sample)
+        # "rel err vs ref" of the metric (part of the CPU leg: the oracle is the checker): the first 512 parameter sets of
+        # the workload, GPU trajectories at the library defaults vs the oracle's exact solution (matrix exponential) and
+        # vs the stock reference path (LSODA defaults), in units of the parity bound 1e-6*|ref| + 1e-9
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import local_models as om
+        nchk = 512
+        pchk = params_h.numpy()[:nchk]
+        got = eng.solve_local_batch(MODEL, pchk, y0, NS, T_GRID, want=("sol",))["sol"]
+        worst_exact, worst_stock, rel_max = 0.0, 0.0, 0.0
+        for b in range(nchk):
+            ex = om.exact_linear(MODEL, pchk[b], y0, NS, T_GRID)
+            worst_exact = max(worst_exact, float((np.abs(got[b] - ex) / (1e-6 * np.abs(ex) + 1e-9)).max()))
+            rel_max = max(rel_max, float((np.abs(got[b] - ex) / np.maximum(np.abs(ex), 1e-12)).max()))
+            if b < 64:
+                st = om.solve_ode(MODEL, pchk[b], y0, NS, T_GRID)[0]
+                worst_stock = max(worst_stock, float((np.abs(got[b] - st) / (1e-6 * np.abs(st) + 1e-7)).max()))
+        cpu["parity"] = {"systems": nchk, "max_err_over_bound_vs_exact": worst_exact, "max_rel_err_vs_exact": rel_max,
+                         "max_err_over_mixed_bound_vs_stock_reference": worst_stock,
+                         "bounds": "1e-6*|ref|+1e-9 (exact), 1e-6*|ref|+1e-7 (stock LSODA path, 64 systems)"}
 
     if rank == 0:
         line = {
