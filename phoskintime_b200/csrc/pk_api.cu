@@ -556,8 +556,12 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     WS(nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
     WS(nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
 #undef WS
-    // (8 chunks measured slower than 4 at 1 M systems: 6.6 vs 6.2 ms — every chunk is a launch with its own tail)
-    const int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 4 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
+    // Large batches: 5 chunks, each 1.2x the previous one — the first upload (nothing to hide behind) is short and every
+    // later upload still fits under the previous chunk's kernel.  Measured at 1 M succ-5 systems (tools/e2e_pipe_scan.py):
+    // 4 equal chunks 3.46 ms, 5 equal 3.36, 4 x1.4 3.30, 5 x1.2 3.30, 6 x1.2 3.30, 3 x1.3 3.47 (every chunk is a launch
+    // with its own tail).
+    const int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 5 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
+    const double growth = nchunks == 5 ? 1.2 : 1.0;
     cudaStream_t sin = h->s_in, sout = h->s_out;
     // small shared inputs first, then the per-system inputs chunk by chunk on the copy-in stream
     CK(cudaMemcpyAsync((void*)a.t, j->t, (size_t)j->T * sizeof(double), cudaMemcpyHostToDevice, sin));
@@ -569,7 +573,17 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
                                cudaMemcpyHostToDevice, sin));
     }
     size_t lo[PIPE_MAX_CHUNKS + 1];
-    for (int c = 0; c <= nchunks; ++c) lo[c] = B * (size_t)c / nchunks;
+    {
+        double total = 0.0, w = 1.0, acc = 0.0;
+        for (int c = 0; c < nchunks; ++c) { total += w; w *= growth; }
+        w = 1.0;
+        lo[0] = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            acc += w;
+            w *= growth;
+            lo[c + 1] = (c + 1 == nchunks) ? B : std::min(B, (size_t)((double)B * acc / total));
+        }
+    }
     for (int c = 0; c < nchunks; ++c) {
         const size_t o = lo[c], cnt = lo[c + 1] - lo[c];
         CK(cudaMemcpyAsync((double*)a.params + o * P, j->params + o * P, cnt * P * sizeof(double),

@@ -234,7 +234,7 @@ def test_host_and_device_paths_agree_and_are_deterministic(engine):
 
 
 def test_pipelined_host_path_equals_device_path(engine):
-    """Host batches >= 400k systems are staged in 4 chunks (H2D / kernel / D2H overlapped on three
+    """Host batches >= 400k systems are staged in 5 chunks of growing size (H2D / kernel / D2H overlapped on three
     streams); every output slice, per-system y0 and the group index must land where the one-launch
     device path puts them."""
     import torch
