@@ -1,4 +1,5 @@
-"""Dev script (GPU box): end-to-end (host buffers) time of the bench workload for the current pipeline settings."""
+"""Dev script (GPU box): end-to-end (host buffers) time of the bench workload for the library's host pipeline (the chunk
+count / growth scan recorded in pk_api.cu was run with temporary environment knobs that have since been removed)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,4 +19,4 @@ for _ in range(3): f()
 ts = []
 for _ in range(10):
     t0 = time.perf_counter(); f(); ts.append(time.perf_counter() - t0)
-print(f"chunks {os.environ.get('PK_DEV_PIPE_CHUNKS')} growth {os.environ.get('PK_DEV_PIPE_GROWTH')}: e2e {np.mean(ts) * 1e3:.3f} ms (min {np.min(ts) * 1e3:.3f}) -> {B / np.mean(ts):.4g} solves/s")
+print(f"e2e {np.mean(ts) * 1e3:.3f} ms (min {np.min(ts) * 1e3:.3f}) -> {B / np.mean(ts):.4g} solves/s")
