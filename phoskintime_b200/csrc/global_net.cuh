@@ -75,7 +75,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int colbuf, rowbuf, bp, partial;  // TILE  > 0: Schur matrix in registers (Gauss-Jordan), exchange buffers
     int tfdata, tfdeg;                // staged topology (doubles)
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
-    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff;
+    int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff, i_cord;
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
 };
 
@@ -333,6 +333,8 @@ struct GlobalCtx {
     // model 2: this CTA's block-inverse scratch (global memory, L2 resident) and each protein's offset into it
     double* binv;
     const int* boff;
+    const int* cord;                  // proteins ordered by block size (descending): the two blocks a warp inverts together
+                                      // are of (nearly) equal size, so neither half-warp idles through the other's columns
 };
 
 
@@ -370,8 +372,8 @@ __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
     const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int N = cx.N;
     for (int i0 = 0; i0 < N; i0 += 16) {
-        const int i = i0 + grp;
-        const bool act = i < N;
+        const bool act = i0 + grp < N;
+        const int i = act ? cx.cord[i0 + grp] : 0;
         const int ns = act ? cx.ns[i] : 0, st = act ? cx.offy[i] : 0, ss = act ? cx.offs[i] : 0;
         const int nst = act ? (1 << ns) : 0;
         const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));     // the two halves of a warp step together
@@ -433,8 +435,8 @@ __device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x)
     const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int N = cx.N;
     for (int i0 = 0; i0 < N; i0 += 16) {
-        const int i = i0 + grp;
-        const bool act = i < N;
+        const bool act = i0 + grp < N;
+        const int i = act ? cx.cord[i0 + grp] : 0;
         const int st = act ? cx.offy[i] : 0;
         const int nst = act ? (1 << cx.ns[i]) : 0;
         const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));
@@ -976,7 +978,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                  ismem + L.i_qlist, ismem + L.i_qpos, ismem + L.i_sprot, (const unsigned char*)(ismem + L.i_ent),
                  smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
-                 a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff};
+                 a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord};
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
     cx.cC = cx.cB + N;
@@ -1015,6 +1017,10 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
             if (tp.model == 2)
                 for (int k = 0; k < i; ++k) bo += 1 << (2 * tp.n_sites[k]);
             ismem[L.i_boff + i] = bo;
+            // position of protein i in the order "larger blocks first" (stable): counting rank
+            int rank = 0;
+            for (int k = 0; k < N; ++k) rank += (tp.n_sites[k] > ns) || (tp.n_sites[k] == ns && k < i);
+            ismem[L.i_cord + rank] = i;
         }
         if constexpr (TILE > 0) {
             // static sparsity of the Schur block as seen by this thread's tile (see gj_assemble); rows of the uploaded

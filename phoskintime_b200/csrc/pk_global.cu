@@ -133,6 +133,7 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     L.i_sprot = itake(n);
     L.i_ent = itake(L.tile * L.tile * pk::GLOBAL_BLOCK / 4);    // one byte per tile slot and thread
     L.i_boff = itake(N);
+    L.i_cord = itake(N);
     o += (io + 1) / 2;
     L.total = o;
     th->smem_bytes = (size_t)o * sizeof(double);
