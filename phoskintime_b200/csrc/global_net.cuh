@@ -96,7 +96,8 @@ struct GlobalArgs {
     const int *mt_prot, *mt_rna, *mt_pho;
     double lam[3], lam_prior;
     double *out_Y, *out_loss, *out_F, *out_metric;
-    double* out_fc;                   // [B][n_fc] fold-change table (simulate.py:105-182) or nullptr
+    double* out_fc;                   // [B][nfc] fold-change table (simulate.py:105-182) or nullptr
+    long long nfc;
     int *out_status, *out_nsteps, *out_nrej;
     double* traj;                     // [grid][T][n] scratch when out_Y is not requested
     double* binv;                     // [grid][binv_stride] model 2: inverses of the per-protein pattern blocks
@@ -234,12 +235,15 @@ __device__ __forceinline__ void loss_sums(const GlobalTopoDev& tp, const double*
 
 // Morris scalar of the global path: fold changes (floor 1e-12) of every protein / mRNA / site at the
 // requested time indices (simulate.py:105-182) reduced as sensitivity.py:106-140.
+// (the output row is re-derived at every store from the constant-bank base pointer and the system index in shared memory:
+//  no 64-bit pointer stays live through the three loops — the TILE = 6 kernel sits at its 128-register cap)
 // fc (optional): the fold changes themselves, [N*n_mt_prot | N*n_mt_rna | total_sites*n_mt_pho] — protein-major, then
 // (site,) time, the row order of simulate_and_measure's three tables after its time filter (simulate.py:184-200).
 __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const double* traj, int n, int metric,
                                                int n_mt_prot, int n_mt_rna, int n_mt_pho, const int* mt_prot,
                                                const int* mt_rna, const int* mt_pho, int mb_prot, int mb_rna, int mb_pho,
-                                               double* red, double* fc_out = nullptr) {
+                                               double* red, double* fc_base = nullptr, long long nfc = 0,
+                                               const long long* sys_ptr = nullptr) {
     const int N = tp.N;
     const bool comb = tp.model == 2;          // simulate.py:135-158
     double s1 = 0.0, s2 = 0.0;
@@ -253,7 +257,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
         const int cnt = comb ? (1 << ns) : ns + 1;
         for (int j = 0; j < cnt; ++j) { a1 += rt[j]; b1 += rb[j]; }
         const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
-        if (fc_out) fc_out[k] = fc;
+        if (fc_base) fc_base[*sys_ptr * nfc + k] = fc;
         s1 += fc;
         s2 = fma(fc, fc, s2);
     }
@@ -261,7 +265,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
         const int i = k / n_mt_rna, ti = mt_rna[k - i * n_mt_rna];
         const int st = tp.offset_y[i];
         const double fc = fmax(traj[(size_t)ti * n + st], 1e-12) / fmax(traj[(size_t)mb_rna * n + st], 1e-12);
-        if (fc_out) fc_out[np_ + k] = fc;
+        if (fc_base) fc_base[*sys_ptr * nfc + np_ + k] = fc;
         s1 += fc;
         s2 = fma(fc, fc, s2);
     }
@@ -282,7 +286,7 @@ __device__ __forceinline__ double metric_value(const GlobalTopoDev& tp, const do
                     b1 = traj[(size_t)mb_pho * n + st + 2 + j];
                 }
                 const double fc = fmax(a1, 1e-12) / fmax(b1, 1e-12);
-                if (fc_out) fc_out[np_ + nr_ + tp.offset_s[i] * n_mt_pho + k] = fc;
+                if (fc_base) fc_base[*sys_ptr * nfc + np_ + nr_ + tp.offset_s[i] * n_mt_pho + k] = fc;
                 s1 += fc;
                 s2 = fma(fc, fc, s2);
             }
@@ -1013,14 +1017,15 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
             const int st = tp.offset_y[i], ns = tp.n_sites[i];
             const int bl = tp.model == 2 ? 1 + (1 << ns) : 2 + ns;
             for (int j = 0; j < bl; ++j) ismem[L.i_sprot + st + j] = i;
-            int bo = 0;                                                // model 2: offset of the block inverse (4^ns each)
-            if (tp.model == 2)
+            if constexpr (COMB) {
+                int bo = 0;                                            // offset of the block inverse (4^ns each)
                 for (int k = 0; k < i; ++k) bo += 1 << (2 * tp.n_sites[k]);
-            ismem[L.i_boff + i] = bo;
-            // position of protein i in the order "larger blocks first" (stable): counting rank
-            int rank = 0;
-            for (int k = 0; k < N; ++k) rank += (tp.n_sites[k] > ns) || (tp.n_sites[k] == ns && k < i);
-            ismem[L.i_cord + rank] = i;
+                ismem[L.i_boff + i] = bo;
+                // position of protein i in the order "larger blocks first" (stable): counting rank
+                int rank = 0;
+                for (int k = 0; k < N; ++k) rank += (tp.n_sites[k] > ns) || (tp.n_sites[k] == ns && k < i);
+                ismem[L.i_cord + rank] = i;
+            }
         }
         if constexpr (TILE > 0) {
             // static sparsity of the Schur block as seen by this thread's tile (see gj_assemble); rows of the uploaded
@@ -1297,10 +1302,8 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
             }
         }
         if (a.out_metric || a.out_fc) {
-            const size_t nfc = (size_t)N * (a.n_mt_prot + a.n_mt_rna) + (size_t)S * a.n_mt_pho;
             const double mv = metric_value(tp, traj, n, a.metric, a.n_mt_prot, a.n_mt_rna, a.n_mt_pho, a.mt_prot, a.mt_rna,
-                                           a.mt_pho, a.mb_prot, a.mb_rna, a.mb_pho, cx.red,
-                                           a.out_fc ? a.out_fc + (size_t)sys * nfc : nullptr);
+                                           a.mt_pho, a.mb_prot, a.mb_rna, a.mb_pho, cx.red, a.out_fc, a.nfc, &s_sys);
             if (threadIdx.x == 0 && a.out_metric) a.out_metric[sys] = mv;
         }
     }

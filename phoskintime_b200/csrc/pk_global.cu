@@ -481,6 +481,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     for (int m = 0; m < 3; ++m) a.lam[m] = j->lambdas[m];
     a.lam_prior = j->lambda_prior;
     a.y0_stride = j->y0_stride;
+    a.nfc = (long long)nfc;
     a.counter = h->counter;
 
     const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile, d.model == 2);
