@@ -5,16 +5,18 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 CSRC := phoskintime_b200/csrc
 OBJD := build
 LIB  := phoskintime_b200/libphoskin_b200.so
-UNITS := pk_api pk_global pk_nlls
+UNITS := pk_api pk_tps_dist pk_tps_succ pk_dense pk_global pk_nlls
 OBJS := $(UNITS:%=$(OBJD)/%.o)
 HDRS := $(wildcard $(CSRC)/*.cuh) $(CSRC)/pk_internal.hpp include/phoskin_b200.h
 FLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xptxas -v -Xcompiler -fPIC
-MAKEFLAGS += -j4
+MAKEFLAGS += -j8
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -Xcompiler -fPIC -o $@ $(OBJS) -ldl
 	@cat $(UNITS:%=$(OBJD)/%.ptxas.log) > $(CSRC)/ptxas.log
-	@grep -c "0 bytes spill stores" $(CSRC)/ptxas.log >/dev/null
+	@# zero local memory in EVERY kernel: no spill and no stack frame (a register array indexed at run time would show up here)
+	@if grep -En '[1-9][0-9]* bytes (stack frame|spill stores|spill loads)' $(CSRC)/ptxas.log; then \
+		echo "local memory in a kernel (see the lines above; $(CSRC)/ptxas.log)"; rm -f $@; exit 1; fi
 
 $(OBJD)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJD)

@@ -1,28 +1,39 @@
-// Thread-per-system RODAS4 kernel for the small local models (distributive, successive).
+// Thread-per-system Rosenbrock kernel for the small local models (distributive, successive).
 //
 // One lane integrates one system with its whole working set (y, the Krylov vector v, y_new, err
 // and the factorised I - h*gamma*M) in registers; the Jacobian structure is exploited analytically:
 //   distributive (models/distmod.py:57-63): arrow matrix  -> Schur pivot on the protein row
-//   successive   (models/succmod.py:33-90): tridiagonal in (P, site_1..site_ns) -> Thomas, with the
-//                pivots obtained from the continuant recurrence so that they are independent
+//   successive   (models/succmod.py:33-90): tridiagonal in (P, site_1..site_ns) -> TWISTED factorisation: eliminated
+//                from both ends towards a middle row and substituted back outwards, so that every solve carries two
+//                independent dependency chains of half the length (the kernel is bound by DFMA latency, not by the
+//                FP64 pipe); the pivots come from the two continuant recurrences, so they are independent too
 // mRNA (row 0) is decoupled in both and eliminated first.  All reciprocals of one factorisation come
-// from ONE FP64 division (batch inversion by prefix products); the error ratio and the step-size
-// controller run in FP32.  Lanes pull systems from a global queue (warp-aggregated atomicAdd) as they finish, so a
-// warp never idles on its slowest member.  The epilogue (clip, flat layout, weighted residual /
-// score_fit, Morris Y) is fused and runs warp-cooperatively when a system completes.
+// from ONE reciprocal (batch inversion by prefix products; MUFU seed + two Newton steps); the error ratio and the
+// step-size controller run in FP32.
+// Work distribution: every warp claims batches of up to 32 consecutive systems with ONE atomicAdd and prefetches their
+// parameter rows into a double-buffered shared-memory stash with cp.async while its lanes are still integrating; a lane
+// that finishes takes the next system from the stash (no global atomic, no exposed HBM latency).  Near the end of the
+// queue the batches shrink (guided self-scheduling) so that no warp sits on a long private tail.
+// Outputs: two instantiations per model.
+//   SCALAR   only per-system scalars are requested (ssr / score_fit / Morris Y): the lane accumulates the weighted
+//            residual sums in registers at the moment it lands on an output time; finished systems are parked in a
+//            per-warp shared-memory ring and up to 32 of them at a time are finished (t = 0 terms, square roots,
+//            divisions, stores) by 32 lanes in lock-step.  No trajectory ever leaves the registers.
+//   !SCALAR  sol / flat rows requested: the lane stores its raw state into a private L2-resident trajectory slot and
+//            the whole warp runs the epilogue of a finished system (coalesced rows, shuffle reductions).
 #pragma once
 #include "pk_common.cuh"
 
 namespace pk {
 
-// a[i] <- 1/a[i] for i < M with one division (Montgomery's trick).
+// a[i] <- 1/a[i] for i < M with one reciprocal (Montgomery's trick).
 template <int M>
 __device__ __forceinline__ void batch_invert(double (&a)[M]) {
     double pre[M];
     pre[0] = a[0];
 #pragma unroll
     for (int i = 1; i < M; ++i) pre[i] = pre[i - 1] * a[i];
-    double inv = 1.0 / pre[M - 1];
+    double inv = fast_rcp(pre[M - 1]);
 #pragma unroll
     for (int i = M - 1; i > 0; --i) {
         double ai = a[i];
@@ -38,6 +49,7 @@ __device__ __forceinline__ void batch_invert(double (&a)[M]) {
 template <int NS_>
 struct DistModel {
     static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4;
+    // FLOPs (FMA = 2) of factor / rhs / one solve as written below — bench.py::flops_per_step mirrors these
     double A, Bm, C, kP, S[NS], k[NS];
     __device__ __forceinline__ void load(const double* p) {
         A = p[0]; Bm = p[1]; C = p[2];
@@ -84,10 +96,13 @@ struct DistModel {
     }
     __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
         x[0] *= F[0];
-        double sz = 0.0;
+        double sz0 = 0.0, sz1 = 0.0;                        // two partial sums: half the dependent chain
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { x[2 + i] *= F[4 + i]; sz += x[2 + i]; }
-        x[1] = fma(F[3], sz, fma(F[2], x[0], x[1])) * F[1];
+        for (int i = 0; i < NS; ++i) {
+            x[2 + i] *= F[4 + i];
+            if (i & 1) sz1 += x[2 + i]; else sz0 += x[2 + i];
+        }
+        x[1] = fma(F[3], sz0 + sz1, fma(F[2], x[0], x[1])) * F[1];
 #pragma unroll
         for (int i = 0; i < NS; ++i) x[2 + i] = fma(F[4 + NS + i], x[1], x[2 + i]);
     }
@@ -95,7 +110,14 @@ struct DistModel {
 
 template <int NS_>
 struct SuccModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4;
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_;
+    // Twisted factorisation of the tridiagonal block over the unknowns j = 0..NS (x[1+j]): rows 0..MID-1 are eliminated
+    // downwards, rows NS..MID+1 upwards, the middle row MID last; back substitution runs outwards from MID.
+    static constexpr int MID = (NS + 1) / 2, NT = MID, NB = NS - MID;
+    // F = [1/q0, cC, c, 1/d_MID, 1/p_j (NT), lt_j = c S_j / p_j (NT: row j into row j+1),
+    //      1/q_j (NB: j = MID+1..NS), lb_j = c / q_j (NB: row j into row j-1), c S_{j-1} (NB: back substitution downwards)]
+    static constexpr int NF = 4 + 2 * NT + 3 * NB;
+    static constexpr int O_IP = 4, O_LT = 4 + NT, O_IQ = 4 + 2 * NT, O_LB = 4 + 2 * NT + NB, O_CS = 4 + 2 * NT + 2 * NB;
     // d[0] = D + S_0 (protein), d[1+i] = 1 + Dr_i + S_{i+1} (site i; no S term for the last site)
     double A, Bm, C, S[NS], d[NS + 1];
     __device__ __forceinline__ void load(const double* p) {
@@ -116,47 +138,99 @@ struct SuccModel {
             f[2 + i] = v;
         }
     }
-    // Tridiagonal block over x_1..x_{1+NS}: diag a_j = 1 + c d_j, sub -c S_{j-1}, super -c.
-    // Continuants theta_j = a_j theta_{j-1} - (c S_{j-1}) c theta_{j-2} give the Thomas pivots
-    // p_j = theta_j / theta_{j-1} without a sequential chain of divisions (no pivoting needed: the
-    // block is strictly column diagonally dominant for non-negative rates).
-    // F = [1/q0, cC, 1/p_j (NS+1), l_j = c S_{j-1}/p_{j-1} (NS), c]
+    // Tridiagonal block: diag a_j = 1 + c d_j, sub (row j, col j-1) -c S_{j-1}, super -c.  No pivoting is needed: for
+    // non-negative rates the block is strictly column diagonally dominant.
+    //   top continuants    th_j = a_j th_{j-1} - (c S_{j-1}) c th_{j-2}   (th_{-1} = 1)      p_j = th_j / th_{j-1}
+    //   bottom continuants ph_j = a_j ph_{j+1} - (c S_j) c ph_{j+2}       (ph_{NS+1} = 1)    q_j = ph_j / ph_{j+1}
+    //   middle pivot       d_M  = Delta / (th_{M-1} ph_{M+1}),
+    //                      Delta = a_M th_{M-1} ph_{M+1} - c^2 S_{M-1} th_{M-2} ph_{M+1} - c^2 S_M th_{M-1} ph_{M+2}
+    // One reciprocal for all of {q0, th_0..th_{M-1}, ph_{M+1}..ph_NS, Delta} (NS + 2 numbers).
     __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
-        double th[NS + 2];                       // th[0] = q0, th[1+j] = theta_j
-        th[0] = fma(c, Bm, 1.0);
-        th[1] = fma(c, d[0], 1.0);
-        double cs[NS];
+        double cs[NS], cc[NS];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) cs[j] = c * S[j];
-        th[2] = fma(fma(c, d[1], 1.0), th[1], -(cs[0] * c));
+        for (int j = 0; j < NS; ++j) { cs[j] = c * S[j]; cc[j] = cs[j] * c; }
+        double th[NT];
+        th[0] = fma(c, d[0], 1.0);
+        if constexpr (NT > 1) th[1] = fma(fma(c, d[1], 1.0), th[0], -cc[0]);
 #pragma unroll
-        for (int j = 2; j <= NS; ++j) th[1 + j] = fma(fma(c, d[j], 1.0), th[j], -(cs[j - 1] * c) * th[j - 1]);
+        for (int j = 2; j < NT; ++j) th[j] = fma(fma(c, d[j], 1.0), th[j - 1], -(cc[j - 1] * th[j - 2]));
+        double ph[NB + 1];                                   // ph[k] = ph_{MID+1+k}; ph[NB] = 1
+        ph[NB] = 1.0;
+        if constexpr (NB > 0) ph[NB - 1] = fma(c, d[NS], 1.0);
+        if constexpr (NB > 1) ph[NB - 2] = fma(fma(c, d[NS - 1], 1.0), ph[NB - 1], -cc[NS - 1]);
+#pragma unroll
+        for (int k = NB - 3; k >= 0; --k) ph[k] = fma(fma(c, d[MID + 1 + k], 1.0), ph[k + 1], -(cc[MID + 1 + k] * ph[k + 2]));
+        const double thm2 = (NT > 1) ? th[NT > 1 ? NT - 2 : 0] : 1.0;      // th_{M-2}
+        const double tp = th[NT - 1] * ph[0];                              // th_{M-1} ph_{M+1}
+        double delta = fma(fma(c, d[MID], 1.0), tp, -(cc[MID - 1] * thm2) * ph[0]);
+        if constexpr (NB > 0) delta = fma(-(cc[MID < NS ? MID : 0] * th[NT - 1]), ph[1], delta);
         double inv[NS + 2];
+        inv[0] = fma(c, Bm, 1.0);
 #pragma unroll
-        for (int j = 0; j < NS + 2; ++j) inv[j] = th[j];
+        for (int j = 0; j < NT; ++j) inv[1 + j] = th[j];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) inv[1 + NT + k] = ph[k];
+        inv[NS + 1] = delta;
         batch_invert<NS + 2>(inv);
         F[0] = inv[0];
         F[1] = c * C;
-        F[2] = inv[1];                                          // 1/p_0 = 1/theta_0
+        F[2] = c;
+        F[3] = tp * inv[NS + 1];
+        F[O_IP] = inv[1];
 #pragma unroll
-        for (int j = 1; j <= NS; ++j) F[2 + j] = th[j] * inv[1 + j];   // theta_{j-1} / theta_j
+        for (int j = 1; j < NT; ++j) F[O_IP + j] = th[j - 1] * inv[1 + j];
 #pragma unroll
-        for (int j = 1; j <= NS; ++j) F[2 + NS + j] = cs[j - 1] * F[1 + j];       // l_j
-        F[3 + 2 * NS] = c;
+        for (int j = 0; j < NT; ++j) F[O_LT + j] = cs[j] * F[O_IP + j];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            F[O_IQ + k] = ph[k + 1] * inv[1 + NT + k];
+            F[O_LB + k] = c * F[O_IQ + k];
+            F[O_CS + k] = cs[MID + k];
+        }
     }
     __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
         x[0] *= F[0];
         x[1] = fma(F[1], x[0], x[1]);
 #pragma unroll
-        for (int j = 1; j <= NS; ++j) x[1 + j] = fma(F[2 + NS + j], x[j], x[1 + j]);        // forward
-        x[1 + NS] *= F[2 + NS];
+        for (int j = 1; j < NT; ++j) x[1 + j] = fma(F[O_LT + j - 1], x[j], x[1 + j]);                       // downwards
 #pragma unroll
-        for (int j = NS - 1; j >= 0; --j) x[1 + j] = fma(F[3 + 2 * NS], x[2 + j], x[1 + j]) * F[2 + j];   // (x_j + c x_{j+1}) / p_j
+        for (int j = NS - 1; j > MID; --j) x[1 + j] = fma(F[O_LB + j - MID], x[2 + j], x[1 + j]);            // upwards
+        double xm = fma(F[O_LT + NT - 1], x[MID], x[1 + MID]);
+        if constexpr (NB > 0) xm = fma(F[O_LB], x[2 + MID], xm);
+        x[1 + MID] = xm * F[3];
+#pragma unroll
+        for (int j = MID - 1; j >= 0; --j) x[1 + j] = fma(F[2], x[2 + j], x[1 + j]) * F[O_IP + j];           // back, upwards
+#pragma unroll
+        for (int j = MID + 1; j <= NS; ++j) x[1 + j] = fma(F[O_CS + j - MID - 1], x[j], x[1 + j]) * F[O_IQ + j - MID - 1];
     }
 };
 
 // ------------------------------------------------------------------------------------ kernel
 constexpr int TPS_BLOCK = 128;
+constexpr int TPS_WARPS = TPS_BLOCK / 32;
+constexpr int TPS_STASH = 32;          // systems per claimed batch (upper bound)
+constexpr int TPS_RING = 32;           // finished systems parked per warp before they are written out
+
+// dynamic shared memory of one CTA (bytes); the host side mirrors this (launch_tps)
+__host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool scalar) {
+    size_t b = (size_t)TPS_WARPS * 2 * TPS_STASH * P * 8;        // parameter stash
+    b += (size_t)TPS_BLOCK * 16;                                 // per-lane system index and |params|^2
+    b += (size_t)TPS_WARPS * 48;                                 // per-warp queue state (TpsQueue)
+    if (scalar) b += (size_t)TPS_WARPS * TPS_RING * (4 * 8 + 8 + 16);
+    b += (size_t)T * 8;
+    if (!scalar) b += ((size_t)L * 2 + 7) & ~(size_t)7;
+    return b;
+}
+
+// Work-queue state of one warp that is only touched when a batch is claimed or swapped in: kept in shared memory (every
+// lane writes the same value) so that it does not occupy registers across the step body.
+struct TpsQueue {
+    long long cur_base, nxt_base, head_seen;
+    unsigned long long pend;      // result of the claim in flight (lane 0's atomicAdd)
+    int nxt_cnt, pend_want;
+    int pad[2];
+};
+static_assert(sizeof(TpsQueue) == 48, "tps_smem_bytes reserves 48 bytes per warp");
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -164,100 +238,256 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// Step loop: every lane owns one system.  A lane that lands on an output time only stores its raw
-// state (N doubles) into its private trajectory slot `traj` (one [T][N] slot per resident lane,
-// ~45 MB in total, L2-resident and reused for every system the lane integrates).  When a lane has
-// produced its last output the WHOLE WARP runs the epilogue for it: 32 lanes walk the T*N stored
-// values coalesced, clip / normalise, write sol and flat rows coalesced, and reduce the weighted
-// residual, score_fit and Morris-Y sums with shuffles.  The divergent part of the loop is thus a
-// handful of stores; the expensive epilogue runs at full warp width once per system.
-template <class M, int MIN_BLOCKS>
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <class M, int MIN_BLOCKS, bool SCALAR>
 __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
     constexpr int N = M::N, NF = M::NF, P = M::P;
-    extern __shared__ double smem[];
-    double* tgrid = smem;                                     // [T]
-    short* fmap = (short*)(smem + a.T);                       // [L]: trajectory index (k*N + i) of every flat entry
-    for (int i = threadIdx.x; i < a.T; i += TPS_BLOCK) tgrid[i] = a.t[i];
-    {
-        const int rl = a.T > RNA_OFFSET ? a.T - RNA_OFFSET : 0;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int T = a.T;
+    const int TN = T * N;
+    const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
+
+    // ---- shared-memory carve-up (tps_smem_bytes)
+    unsigned char* sp = smem_raw;
+    double* const stash = (double*)sp + (size_t)wid * 2 * TPS_STASH * P;          // [2][TPS_STASH][P] of this warp
+    sp += (size_t)TPS_WARPS * 2 * TPS_STASH * P * 8;
+    long long* const lane_sys = (long long*)sp;  sp += TPS_BLOCK * 8;             // system index of every lane
+    double* const lane_p2 = (double*)sp;         sp += TPS_BLOCK * 8;             // |physical params|^2 (score_fit's l2 term)
+    volatile TpsQueue* const q = (volatile TpsQueue*)sp + wid;  sp += TPS_WARPS * sizeof(TpsQueue);
+    double* ring_v = nullptr;                    // [TPS_RING][4]: ssr, sum |r|, sum r^2, |params|^2
+    long long* ring_sys = nullptr;
+    int* ring_i = nullptr;                       // [TPS_RING][4]: status, accepted, rejected, -
+    if constexpr (SCALAR) {
+        ring_v = (double*)sp + (size_t)wid * TPS_RING * 4;       sp += (size_t)TPS_WARPS * TPS_RING * 32;
+        ring_sys = (long long*)sp + (size_t)wid * TPS_RING;      sp += (size_t)TPS_WARPS * TPS_RING * 8;
+        ring_i = (int*)sp + (size_t)wid * TPS_RING * 4;          sp += (size_t)TPS_WARPS * TPS_RING * 16;
+    }
+    double* const tgrid = (double*)sp;           sp += (size_t)T * 8;
+    short* const fmap = (short*)sp;              // !SCALAR: trajectory index (k*N + i) of every flat entry
+    for (int i = threadIdx.x; i < T; i += TPS_BLOCK) tgrid[i] = a.t[i];
+    if constexpr (!SCALAR) {
         for (int fi = threadIdx.x; fi < a.L; fi += TPS_BLOCK) {
             int k, i;
-            if (fi < rl) { k = fi + RNA_OFFSET; i = 0; }
-            else if (fi < rl + a.T) { k = fi - rl; i = 1; }
-            else { const int j = fi - rl - a.T; i = 2 + j / a.T; k = j - (i - 2) * a.T; }
+            if (fi < rna_len) { k = fi + RNA_OFFSET; i = 0; }
+            else if (fi < rna_len + T) { k = fi - rna_len; i = 1; }
+            else { const int j = fi - rna_len - T; i = 2 + j / T; k = j - (i - 2) * T; }
             fmap[fi] = (short)(k * N + i);
         }
     }
     __syncthreads();
 
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int T = a.T;
-    const int TN = T * N;
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
-    const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
-    double* const warp_traj = a.traj + ((size_t)blockIdx.x * TPS_BLOCK + (threadIdx.x & ~31)) * TN;
-    double* const my_traj = warp_traj + (size_t)lane * TN;
+    double* warp_traj = nullptr;
+    double* my_traj = nullptr;
+    if constexpr (!SCALAR) {
+        warp_traj = a.traj + ((size_t)blockIdx.x * TPS_BLOCK + (threadIdx.x & ~31)) * TN;
+        my_traj = warp_traj + (size_t)lane * TN;
+    }
 
+    // ---- work queue state of the warp (uniform across its lanes; the rarely touched part lives in *q)
+    int cur_cnt = 0, cur_taken = 0, pb = 0;
+    int pf = 0;                               // 0 idle, 1 claim in flight, 2 copies in flight, 3 queue drained
+    const bool al16 = ((reinterpret_cast<unsigned long long>(a.params) & 15ull) == 0);
+    int nfin = 0;                             // SCALAR: parked finished systems
+    if (lane == 0) { q->cur_base = 0; q->nxt_base = 0; q->head_seen = 0; q->pend = 0; q->nxt_cnt = 0; q->pend_want = 0; }
+    __syncwarp();
+
+    // claim in flight -> copies in flight (pf 1 -> 2), or queue drained (pf 1 -> 3)
+    auto consume_claim = [&]() {
+        const long long b = (long long)q->pend;
+        const long long c = min((long long)q->pend_want, a.B - b);
+        __syncwarp();
+        if (c <= 0) pf = 3;
+        else {
+            if (lane == 0) { q->nxt_base = b; q->nxt_cnt = (int)c; q->head_seen = b + c; }
+            double* dst = stash + (size_t)(pb ^ 1) * TPS_STASH * P;
+            const double* src = a.params + (size_t)b * P;
+            if (al16) { for (int e = lane; e < (int)c * (P / 2); e += 32) cp_async16(dst + 2 * e, src + 2 * e); }
+            else { for (int e = lane; e < (int)c * P; e += 32) cp_async8(dst + e, src + e); }
+            pf = 2;
+        }
+    };
+    auto issue_claim = [&](int want) {
+        if (lane == 0) { q->pend_want = want; q->pend = atomicAdd(a.counter, (unsigned long long)want); }
+        __syncwarp();
+        pf = 1;
+    };
+
+    // ---- per-lane state
     bool active = false, exhausted = false;
-    long long sys = -1;
     M mdl;
     double y[N];
     double t = 0.0;
     StepCtl ctl;
-    int kout = 0, nst = 0, nrej = 0, status = 0;
-    double p2own = 0.0;
+    int kout = 0, nst = 0, nrej = 0, status = 0, grp = 0;
+    double acc_w = 0.0, acc_1 = 0.0, acc_2 = 0.0;      // SCALAR: weighted SSR, sum |r|, sum r^2 (Morris Y: -, sum v, sum v^2)
 
-    for (;;) {
-        // ------------------------------------------------------------------ refill idle lanes
-        unsigned need = __ballot_sync(FULL, !active && !exhausted);
-        if (need) {
-            int leader = __ffs(need) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (!active && !exhausted) {
-                long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
-                if (idx < a.B) {
-                    sys = idx;
-                    active = true;
-                    const double* pr = a.params + (size_t)sys * P;
-                    double pv[P];
+    // SCALAR: write out the parked systems, one per lane
+    auto flush_ring = [&]() {
+        if constexpr (SCALAR) {
+            __syncwarp();
+            if (lane < nfin) {
+                const long long fs = ring_sys[lane];
+                double ssr = ring_v[lane * 4 + 0], s1 = ring_v[lane * 4 + 1], s2 = ring_v[lane * 4 + 2];
+                const double p2 = ring_v[lane * 4 + 3];
+                const int fstatus = ring_i[lane * 4 + 0];
+                // the t = t[0] row (the initial state) is added here, at full warp width
+                const double* y0 = a.y0 + (a.y0_stride ? (size_t)fs * a.y0_stride : 0);
+                if (a.ymode) {
 #pragma unroll
-                    for (int i = 0; i < P; ++i) pv[i] = pr[i];
-                    if (a.log_params) {
-#pragma unroll 1
-                        for (int i = 0; i < P; ++i) pv[i] = exp(pv[i]);
-                    }
-                    mdl.load(pv);
-                    p2own = 0.0;                      // |physical params|^2 for score_fit's l2 term
-#pragma unroll
-                    for (int i = 0; i < P; ++i) p2own = fma(pv[i], pv[i], p2own);
-                    const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
-#pragma unroll
-                    for (int i = 0; i < N; ++i) { y[i] = y0[i]; my_traj[i] = y[i]; }
-                    t = tgrid[0];
-                    nst = nrej = status = 0;
-                    kout = 1;
-                    // initial step: 1% of the time scale |y|/|f| in the error-weighted norm
-                    double f0[N];
-                    mdl.rhs(y, f0);
-                    float d0 = 0.0f, d1 = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        float sc = (float)fma(a.rtol, fabs(y[i]), a.atol);
-                        d0 = fmaxf(d0, __fdividef((float)fabs(y[i]), sc));
-                        d1 = fmaxf(d1, __fdividef((float)fabs(f0[i]), sc));
-                    }
-                    double h0 = (d0 < 1e-5f || d1 < 1e-5f || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
-                    ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
+                    for (int i = 0; i < N; ++i) { const double v = fmax(y0[i], 0.0); s1 += v; s2 = fma(v, v, s2); }
                 } else {
-                    exhausted = true;
+                    const int g = a.group ? a.group[fs] : 0;
+                    const double* tg = a.target + (size_t)g * a.L;
+                    const double* sg = a.isigma ? a.isigma + (size_t)g * a.sigma_len : nullptr;
+#pragma unroll
+                    for (int i = 1; i < N; ++i) {              // row 0 of the RNA column is not part of flat (sol[5:, 0])
+                        const int fi = rna_len + (i - 1) * T;
+                        const double dlt = fmax(y0[i], 0.0) - __ldg(tg + fi);
+                        s1 += fabs(dlt);
+                        s2 = fma(dlt, dlt, s2);
+                        if (sg) { const double w = dlt * __ldg(sg + fi); ssr = fma(w, w, ssr); }
+                    }
+                    if (RNA_OFFSET == 0 && T > 0) {
+                        const double dlt = fmax(y0[0], 0.0) - __ldg(tg);
+                        s1 += fabs(dlt);
+                        s2 = fma(dlt, dlt, s2);
+                        if (sg) { const double w = dlt * __ldg(sg); ssr = fma(w, w, ssr); }
+                    }
+                    if (!sg) ssr += s2;                        // unit weights: the weighted and the plain sums coincide
+                }
+                const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+                if (fstatus != 0) { ssr = qnan; s1 = qnan; s2 = qnan; }
+                if (a.out_status) a.out_status[fs] = fstatus;
+                if (a.out_nsteps) a.out_nsteps[fs] = ring_i[lane * 4 + 1];
+                if (a.out_nrej) a.out_nrej[fs] = ring_i[lane * 4 + 2];
+                if (a.out_ssr) a.out_ssr[fs] = ssr;
+                if (a.out_score) {
+                    // score_fit (config/config.py:176-226) with r = |target - pred| / L
+                    const double invL = 1.0 / (double)a.L;
+                    const double r1 = s1 * invL, r2 = s2 * invL * invL;
+                    const double mean_r2 = r2 * invL, mae = r1 * invL;
+                    a.out_score[fs] = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                                      a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
+                }
+                if (a.out_Y) {
+                    const double len = (double)TN, mean = s1 / len;
+                    double yv;
+                    switch (a.y_metric) {
+                        case 0: yv = s1; break;
+                        case 1: yv = mean; break;
+                        case 2: yv = s2 / len - mean * mean; break;
+                        default: yv = sqrt(s2); break;
+                    }
+                    a.out_Y[fs] = yv;
                 }
             }
+            __syncwarp();
+            nfin = 0;
+        }
+    };
+
+    for (;;) {
+        // ------------------------------------------------------------------ refill idle lanes from the stash
+        unsigned need = __ballot_sync(FULL, !active && !exhausted);
+        while (need) {
+            if (cur_taken == cur_cnt) {
+                // the current batch is used up: make the prefetched one current
+                if (pf == 0) issue_claim(TPS_STASH);                   // (only before the first batch)
+                if (pf == 1) consume_claim();
+                if (pf == 3) {
+                    if (!active) exhausted = true;
+                    break;
+                }
+                cp_async_wait_all();
+                __syncwarp();
+                cur_cnt = q->nxt_cnt; cur_taken = 0; pb ^= 1; pf = 0;
+                __syncwarp();
+                if (lane == 0) q->cur_base = q->nxt_base;
+                if (a.log_params) {
+                    double* cur = stash + (size_t)pb * TPS_STASH * P;
+                    for (int e = lane; e < cur_cnt * P; e += 32) cur[e] = exp(cur[e]);
+                }
+                __syncwarp();
+            }
+            const int avail = cur_cnt - cur_taken;
+            const int rank = __popc(need & lt_mask);
+            if (((need >> lane) & 1u) && rank < avail) {
+                const int slot = cur_taken + rank;
+                const long long sys = q->cur_base + slot;
+                const double* pr = stash + ((size_t)pb * TPS_STASH + slot) * P;
+                double p2 = 0.0;                      // |physical params|^2 for score_fit's l2 term
+                {
+                    double pv[P];
+#pragma unroll
+                    for (int i = 0; i < P; ++i) { pv[i] = pr[i]; p2 = fma(pv[i], pv[i], p2); }
+                    mdl.load(pv);
+                }
+                lane_sys[threadIdx.x] = sys;
+                lane_p2[threadIdx.x] = p2;
+                const double* y0 = a.y0 + (a.y0_stride ? (size_t)sys * a.y0_stride : 0);
+#pragma unroll
+                for (int i = 0; i < N; ++i) y[i] = y0[i];
+                if constexpr (!SCALAR) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) my_traj[i] = y[i];
+                } else {
+                    acc_w = acc_1 = acc_2 = 0.0;
+                    grp = (want_loss && a.group) ? a.group[sys] : 0;
+                    if (want_loss && a.lam != 0.0) {
+                        // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423); theta = the caller's
+                        // (possibly logarithmic) parameters
+                        const double* th = a.params + (size_t)sys * P;
+                        const double* sgr = (a.isigma && a.sigma_len > a.L) ? a.isigma + (size_t)grp * a.sigma_len + a.L : nullptr;
+                        for (int i = 0; i < P; ++i) {
+                            double w = a.lam / (double)P * th[i] * th[i];
+                            if (sgr) w *= __ldg(sgr + i);
+                            acc_w = fma(w, w, acc_w);
+                        }
+                    }
+                }
+                t = tgrid[0];
+                nst = nrej = status = 0;
+                kout = 1;
+                // initial step: 1% of the time scale |y|/|f| in the error-weighted norm
+                double f0[N];
+                mdl.rhs(y, f0);
+                float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    float sc = (float)fma(a.rtol, fabs(y[i]), a.atol);
+                    d0 = fmaxf(d0, __fdividef((float)fabs(y[i]), sc));
+                    d1 = fmaxf(d1, __fdividef((float)fabs(f0[i]), sc));
+                }
+                double h0 = (d0 < 1e-5f || d1 < 1e-5f || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
+                ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
+                active = true;
+            }
+            cur_taken += min(__popc(need), avail);
+            need = __ballot_sync(FULL, !active && !exhausted);
         }
         if (__all_sync(FULL, !active)) break;
+
+        // ------------------------------------------------------------------ background prefetch of the next batch
+        if (pf == 0) {
+            // guided self-scheduling: full batches until ~64 systems per warp are left, then half of the per-warp share
+            const long long nwarps = (long long)gridDim.x * TPS_WARPS;
+            const long long rem = a.B - q->head_seen;
+            issue_claim(rem > 64 * nwarps ? TPS_STASH : (int)max(1LL, min((long long)TPS_STASH, rem / (2 * nwarps))));
+        } else if (pf == 1) {
+            consume_claim();
+        }
 
         // ------------------------------------------------------------------ one step attempt
         bool finished = false;
@@ -330,30 +560,67 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     if (status == 0 && !store && nst + nrej >= a.max_steps) status = 1;
                 }
                 if (store) {
-                    double* o = my_traj + kout * N;
+                    if constexpr (SCALAR) {
+                        // the residual sums of this output row, straight from the registers (np.clip(sol, 0, None) first)
+                        if (a.ymode) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) o[i] = y[i];
+                            for (int i = 0; i < N; ++i) { const double v = fmax(y[i], 0.0); acc_1 += v; acc_2 = fma(v, v, acc_2); }
+                        } else {
+                            const double* tg = a.target + (size_t)grp * a.L + kout;
+                            const double* sg = a.isigma ? a.isigma + (size_t)grp * a.sigma_len + kout : nullptr;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                // flat layout (models/distmod.py:124-134): [sol[5:,0] | sol[:,1] | sol[:,2:].T]
+                                if (i == 0 && kout < RNA_OFFSET) continue;
+                                const int fo = (i == 0) ? -RNA_OFFSET : rna_len + (i - 1) * T;
+                                const double dlt = fmax(y[i], 0.0) - __ldg(tg + fo);
+                                acc_1 += fabs(dlt);
+                                acc_2 = fma(dlt, dlt, acc_2);
+                                if (sg) { const double w = dlt * __ldg(sg + fo); acc_w = fma(w, w, acc_w); }
+                            }
+                        }
+                    } else {
+                        double* o = my_traj + kout * N;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) o[i] = y[i];
+                    }
                     ++kout;
                 }
             }
             finished = (kout >= T) || (status != 0);
         }
 
-        // ------------------------------------------ warp-cooperative epilogue of finished systems
         unsigned fin = __ballot_sync(FULL, finished);
+        if constexpr (SCALAR) {
+            // ------------------------------------------ park finished systems; 32 of them are written out together
+            if (fin) {
+                const int nnew = __popc(fin);
+                if (nfin + nnew > TPS_RING) flush_ring();
+                if (finished) {
+                    const int slot = nfin + __popc(fin & lt_mask);
+                    ring_sys[slot] = lane_sys[threadIdx.x];
+                    ring_v[slot * 4 + 0] = acc_w; ring_v[slot * 4 + 1] = acc_1; ring_v[slot * 4 + 2] = acc_2;
+                    ring_v[slot * 4 + 3] = lane_p2[threadIdx.x];
+                    ring_i[slot * 4 + 0] = status; ring_i[slot * 4 + 1] = nst; ring_i[slot * 4 + 2] = nrej;
+                    active = false;
+                }
+                nfin += nnew;
+            }
+        } else {
+        // ------------------------------------------ warp-cooperative epilogue of finished systems
         while (fin) {
             const int f = __ffs(fin) - 1;
             fin &= fin - 1;
-            const size_t fsys = (size_t)__shfl_sync(FULL, sys, f);
             const int fstatus = __shfl_sync(FULL, status, f);
             const int fvalid = __shfl_sync(FULL, kout, f);          // outputs 0..fvalid-1 were produced
             const int fnst = __shfl_sync(FULL, nst, f), fnrej = __shfl_sync(FULL, nrej, f);
             __syncwarp();                                           // the owner's trajectory stores are visible
+            const size_t fsys = (size_t)lane_sys[(threadIdx.x & ~31) + f];
             const double* tr = warp_traj + (size_t)f * TN;
             const double* y0 = a.y0 + (a.y0_stride ? fsys * (size_t)a.y0_stride : 0);
             const int g = (want_loss && a.group) ? a.group[fsys] : 0;
             const double* tg = want_loss ? a.target + (size_t)g * a.L : nullptr;
-            const double* sg = (want_loss && a.sigma) ? a.sigma + (size_t)g * a.sigma_len : nullptr;
+            const double* sg = (want_loss && a.isigma) ? a.isigma + (size_t)g * a.sigma_len : nullptr;
             const double qnan = __longlong_as_double(0x7ff8000000000000LL);
             double ssr = 0.0, sr = 0.0, sr2 = 0.0, s1 = 0.0, s2 = 0.0, dyn = 0.0;
             // Fast path (loss and/or flat only, successful system): walk the L flat entries through the index table —
@@ -376,7 +643,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                             if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
                             if (want_loss) {
                                 const double dlt = v - __ldg(tg + fi);
-                                const double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                                const double w = sg ? dlt * __ldg(sg + fi) : dlt;
                                 ssr = fma(w, w, ssr);
                                 sr += fabs(dlt);
                                 sr2 = fma(dlt, dlt, sr2);
@@ -397,7 +664,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     if (a.out_flat) a.out_flat[fsys * a.L + fi] = v;
                     if (want_loss) {
                         const double dlt = v - __ldg(tg + fi);
-                        const double w = sg ? dlt / __ldg(sg + fi) : dlt;
+                        const double w = sg ? dlt * __ldg(sg + fi) : dlt;
                         ssr = fma(w, w, ssr);
                         sr += fabs(dlt);
                         sr2 = fma(dlt, dlt, sr2);
@@ -412,7 +679,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     }
                 }
             }
-            const double p2 = __shfl_sync(FULL, p2own, f);           // computed by the owner when it loaded the parameters
+            const double p2 = lane_p2[(threadIdx.x & ~31) + f];      // computed by the owner when it loaded the parameters
             if (want_loss) {
                 if (a.lam != 0.0) {
                     // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423)
@@ -420,7 +687,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     for (int i = lane; i < P; i += 32) {
                         const double th = a.params[fsys * P + i];
                         double w = a.lam / (double)P * th * th;
-                        if (sgr) w /= __ldg(sgr + i);
+                        if (sgr) w *= __ldg(sgr + i);
                         ssr = fma(w, w, ssr);
                     }
                 }
@@ -455,7 +722,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             }
         }
         if (finished) active = false;
+        }
     }
+    flush_ring();
 }
 
 }  // namespace pk

@@ -4,8 +4,6 @@
 // hosts without it and reuses the copy PyTorch already mapped).
 #include "pk_internal.hpp"
 
-#include "local_dense.cuh"
-#include "local_tps.cuh"
 #include "pk_common.cuh"
 
 namespace pkh {
@@ -63,6 +61,12 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     }
     double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
     if (s == 123.456) out[0] = s;
+}
+
+// out[i] = 1 / in[i]: the residual weights 1/sigma of the thread-per-system kernels (one launch per job that passes sigma)
+__global__ void recip_kernel(const double* in, double* out, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0 / in[i];
 }
 
 // ---- Morris elementary effects (SALib.analyze.morris as called at sensitivity/analysis.py:264)
@@ -148,86 +152,12 @@ __global__ void __launch_bounds__(256) morris_stats_kernel(const double* ee, lon
 namespace {
 
 // Register-resident kernel limits: the largest site counts that compile with ZERO local-memory
-// spill (csrc/ptxas.log); larger systems take the shared-memory dense path.
-constexpr int TPS_MAX_NS_DIST = 8;
-constexpr int TPS_MAX_NS_SUCC = 8;
-// Resident CTAs per SM the register allocator must allow with ZERO spill (checked in ptxas.log):
-// n <= 5 states fit 128 registers (4 CTAs x 128 lanes), mid sizes get 168 (3 CTAs), the rest 255.
-template <class M> constexpr int tps_min_blocks() { return M::N <= 5 ? 4 : (M::N + M::NF <= 26 ? 3 : 2); }
-using pk::TPS_BLOCK;
+// spill (csrc/ptxas.log); larger systems take the shared-memory dense path.  The kernels are instantiated in their own
+// translation units (pk_tps_dist.cu, pk_tps_succ.cu, pk_dense.cu) so that the library builds in parallel.
+constexpr int TPS_MAX_NS_DIST = pkh::TPS_MAX_NS;
+constexpr int TPS_MAX_NS_SUCC = pkh::TPS_MAX_NS;
 constexpr int PIPE_MAX_CHUNKS = pk_handle_s::MAX_CHUNKS;
 constexpr size_t PIPE_MIN_CHUNK = 100000;   // host-path batches >= 2x/4x this are pipelined in 2/4 chunks
-
-template <class M>
-cudaError_t launch_tps(pk_handle_s* h, pk::LocalArgs a) {
-    size_t smem = (size_t)a.T * sizeof(double) + (((size_t)a.L * sizeof(short) + 7) & ~(size_t)7);   // time grid + flat index table
-    auto kern = pk::local_tps_kernel<M, tps_min_blocks<M>()>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPS_BLOCK, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    long long need = (a.B + TPS_BLOCK - 1) / TPS_BLOCK;
-    long long grid = (long long)h->sm_count * per_sm;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    // one [T][n] trajectory slot per resident lane (L2-resident, reused for every system of the lane)
-    e = h->traj.ensure((size_t)grid * TPS_BLOCK * a.T * M::N * sizeof(double));
-    if (e != cudaSuccess) return e;
-    a.traj = (double*)h->traj.p;
-    kern<<<(unsigned)grid, TPS_BLOCK, smem, h->stream>>>(a);
-    return cudaGetLastError();
-}
-
-template <template <int> class M, int MAXNS>
-cudaError_t dispatch_tps(pk_handle_s* h, const pk::LocalArgs& a) {
-    switch (a.ns) {
-        case 1: return launch_tps<M<1>>(h, a);
-        case 2: return launch_tps<M<2>>(h, a);
-        case 3: return launch_tps<M<3>>(h, a);
-        case 4: return launch_tps<M<4>>(h, a);
-        case 5: return launch_tps<M<5>>(h, a);
-        case 6: return launch_tps<M<6>>(h, a);
-        case 7: return launch_tps<M<7>>(h, a);
-        case 8: return launch_tps<M<8>>(h, a);
-        default: return cudaErrorInvalidValue;
-    }
-}
-
-template <int MODEL, int NT>
-cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
-    pk::DenseLayout lay;
-    lay.n = a.n;
-    lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
-    lay.P = a.P;
-    lay.nobs = 2 + a.ns;
-    size_t smem = (size_t)lay.total() * sizeof(double);
-    auto kern = pk::local_dense_kernel<MODEL, NT>;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)h->sm_count * per_sm;
-    if (grid > a.B) grid = a.B;
-    if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, NT, smem, h->stream>>>(a, lay);
-    return cudaGetLastError();
-}
-
-// one system per 1, 2 or 4 warps: the shared-memory matrix limits the systems resident on an SM (5 at 65 states),
-// so larger systems get more threads each to keep the SM's issue slots busy
-template <int MODEL>
-cudaError_t launch_dense(pk_handle_s* h, const pk::LocalArgs& a) {
-    if (a.n >= 40) return launch_dense_nt<MODEL, 128>(h, a);
-    if (a.n >= 24) return launch_dense_nt<MODEL, 64>(h, a);
-    return launch_dense_nt<MODEL, 32>(h, a);
-}
 
 int dims(int model, int ns, int T, int* n, int* P, int* L) {
     if (ns < 1) return fail("n_sites must be >= 1");
@@ -317,7 +247,7 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
                        &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
@@ -446,6 +376,8 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     a.w_delta = j->score_w[3]; a.w_mu = j->score_w[4];
     a.y0_stride = j->y0_stride;
     a.counter = h->counter;
+    // the flat-index table of the trajectory-slot epilogue holds k*n + i as a short
+    if (tps_path && (long long)j->T * n > 32767) return fail("T * n_states must be <= 32767 on the thread-per-system path");
 
     const size_t y0_elems = j->y0_stride ? (B - 1) * (size_t)j->y0_stride + n : (size_t)n;
     const size_t G = want_loss ? (size_t)j->n_groups : 0;
@@ -453,16 +385,19 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
 
     auto launch = [&](const pk::LocalArgs& ac) -> cudaError_t {
         const bool tps = tps_path;
-        if (tps) return (j->model == PK_DISTMOD) ? dispatch_tps<pk::DistModel, TPS_MAX_NS_DIST>(h, ac)
-                                                  : dispatch_tps<pk::SuccModel, TPS_MAX_NS_SUCC>(h, ac);
-        if (j->model == PK_DISTMOD) return launch_dense<0>(h, ac);
-        if (j->model == PK_SUCCMOD) return launch_dense<1>(h, ac);
-        return launch_dense<2>(h, ac);
+        if (tps) return (j->model == PK_DISTMOD) ? pkh::launch_tps_dist(h, ac) : pkh::launch_tps_succ(h, ac);
+        return pkh::launch_dense_model(h, ac, j->model == PK_DISTMOD ? 0 : (j->model == PK_SUCCMOD ? 1 : 2));
     };
 
     if (!host) {
         a.params = j->params; a.y0 = j->y0; a.t = j->t;
         a.target = j->target; a.sigma = j->sigma; a.group = j->group;
+        if (tps_path && want_loss && j->sigma) {
+            const long long ns_ = (long long)G * j->sigma_len;
+            CK(h->isig.ensure((size_t)ns_ * sizeof(double)));
+            pk::recip_kernel<<<(unsigned)((ns_ + 255) / 256), 256, 0, st>>>(j->sigma, (double*)h->isig.p, ns_);
+            a.isigma = (const double*)h->isig.p;
+        }
         a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
         a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
         a.out_nrej = j->out_nrej;
@@ -571,6 +506,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         if (j->sigma)
             CK(cudaMemcpyAsync((void*)a.sigma, j->sigma, G * (size_t)j->sigma_len * sizeof(double),
                                cudaMemcpyHostToDevice, sin));
+        CK(cudaEventRecord(h->ev_in[PIPE_MAX_CHUNKS - 1], sin));
     }
     size_t lo[PIPE_MAX_CHUNKS + 1];
     {
@@ -594,6 +530,13 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         if (a.group)
             CK(cudaMemcpyAsync((int*)a.group + o, j->group + o, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, sin));
         CK(cudaEventRecord(h->ev_in[c], sin));
+    }
+    if (tps_path && want_loss && j->sigma) {
+        const long long ns_ = (long long)G * j->sigma_len;
+        CK(h->isig.ensure((size_t)ns_ * sizeof(double)));
+        CK(cudaStreamWaitEvent(st, h->ev_in[PIPE_MAX_CHUNKS - 1], 0));       // recorded right after the sigma upload
+        pk::recip_kernel<<<(unsigned)((ns_ + 255) / 256), 256, 0, st>>>(a.sigma, (double*)h->isig.p, ns_);
+        a.isigma = (const double*)h->isig.p;
     }
     CK(cudaEventRecord(h->ev0, st));
     for (int c = 0; c < nchunks; ++c) {

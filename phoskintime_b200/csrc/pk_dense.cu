@@ -1,0 +1,49 @@
+// Dense (shared-memory matrix) kernels: random model and the distributive / successive models beyond 8 sites.
+#include "pk_internal.hpp"
+
+#include "local_dense.cuh"
+
+namespace pkh {
+namespace {
+
+template <int MODEL, int NT>
+cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
+    pk::DenseLayout lay;
+    lay.n = a.n;
+    lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
+    lay.P = a.P;
+    lay.nobs = 2 + a.ns;
+    size_t smem = (size_t)lay.total() * sizeof(double);
+    auto kern = pk::local_dense_kernel<MODEL, NT>;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)h->sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, NT, smem, h->stream>>>(a, lay);
+    return cudaGetLastError();
+}
+
+// one system per 1, 2 or 4 warps: the shared-memory matrix limits the systems resident on an SM (5 at 65 states),
+// so larger systems get more threads each to keep the SM's issue slots busy
+template <int MODEL>
+cudaError_t launch_dense(pk_handle_s* h, const pk::LocalArgs& a) {
+    if (a.n >= 40) return launch_dense_nt<MODEL, 128>(h, a);
+    if (a.n >= 24) return launch_dense_nt<MODEL, 64>(h, a);
+    return launch_dense_nt<MODEL, 32>(h, a);
+}
+
+}  // namespace
+
+cudaError_t launch_dense_model(pk_handle_s* h, const pk::LocalArgs& a, int model) {
+    if (model == 0) return launch_dense<0>(h, a);
+    if (model == 1) return launch_dense<1>(h, a);
+    return launch_dense<2>(h, a);
+}
+
+}  // namespace pkh

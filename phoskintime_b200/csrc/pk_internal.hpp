@@ -61,7 +61,7 @@ struct pk_handle_s {
     static constexpr int MAX_CHUNKS = 8;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-    pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj;
+    pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj, isig;
     pkh::DevBuf g_params, g_y0, g_t, g_stops, g_Y, g_loss, g_F, g_metric, g_status, g_nsteps, g_nrej, g_traj, g_binv, g_fc;
     unsigned long long* counter = nullptr;
     int last_launches = 0;
@@ -74,6 +74,13 @@ struct pk_handle_s {
     std::vector<pkh::GlobalTopoHost*> topos;   // uploaded global networks (index = topology id)
 };
 
+namespace pk {
+struct LocalArgs;
+}
 namespace pkh {
 void release_global_topologies(pk_handle_s* h);   // pk_global.cu
+constexpr int TPS_MAX_NS = 8;                     // thread-per-system kernels: 1..8 sites (pk_tps_launch.cuh)
+cudaError_t launch_tps_dist(pk_handle_s* h, const pk::LocalArgs& a);               // pk_tps_dist.cu
+cudaError_t launch_tps_succ(pk_handle_s* h, const pk::LocalArgs& a);               // pk_tps_succ.cu
+cudaError_t launch_dense_model(pk_handle_s* h, const pk::LocalArgs& a, int model); // pk_dense.cu (0 dist, 1 succ, 2 rand)
 }

@@ -1,0 +1,10 @@
+// dev-only: one instantiation of the thread-per-system kernel for quick ptxas / SASS checks
+#include "../../phoskintime_b200/csrc/local_tps.cuh"
+#ifndef DEV_MODEL
+#define DEV_MODEL SuccModel<5>
+#endif
+#ifndef DEV_MINB
+#define DEV_MINB 3
+#endif
+template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, true>(const pk::LocalArgs);
+template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, false>(const pk::LocalArgs);
