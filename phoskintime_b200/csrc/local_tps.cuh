@@ -218,6 +218,7 @@ __host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool sc
     b += (size_t)TPS_WARPS * 48;                                 // per-warp queue state (TpsQueue)
     if (scalar) b += (size_t)TPS_WARPS * TPS_RING * (4 * 8 + 8 + 16);
     b += (size_t)T * 8;
+    if (scalar) b += (size_t)T * (P / 2) * 16;                   // {target, weight} table of a single-group job (n = P/2 states)
     if (!scalar) b += ((size_t)L * 2 + 7) & ~(size_t)7;
     return b;
 }
@@ -226,9 +227,8 @@ __host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool sc
 // lane writes the same value) so that it does not occupy registers across the step body.
 struct TpsQueue {
     long long cur_base, nxt_base, head_seen;
-    unsigned long long pend;      // result of the claim in flight (lane 0's atomicAdd)
     int nxt_cnt, pend_want;
-    int pad[2];
+    int pad[4];
 };
 static_assert(sizeof(TpsQueue) == 48, "tps_smem_bytes reserves 48 bytes per warp");
 
@@ -249,6 +249,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <class M, int MIN_BLOCKS, bool SCALAR>
 __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
     constexpr int N = M::N, NF = M::NF, P = M::P;
+    static_assert(2 * N == P, "tps_smem_bytes sizes the residual table with n = P/2");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -272,9 +273,14 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
         ring_sys = (long long*)sp + (size_t)wid * TPS_RING;      sp += (size_t)TPS_WARPS * TPS_RING * 8;
         ring_i = (int*)sp + (size_t)wid * TPS_RING * 4;          sp += (size_t)TPS_WARPS * TPS_RING * 16;
     }
+    double2* const tw_s = (double2*)sp;          // SCALAR: the {target, weight} rows of a single-group job
+    if constexpr (SCALAR) sp += (size_t)TN * 16;
     double* const tgrid = (double*)sp;           sp += (size_t)T * 8;
     short* const fmap = (short*)sp;              // !SCALAR: trajectory index (k*N + i) of every flat entry
     for (int i = threadIdx.x; i < T; i += TPS_BLOCK) tgrid[i] = a.t[i];
+    const bool tw_in_smem = SCALAR && a.tw && a.n_groups == 1;
+    if (tw_in_smem)
+        for (int i = threadIdx.x; i < TN; i += TPS_BLOCK) tw_s[i] = a.tw[i];
     if constexpr (!SCALAR) {
         for (int fi = threadIdx.x; fi < a.L; fi += TPS_BLOCK) {
             int k, i;
@@ -300,12 +306,13 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     int pf = 0;                               // 0 idle, 1 claim in flight, 2 copies in flight, 3 queue drained
     const bool al16 = ((reinterpret_cast<unsigned long long>(a.params) & 15ull) == 0);
     int nfin = 0;                             // SCALAR: parked finished systems
-    if (lane == 0) { q->cur_base = 0; q->nxt_base = 0; q->head_seen = 0; q->pend = 0; q->nxt_cnt = 0; q->pend_want = 0; }
+    unsigned long long pend = 0;              // lane 0: result of the claim in flight (consumed an iteration later)
+    if (lane == 0) { q->cur_base = 0; q->nxt_base = 0; q->head_seen = 0; q->nxt_cnt = 0; q->pend_want = 0; }
     __syncwarp();
 
     // claim in flight -> copies in flight (pf 1 -> 2), or queue drained (pf 1 -> 3)
     auto consume_claim = [&]() {
-        const long long b = (long long)q->pend;
+        const long long b = (long long)__shfl_sync(FULL, pend, 0);
         const long long c = min((long long)q->pend_want, a.B - b);
         __syncwarp();
         if (c <= 0) pf = 3;
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
         }
     };
     auto issue_claim = [&](int want) {
-        if (lane == 0) { q->pend_want = want; q->pend = atomicAdd(a.counter, (unsigned long long)want); }
+        if (lane == 0) { q->pend_want = want; pend = atomicAdd(a.counter, (unsigned long long)want); }
         __syncwarp();
         pf = 1;
     };
@@ -460,17 +467,18 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 t = tgrid[0];
                 nst = nrej = status = 0;
                 kout = 1;
-                // initial step: 1% of the time scale |y|/|f| in the error-weighted norm
+                // initial step: 1% of the time scale max|y| / max|f|.  The maxima are taken on the high words of the doubles
+                // (monotone for non-negative values, 20 mantissa bits: plenty for a first guess the controller corrects).
                 double f0[N];
                 mdl.rhs(y, f0);
-                float d0 = 0.0f, d1 = 0.0f;
+                int my = 0, mf = 0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
-                    float sc = (float)fma(a.rtol, fabs(y[i]), a.atol);
-                    d0 = fmaxf(d0, __fdividef((float)fabs(y[i]), sc));
-                    d1 = fmaxf(d1, __fdividef((float)fabs(f0[i]), sc));
+                    my = max(my, __double2hiint(y[i]) & 0x7fffffff);
+                    mf = max(mf, __double2hiint(f0[i]) & 0x7fffffff);
                 }
-                double h0 = (d0 < 1e-5f || d1 < 1e-5f || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
+                const float d0 = (float)__hiloint2double(my, 0), d1 = (float)__hiloint2double(mf, 0);
+                double h0 = (!(d0 > 1e-30f) || !(d1 > 1e-30f) || !(d0 < 3.0e38f) || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
                 ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
                 active = true;
             }
@@ -557,26 +565,41 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         ctl.h = ctl_reject(ctl, hh, err, a.m.expo);
                         if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
                     }
-                    if (status == 0 && !store && nst + nrej >= a.max_steps) status = 1;
                 }
                 if (store) {
                     if constexpr (SCALAR) {
-                        // the residual sums of this output row, straight from the registers (np.clip(sol, 0, None) first)
+                        // the residual sums of this output row, straight from the registers.  np.clip(sol, 0, None) on the
+                        // sign bit (integer pipe; NaN stays NaN as in numpy).
                         if (a.ymode) {
 #pragma unroll
-                            for (int i = 0; i < N; ++i) { const double v = fmax(y[i], 0.0); acc_1 += v; acc_2 = fma(v, v, acc_2); }
-                        } else {
-                            const double* tg = a.target + (size_t)grp * a.L + kout;
-                            const double* sg = a.isigma ? a.isigma + (size_t)grp * a.sigma_len + kout : nullptr;
-#pragma unroll
                             for (int i = 0; i < N; ++i) {
-                                // flat layout (models/distmod.py:124-134): [sol[5:,0] | sol[:,1] | sol[:,2:].T]
-                                if (i == 0 && kout < RNA_OFFSET) continue;
-                                const int fo = (i == 0) ? -RNA_OFFSET : rna_len + (i - 1) * T;
-                                const double dlt = fmax(y[i], 0.0) - __ldg(tg + fo);
-                                acc_1 += fabs(dlt);
-                                acc_2 = fma(dlt, dlt, acc_2);
-                                if (sg) { const double w = dlt * __ldg(sg + fo); acc_w = fma(w, w, acc_w); }
+                                const double v = __double2hiint(y[i]) < 0 ? 0.0 : y[i];
+                                acc_1 += v; acc_2 = fma(v, v, acc_2);
+                            }
+                        } else {
+                            // row kout of the {target, weight} table (trajectory order: one base address, 16-byte loads);
+                            // flat (models/distmod.py:124-134) = [sol[5:,0] | sol[:,1] | sol[:,2:].T]: the RNA column only from row 5
+                            // (generic pointer: the shared-memory copy of a single-group job, the L1-cached global table otherwise)
+                            const double2* row = tw_in_smem ? tw_s + kout * N : a.tw + ((size_t)grp * TN + kout * N);
+                            if (a.isigma != nullptr) {
+#pragma unroll
+                                for (int i = 0; i < N; ++i) {
+                                    if (i == 0 && kout < RNA_OFFSET) continue;
+                                    const double2 e = row[i];
+                                    const double dlt = (__double2hiint(y[i]) < 0 ? 0.0 : y[i]) - e.x;
+                                    const double w = dlt * e.y;
+                                    acc_1 += fabs(dlt);
+                                    acc_2 = fma(dlt, dlt, acc_2);
+                                    acc_w = fma(w, w, acc_w);
+                                }
+                            } else {                       // unit weights: the weighted sum is acc_2 (added when the system is written out)
+#pragma unroll
+                                for (int i = 0; i < N; ++i) {
+                                    if (i == 0 && kout < RNA_OFFSET) continue;
+                                    const double dlt = (__double2hiint(y[i]) < 0 ? 0.0 : y[i]) - row[i].x;
+                                    acc_1 += fabs(dlt);
+                                    acc_2 = fma(dlt, dlt, acc_2);
+                                }
                             }
                         }
                     } else {
@@ -586,6 +609,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     }
                     ++kout;
                 }
+                if (status == 0 && kout < T && nst + nrej >= a.max_steps) status = 1;      // outputs still missing
             }
             finished = (kout >= T) || (status != 0);
         }

@@ -63,10 +63,28 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     if (s == 123.456) out[0] = s;
 }
 
-// out[i] = 1 / in[i]: the residual weights 1/sigma of the thread-per-system kernels (one launch per job that passes sigma)
-__global__ void recip_kernel(const double* in, double* out, long long n) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = 1.0 / in[i];
+// Residual tables of the thread-per-system kernels, one launch per job that asks for the fused loss:
+//   isig[g][q] = 1 / sigma[g][q]                                    (q < sigma_len; only when sigma is given)
+//   tw[g][k*n + i] = {target, weight} of trajectory entry (output k, state i) in TRAJECTORY order, weight = 1/sigma or 1;
+//                    entries that are not part of flat (the RNA column before sol[5:, 0] starts) get {0, 0}
+// so that a lane that lands on output k reads the n pairs of its row with ONE base address (16-byte loads).
+__global__ void tps_prep_kernel(const double* target, const double* sigma, int G, int T, int n, int L, int sigma_len,
+                                double* isig, double2* tw) {
+    const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int TN = T * n;
+    if (sigma && id < (long long)G * sigma_len) isig[id] = 1.0 / sigma[id];
+    if (id < (long long)G * TN) {
+        const int g = (int)(id / TN), r = (int)(id - (long long)g * TN);
+        const int k = r / n, i = r - k * n;
+        const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
+        const int fi = (i == 0) ? (k >= RNA_OFFSET ? k - RNA_OFFSET : -1) : rna_len + (i - 1) * T + k;
+        double2 v = make_double2(0.0, 0.0);
+        if (fi >= 0) {
+            v.x = target[(size_t)g * L + fi];
+            v.y = sigma ? 1.0 / sigma[(size_t)g * sigma_len + fi] : 1.0;
+        }
+        tw[id] = v;
+    }
 }
 
 // ---- Morris elementary effects (SALib.analyze.morris as called at sensitivity/analysis.py:264)
@@ -247,7 +265,7 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
                        &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
@@ -383,6 +401,22 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     const size_t G = want_loss ? (size_t)j->n_groups : 0;
     const size_t TN = (size_t)j->T * n;
 
+    // thread-per-system kernels: reciprocal weights and the {target, weight} table in trajectory order (tps_prep_kernel)
+    auto tps_prep = [&](const double* d_target, const double* d_sigma) -> cudaError_t {
+        const long long n_is = d_sigma ? (long long)G * j->sigma_len : 0, n_tw = (long long)G * TN;
+        cudaError_t e = h->isig.ensure((size_t)(n_is + 1) * sizeof(double));
+        if (e != cudaSuccess) return e;
+        e = h->tw.ensure((size_t)n_tw * 2 * sizeof(double));
+        if (e != cudaSuccess) return e;
+        const long long nthr = std::max(n_is, n_tw);
+        pk::tps_prep_kernel<<<(unsigned)((nthr + 255) / 256), 256, 0, st>>>(d_target, d_sigma, (int)G, j->T, n, L, j->sigma_len,
+                                                                          (double*)h->isig.p, (double2*)h->tw.p);
+        a.isigma = d_sigma ? (const double*)h->isig.p : nullptr;
+        a.tw = (const double2*)h->tw.p;
+        a.n_groups = (int)G;
+        return cudaGetLastError();
+    };
+
     auto launch = [&](const pk::LocalArgs& ac) -> cudaError_t {
         const bool tps = tps_path;
         if (tps) return (j->model == PK_DISTMOD) ? pkh::launch_tps_dist(h, ac) : pkh::launch_tps_succ(h, ac);
@@ -392,12 +426,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     if (!host) {
         a.params = j->params; a.y0 = j->y0; a.t = j->t;
         a.target = j->target; a.sigma = j->sigma; a.group = j->group;
-        if (tps_path && want_loss && j->sigma) {
-            const long long ns_ = (long long)G * j->sigma_len;
-            CK(h->isig.ensure((size_t)ns_ * sizeof(double)));
-            pk::recip_kernel<<<(unsigned)((ns_ + 255) / 256), 256, 0, st>>>(j->sigma, (double*)h->isig.p, ns_);
-            a.isigma = (const double*)h->isig.p;
-        }
+        if (tps_path && want_loss) CK(tps_prep(a.target, a.sigma));
         a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
         a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
         a.out_nrej = j->out_nrej;
@@ -531,12 +560,9 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
             CK(cudaMemcpyAsync((int*)a.group + o, j->group + o, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, sin));
         CK(cudaEventRecord(h->ev_in[c], sin));
     }
-    if (tps_path && want_loss && j->sigma) {
-        const long long ns_ = (long long)G * j->sigma_len;
-        CK(h->isig.ensure((size_t)ns_ * sizeof(double)));
-        CK(cudaStreamWaitEvent(st, h->ev_in[PIPE_MAX_CHUNKS - 1], 0));       // recorded right after the sigma upload
-        pk::recip_kernel<<<(unsigned)((ns_ + 255) / 256), 256, 0, st>>>(a.sigma, (double*)h->isig.p, ns_);
-        a.isigma = (const double*)h->isig.p;
+    if (tps_path && want_loss) {
+        CK(cudaStreamWaitEvent(st, h->ev_in[PIPE_MAX_CHUNKS - 1], 0));       // recorded right after the target / sigma upload
+        CK(tps_prep(a.target, a.sigma));
     }
     CK(cudaEventRecord(h->ev0, st));
     for (int c = 0; c < nchunks; ++c) {
