@@ -22,6 +22,8 @@
 //   !SCALAR  sol / flat rows requested: the lane stores its raw state into a private L2-resident trajectory slot and
 //            the whole warp runs the epilogue of a finished system (coalesced rows, shuffle reductions).
 #pragma once
+#include <type_traits>
+
 #include "pk_common.cuh"
 
 namespace pk {
@@ -44,33 +46,51 @@ __device__ __forceinline__ void batch_invert(double (&a)[M]) {
 }
 
 // ------------------------------------------------------------------------------------ models
-// Each model provides rhs(y) = M y + b, factor(c) of A = I - c M (c = h*gamma) and an in-place
-// solve A x = r.
+// Each model provides rhs(y) = M y + b, factor(c) of A = I - c M (c = h*gamma) and an in-place solve A x = r.
+// Its P derived rate coefficients live either in registers (RegCoef) or in a per-lane shared-memory column (SmemCoef:
+// 2P registers less per lane, which buys the resident warps the latency-bound step loop needs; the coefficients are
+// read once per step, conflict-free at [coefficient][lane]).
+constexpr int TPS_BLOCK = 128;
+template <int NC>
+struct RegCoef {
+    double v[NC];
+    __device__ __forceinline__ double get(int k) const { return v[k]; }
+    __device__ __forceinline__ void set(int k, double x) { v[k] = x; }
+};
+struct SmemCoef {
+    double* p;                       // &coef[0][lane]; coefficient k at p[k * TPS_BLOCK]
+    __device__ __forceinline__ double get(int k) const { return p[k * TPS_BLOCK]; }
+    __device__ __forceinline__ void set(int k, double x) { p[k * TPS_BLOCK] = x; }
+};
+
 template <int NS_>
 struct DistModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4;
-    // FLOPs (FMA = 2) of factor / rhs / one solve as written below — bench.py::flops_per_step mirrors these
-    double A, Bm, C, kP, S[NS], k[NS];
-    __device__ __forceinline__ void load(const double* p) {
-        A = p[0]; Bm = p[1]; C = p[2];
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NF = 2 * NS_ + 4, NC = P;
+    // coefficients: [A, B, C, kP = D + sum S, S_i (NS), k_i = 1 + D_i (NS)]
+    static constexpr int cA = 0, cB = 1, cC = 2, cKP = 3, cS = 4, cK = 4 + NS_;
+    template <class Co>
+    __device__ static __forceinline__ void load(Co& c, const double* p) {
+        c.set(cA, p[0]); c.set(cB, p[1]); c.set(cC, p[2]);
         double sS = 0.0;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { S[i] = p[4 + i]; sS += S[i]; k[i] = 1.0 + p[4 + NS + i]; }
-        kP = p[3] + sS;
+        for (int i = 0; i < NS; ++i) { c.set(cS + i, p[4 + i]); sS += p[4 + i]; c.set(cK + i, 1.0 + p[4 + NS + i]); }
+        c.set(cKP, p[3] + sS);
     }
-    __device__ __forceinline__ void rhs(const double (&y)[N], double (&f)[N]) const {
-        f[0] = fma(-Bm, y[0], A);
-        double acc = fma(C, y[0], -kP * y[1]);
+    template <class Co>
+    __device__ static __forceinline__ void rhs(const Co& c, const double (&y)[N], double (&f)[N]) {
+        f[0] = fma(-c.get(cB), y[0], c.get(cA));
+        double acc = fma(c.get(cC), y[0], -c.get(cKP) * y[1]);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { acc += y[2 + i]; f[2 + i] = fma(S[i], y[1], -k[i] * y[2 + i]); }
+        for (int i = 0; i < NS; ++i) { acc += y[2 + i]; f[2 + i] = fma(c.get(cS + i), y[1], -c.get(cK + i) * y[2 + i]); }
         f[1] = acc;
     }
     // rows: (1+cB) x0 = r0 ; -cC x0 + (1+c kP) x1 - c sum x_{2+i} = r1 ; -c S_i x1 + q_i x_{2+i} = r_{2+i}
     // F = [1/q0, 1/pivot, cC, c, 1/q_i (NS), c S_i / q_i (NS)]
-    __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
-        double q[NS], pre[NS], suf[NS];
+    template <class Co>
+    __device__ static __forceinline__ void factor(const Co& co, double c, double (&F)[NF]) {
+        double q[NS], pre[NS], suf[NS], S[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) q[i] = fma(c, k[i], 1.0);
+        for (int i = 0; i < NS; ++i) { q[i] = fma(c, co.get(cK + i), 1.0); S[i] = co.get(cS + i); }
         pre[0] = 1.0;
 #pragma unroll
         for (int i = 1; i < NS; ++i) pre[i] = pre[i - 1] * q[i - 1];
@@ -81,11 +101,11 @@ struct DistModel {
         double sq = 0.0;                                   // sum_i S_i prod_{j != i} q_j
 #pragma unroll
         for (int i = 0; i < NS; ++i) { pre[i] *= suf[i]; sq = fma(S[i], pre[i], sq); }
-        double inv[3] = {fma(c, Bm, 1.0), Q, fma(fma(c, kP, 1.0), Q, -(c * c) * sq)};   // q0, Q, pivot*Q
+        double inv[3] = {fma(c, co.get(cB), 1.0), Q, fma(fma(c, co.get(cKP), 1.0), Q, -(c * c) * sq)};   // q0, Q, pivot*Q
         batch_invert<3>(inv);
         F[0] = inv[0];
         F[1] = Q * inv[2];
-        F[2] = c * C;
+        F[2] = c * co.get(cC);
         F[3] = c;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
@@ -94,7 +114,7 @@ struct DistModel {
             F[4 + NS + i] = c * S[i] * iq;
         }
     }
-    __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
+    __device__ static __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) {
         x[0] *= F[0];
         double sz0 = 0.0, sz1 = 0.0;                        // two partial sums: half the dependent chain
 #pragma unroll
@@ -110,7 +130,7 @@ struct DistModel {
 
 template <int NS_>
 struct SuccModel {
-    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_;
+    static constexpr int NS = NS_, N = NS_ + 2, P = 4 + 2 * NS_, NC = P;
     // Twisted factorisation of the tridiagonal block over the unknowns j = 0..NS (x[1+j]): rows 0..MID-1 are eliminated
     // downwards, rows NS..MID+1 upwards, the middle row MID last; back substitution runs outwards from MID.
     static constexpr int MID = (NS + 1) / 2, NT = MID, NB = NS - MID;
@@ -118,22 +138,25 @@ struct SuccModel {
     //      1/q_j (NB: j = MID+1..NS), lb_j = c / q_j (NB: row j into row j-1), c S_{j-1} (NB: back substitution downwards)]
     static constexpr int NF = 4 + 2 * NT + 3 * NB;
     static constexpr int O_IP = 4, O_LT = 4 + NT, O_IQ = 4 + 2 * NT, O_LB = 4 + 2 * NT + NB, O_CS = 4 + 2 * NT + 2 * NB;
-    // d[0] = D + S_0 (protein), d[1+i] = 1 + Dr_i + S_{i+1} (site i; no S term for the last site)
-    double A, Bm, C, S[NS], d[NS + 1];
-    __device__ __forceinline__ void load(const double* p) {
-        A = p[0]; Bm = p[1]; C = p[2];
+    // coefficients: [A, B, C, S_i (NS), d_j (NS+1)] with d_0 = D + S_0 (protein), d_{1+i} = 1 + Dr_i + S_{i+1} (site i; no S
+    // term for the last site)
+    static constexpr int cA = 0, cB = 1, cC = 2, cS = 3, cD = 3 + NS_;
+    template <class Co>
+    __device__ static __forceinline__ void load(Co& c, const double* p) {
+        c.set(cA, p[0]); c.set(cB, p[1]); c.set(cC, p[2]);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) S[i] = p[4 + i];
-        d[0] = p[3] + S[0];
+        for (int i = 0; i < NS; ++i) c.set(cS + i, p[4 + i]);
+        c.set(cD, p[3] + p[4]);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) d[1 + i] = 1.0 + p[4 + NS + i] + (i < NS - 1 ? S[i < NS - 1 ? i + 1 : i] : 0.0);
+        for (int i = 0; i < NS; ++i) c.set(cD + 1 + i, 1.0 + p[4 + NS + i] + (i < NS - 1 ? p[i < NS - 1 ? 5 + i : 4] : 0.0));
     }
-    __device__ __forceinline__ void rhs(const double (&y)[N], double (&f)[N]) const {
-        f[0] = fma(-Bm, y[0], A);
-        f[1] = fma(C, y[0], fma(-d[0], y[1], y[2]));
+    template <class Co>
+    __device__ static __forceinline__ void rhs(const Co& c, const double (&y)[N], double (&f)[N]) {
+        f[0] = fma(-c.get(cB), y[0], c.get(cA));
+        f[1] = fma(c.get(cC), y[0], fma(-c.get(cD), y[1], y[2]));
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            double v = fma(S[i], y[1 + i], -d[1 + i] * y[2 + i]);
+            double v = fma(c.get(cS + i), y[1 + i], -c.get(cD + 1 + i) * y[2 + i]);
             if (i < NS - 1) v += y[i < NS - 1 ? 3 + i : 2 + i];
             f[2 + i] = v;
         }
@@ -145,10 +168,13 @@ struct SuccModel {
     //   middle pivot       d_M  = Delta / (th_{M-1} ph_{M+1}),
     //                      Delta = a_M th_{M-1} ph_{M+1} - c^2 S_{M-1} th_{M-2} ph_{M+1} - c^2 S_M th_{M-1} ph_{M+2}
     // One reciprocal for all of {q0, th_0..th_{M-1}, ph_{M+1}..ph_NS, Delta} (NS + 2 numbers).
-    __device__ __forceinline__ void factor(double c, double (&F)[NF]) const {
-        double cs[NS], cc[NS];
+    template <class Co>
+    __device__ static __forceinline__ void factor(const Co& co, double c, double (&F)[NF]) {
+        double cs[NS], cc[NS], d[NS + 1];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) { cs[j] = c * S[j]; cc[j] = cs[j] * c; }
+        for (int j = 0; j < NS; ++j) { cs[j] = c * co.get(cS + j); cc[j] = cs[j] * c; }
+#pragma unroll
+        for (int j = 0; j <= NS; ++j) d[j] = co.get(cD + j);
         double th[NT];
         th[0] = fma(c, d[0], 1.0);
         if constexpr (NT > 1) th[1] = fma(fma(c, d[1], 1.0), th[0], -cc[0]);
@@ -165,7 +191,7 @@ struct SuccModel {
         double delta = fma(fma(c, d[MID], 1.0), tp, -(cc[MID - 1] * thm2) * ph[0]);
         if constexpr (NB > 0) delta = fma(-(cc[MID < NS ? MID : 0] * th[NT - 1]), ph[1], delta);
         double inv[NS + 2];
-        inv[0] = fma(c, Bm, 1.0);
+        inv[0] = fma(c, co.get(cB), 1.0);
 #pragma unroll
         for (int j = 0; j < NT; ++j) inv[1 + j] = th[j];
 #pragma unroll
@@ -173,7 +199,7 @@ struct SuccModel {
         inv[NS + 1] = delta;
         batch_invert<NS + 2>(inv);
         F[0] = inv[0];
-        F[1] = c * C;
+        F[1] = c * co.get(cC);
         F[2] = c;
         F[3] = tp * inv[NS + 1];
         F[O_IP] = inv[1];
@@ -188,7 +214,7 @@ struct SuccModel {
             F[O_CS + k] = cs[MID + k];
         }
     }
-    __device__ __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) const {
+    __device__ static __forceinline__ void solve(const double (&F)[NF], double (&x)[N]) {
         x[0] *= F[0];
         x[1] = fma(F[1], x[0], x[1]);
 #pragma unroll
@@ -206,17 +232,18 @@ struct SuccModel {
 };
 
 // ------------------------------------------------------------------------------------ kernel
-constexpr int TPS_BLOCK = 128;
 constexpr int TPS_WARPS = TPS_BLOCK / 32;
-constexpr int TPS_STASH = 32;          // systems per claimed batch (upper bound)
+constexpr int TPS_STASH = 24;          // systems per claimed batch (upper bound; two buffers of this size per warp)
 constexpr int TPS_RING = 32;           // finished systems parked per warp before they are written out
 
 // dynamic shared memory of one CTA (bytes); the host side mirrors this (launch_tps)
-__host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool scalar) {
+__host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool scalar, bool csmem) {
     size_t b = (size_t)TPS_WARPS * 2 * TPS_STASH * P * 8;        // parameter stash
+    if (csmem) b += (size_t)TPS_BLOCK * P * 8;                   // per-lane model coefficients (SmemCoef)
     b += (size_t)TPS_BLOCK * 16;                                 // per-lane system index and |params|^2
     b += (size_t)TPS_WARPS * 48;                                 // per-warp queue state (TpsQueue)
     if (scalar) b += (size_t)TPS_WARPS * TPS_RING * (4 * 8 + 8 + 16);
+    if (scalar) b += (size_t)TPS_BLOCK * 4 * 8;                  // per-lane residual sums (3) and group index
     b += (size_t)T * 8;
     if (scalar) b += (size_t)T * (P / 2) * 16;                   // {target, weight} table of a single-group job (n = P/2 states)
     if (!scalar) b += ((size_t)L * 2 + 7) & ~(size_t)7;
@@ -246,7 +273,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <class M, int MIN_BLOCKS, bool SCALAR>
+template <class M, int MIN_BLOCKS, bool SCALAR, bool CSMEM>
 __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const LocalArgs a) {
     constexpr int N = M::N, NF = M::NF, P = M::P;
     static_assert(2 * N == P, "tps_smem_bytes sizes the residual table with n = P/2");
@@ -262,6 +289,8 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     unsigned char* sp = smem_raw;
     double* const stash = (double*)sp + (size_t)wid * 2 * TPS_STASH * P;          // [2][TPS_STASH][P] of this warp
     sp += (size_t)TPS_WARPS * 2 * TPS_STASH * P * 8;
+    double* const lane_coef = (double*)sp;                                        // CSMEM: [P][TPS_BLOCK]
+    if constexpr (CSMEM) sp += (size_t)TPS_BLOCK * P * 8;
     long long* const lane_sys = (long long*)sp;  sp += TPS_BLOCK * 8;             // system index of every lane
     double* const lane_p2 = (double*)sp;         sp += TPS_BLOCK * 8;             // |physical params|^2 (score_fit's l2 term)
     volatile TpsQueue* const q = (volatile TpsQueue*)sp + wid;  sp += TPS_WARPS * sizeof(TpsQueue);
@@ -273,6 +302,10 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
         ring_sys = (long long*)sp + (size_t)wid * TPS_RING;      sp += (size_t)TPS_WARPS * TPS_RING * 8;
         ring_i = (int*)sp + (size_t)wid * TPS_RING * 4;          sp += (size_t)TPS_WARPS * TPS_RING * 16;
     }
+    // SCALAR: the residual sums of the system a lane is integrating live in shared memory ([4][TPS_BLOCK] columns: weighted
+    // SSR, sum |r|, sum r^2 (Morris Y: -, sum v, sum v^2), group index) — touched only when the lane lands on an output time
+    double* const lacc = (double*)sp + threadIdx.x;
+    if constexpr (SCALAR) sp += (size_t)TPS_BLOCK * 4 * 8;
     double2* const tw_s = (double2*)sp;          // SCALAR: the {target, weight} rows of a single-group job
     if constexpr (SCALAR) sp += (size_t)TN * 16;
     double* const tgrid = (double*)sp;           sp += (size_t)T * 8;
@@ -333,12 +366,12 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
 
     // ---- per-lane state
     bool active = false, exhausted = false;
-    M mdl;
+    typename std::conditional<CSMEM, SmemCoef, RegCoef<M::NC>>::type co;
+    if constexpr (CSMEM) co.p = lane_coef + threadIdx.x;
     double y[N];
     double t = 0.0;
     StepCtl ctl;
-    int kout = 0, nst = 0, nrej = 0, status = 0, grp = 0;
-    double acc_w = 0.0, acc_1 = 0.0, acc_2 = 0.0;      // SCALAR: weighted SSR, sum |r|, sum r^2 (Morris Y: -, sum v, sum v^2)
+    int kout = 0, nst = 0, nrej = 0, status = 0;
 
     // SCALAR: write out the parked systems, one per lane
     auto flush_ring = [&]() {
@@ -439,7 +472,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     double pv[P];
 #pragma unroll
                     for (int i = 0; i < P; ++i) { pv[i] = pr[i]; p2 = fma(pv[i], pv[i], p2); }
-                    mdl.load(pv);
+                    M::load(co, pv);
                 }
                 lane_sys[threadIdx.x] = sys;
                 lane_p2[threadIdx.x] = p2;
@@ -450,8 +483,8 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
 #pragma unroll
                     for (int i = 0; i < N; ++i) my_traj[i] = y[i];
                 } else {
-                    acc_w = acc_1 = acc_2 = 0.0;
-                    grp = (want_loss && a.group) ? a.group[sys] : 0;
+                    double acc_w = 0.0;
+                    const int grp = (want_loss && a.group) ? a.group[sys] : 0;
                     if (want_loss && a.lam != 0.0) {
                         // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423); theta = the caller's
                         // (possibly logarithmic) parameters
@@ -463,6 +496,8 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                             acc_w = fma(w, w, acc_w);
                         }
                     }
+                    lacc[0] = acc_w; lacc[TPS_BLOCK] = 0.0; lacc[2 * TPS_BLOCK] = 0.0;
+                    ((int*)(lacc + 3 * TPS_BLOCK))[0] = grp;
                 }
                 t = tgrid[0];
                 nst = nrej = status = 0;
@@ -470,7 +505,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 // initial step: 1% of the time scale max|y| / max|f|.  The maxima are taken on the high words of the doubles
                 // (monotone for non-negative values, 20 mantissa bits: plenty for a first guess the controller corrects).
                 double f0[N];
-                mdl.rhs(y, f0);
+                M::rhs(co, y, f0);
                 int my = 0, mf = 0;
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
@@ -513,31 +548,31 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     else if (hh > 0.5 * rem) hh = 0.5 * rem;
 
                     double F[NF];
-                    mdl.factor(hh * a.m.gamma, F);
+                    M::factor(co, hh * a.m.gamma, F);
                     double v[N], yn[N], er[N];
-                    mdl.rhs(y, v);
+                    M::rhs(co, y, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) v[i] *= hh;
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) yn[i] = fma(a.m.mu[0], v[i], y[i]);
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[1], v[i], yn[i]); er[i] = a.m.eps[1] * v[i]; }
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[2], v[i], yn[i]); er[i] = fma(a.m.eps[2], v[i], er[i]); }
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[3], v[i], yn[i]); er[i] = fma(a.m.eps[3], v[i], er[i]); }
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[4], v[i], yn[i]); er[i] = fma(a.m.eps[4], v[i], er[i]); }
-                    mdl.solve(F, v);
+                    M::solve(F, v);
 #pragma unroll
                     for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[5], v[i], yn[i]); er[i] = fma(a.m.eps[5], v[i], er[i]); }
                     if (a.m.nsol > 6) {                    // ROS6L: seventh solve (uniform over the grid)
-                        mdl.solve(F, v);
+                        M::solve(F, v);
 #pragma unroll
                         for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[6], v[i], yn[i]); er[i] = fma(a.m.eps[6], v[i], er[i]); }
                     }
@@ -549,27 +584,28 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], rtolf, floorf_, kapf, atolf));
                         chk += yn[i];
                     }
-                    if (!(fabs(chk) < 3.0e38) || !(err < 3.0e38f)) {     // NaN/inf, or beyond the FP32 range of the error scale
-                        status = 3;
-                    } else if (err <= 1.0f) {
-                        ++nst;
-                        const double hprop = ctl.h;
-                        const double hnew = ctl_accept(ctl, hh, err, a.m.expo);
-                        ctl.h = (hh < hprop) ? fmax(hnew, fmin(hprop, 6.0 * hh)) : hnew;
+                    // Accept / reject without branches (a branch here splits the warp into landing and non-landing lanes
+                    // that then walk the same code twice): everything is a select on `acc`.
+                    const bool finite = (fabs(chk) < 3.0e38) && (err < 3.0e38f);   // else NaN/inf, or beyond the FP32 range of the error scale
+                    const bool acc = finite && (err <= 1.0f);
+                    const double hprop = ctl.h;
+                    double hnew = ctl_step(ctl, hh, err, a.m.expo, acc);
+                    if (acc && hh < hprop) hnew = fmax(hnew, fmin(hprop, 6.0 * hh));     // the output grid shortened this step
+                    ctl.h = hnew;
 #pragma unroll
-                        for (int i = 0; i < N; ++i) y[i] = yn[i];
-                        if (land) { t = tout; store = true; }
-                        else t += hh;
-                    } else {
-                        ++nrej;
-                        ctl.h = ctl_reject(ctl, hh, err, a.m.expo);
-                        if (ctl.h < 1e-14 * fmax(1.0, fabs(t))) status = 2;
-                    }
+                    for (int i = 0; i < N; ++i) y[i] = acc ? yn[i] : y[i];
+                    t = acc ? (land ? tout : t + hh) : t;
+                    store = acc && land;
+                    nst += acc ? 1 : 0;
+                    nrej += acc ? 0 : 1;
+                    if (!finite) status = 3;
+                    else if (!acc && hnew < 1e-14 * fmax(1.0, fabs(t))) status = 2;
                 }
                 if (store) {
                     if constexpr (SCALAR) {
                         // the residual sums of this output row, straight from the registers.  np.clip(sol, 0, None) on the
                         // sign bit (integer pipe; NaN stays NaN as in numpy).
+                        double acc_1 = lacc[TPS_BLOCK], acc_2 = lacc[2 * TPS_BLOCK];
                         if (a.ymode) {
 #pragma unroll
                             for (int i = 0; i < N; ++i) {
@@ -580,8 +616,10 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                             // row kout of the {target, weight} table (trajectory order: one base address, 16-byte loads);
                             // flat (models/distmod.py:124-134) = [sol[5:,0] | sol[:,1] | sol[:,2:].T]: the RNA column only from row 5
                             // (generic pointer: the shared-memory copy of a single-group job, the L1-cached global table otherwise)
+                            const int grp = ((const int*)(lacc + 3 * TPS_BLOCK))[0];
                             const double2* row = tw_in_smem ? tw_s + kout * N : a.tw + ((size_t)grp * TN + kout * N);
                             if (a.isigma != nullptr) {
+                                double acc_w = lacc[0];
 #pragma unroll
                                 for (int i = 0; i < N; ++i) {
                                     if (i == 0 && kout < RNA_OFFSET) continue;
@@ -592,6 +630,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                                     acc_2 = fma(dlt, dlt, acc_2);
                                     acc_w = fma(w, w, acc_w);
                                 }
+                                lacc[0] = acc_w;
                             } else {                       // unit weights: the weighted sum is acc_2 (added when the system is written out)
 #pragma unroll
                                 for (int i = 0; i < N; ++i) {
@@ -602,6 +641,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                                 }
                             }
                         }
+                        lacc[TPS_BLOCK] = acc_1; lacc[2 * TPS_BLOCK] = acc_2;
                     } else {
                         double* o = my_traj + kout * N;
 #pragma unroll
@@ -623,7 +663,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 if (finished) {
                     const int slot = nfin + __popc(fin & lt_mask);
                     ring_sys[slot] = lane_sys[threadIdx.x];
-                    ring_v[slot * 4 + 0] = acc_w; ring_v[slot * 4 + 1] = acc_1; ring_v[slot * 4 + 2] = acc_2;
+                    ring_v[slot * 4 + 0] = lacc[0]; ring_v[slot * 4 + 1] = lacc[TPS_BLOCK]; ring_v[slot * 4 + 2] = lacc[2 * TPS_BLOCK];
                     ring_v[slot * 4 + 3] = lane_p2[threadIdx.x];
                     ring_i[slot * 4 + 0] = status; ring_i[slot * 4 + 1] = nst; ring_i[slot * 4 + 2] = nrej;
                     active = false;

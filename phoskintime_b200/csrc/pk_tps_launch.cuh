@@ -7,15 +7,26 @@
 
 namespace pkh {
 
-// Resident CTAs per SM the register allocator must allow with ZERO spill and no stack frame (checked in ptxas.log by the
-// Makefile): n <= 5 states fit 128 registers (4 CTAs x 128 lanes), mid sizes get 168 (3 CTAs), the rest 255.
-template <class M> constexpr int tps_min_blocks() { return M::N <= 5 ? 4 : (M::N <= 7 ? 3 : 2); }
+// Launch configuration per model size: resident CTAs per SM the register allocator must allow with ZERO spill and no
+// stack frame (checked in ptxas.log by the Makefile), and whether the model's rate coefficients live in shared memory
+// (SmemCoef: 2P registers less per lane).  n <= 5 states fit 128 registers with everything in registers (4 CTAs x 128
+// lanes); 6-7 states reach 4 CTAs with the coefficients in shared memory (16 instead of 12 warps per SM for the
+// latency-bound step loop); larger systems keep 2 CTAs.
+struct TpsCfg { int min_blocks; bool csmem; };
+template <class M> constexpr TpsCfg tps_cfg() {
+#ifdef PK_TPS_CFG_OVERRIDE
+    return TpsCfg{PK_TPS_CFG_OVERRIDE};
+#else
+    return M::N <= 4 ? TpsCfg{4, false} : (M::N <= 7 ? TpsCfg{4, true} : TpsCfg{2, false});
+#endif
+}
 
 template <class M, bool SCALAR>
 cudaError_t launch_tps_mode(pk_handle_s* h, pk::LocalArgs a) {
     using pk::TPS_BLOCK;
-    const size_t smem = pk::tps_smem_bytes(M::P, a.T, a.L, SCALAR);
-    auto kern = pk::local_tps_kernel<M, tps_min_blocks<M>(), SCALAR>;
+    constexpr TpsCfg cfg = tps_cfg<M>();
+    const size_t smem = pk::tps_smem_bytes(M::P, a.T, a.L, SCALAR, cfg.csmem);
+    auto kern = pk::local_tps_kernel<M, cfg.min_blocks, SCALAR, cfg.csmem>;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -6,5 +6,8 @@
 #ifndef DEV_MINB
 #define DEV_MINB 3
 #endif
-template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, true>(const pk::LocalArgs);
-template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, false>(const pk::LocalArgs);
+#ifndef DEV_CSMEM
+#define DEV_CSMEM false
+#endif
+template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, true, DEV_CSMEM>(const pk::LocalArgs);
+template __global__ void pk::local_tps_kernel<pk::DEV_MODEL, DEV_MINB, false, DEV_CSMEM>(const pk::LocalArgs);
