@@ -241,6 +241,7 @@ __host__ __device__ constexpr size_t tps_smem_bytes(int P, int T, int L, bool sc
     size_t b = (size_t)TPS_WARPS * 2 * TPS_STASH * P * 8;        // parameter stash
     if (csmem) b += (size_t)TPS_BLOCK * P * 8;                   // per-lane model coefficients (SmemCoef)
     b += (size_t)TPS_BLOCK * 16;                                 // per-lane system index and |params|^2
+    b += (size_t)TPS_BLOCK * 16;                                 // per-lane controller record (TpsCtlRec)
     b += (size_t)TPS_WARPS * 48;                                 // per-warp queue state (TpsQueue)
     if (scalar) b += (size_t)TPS_WARPS * TPS_RING * (4 * 8 + 8 + 16);
     if (scalar) b += (size_t)TPS_BLOCK * 4 * 8;                  // per-lane residual sums (3) and group index
@@ -258,6 +259,14 @@ struct TpsQueue {
     int pad[4];
 };
 static_assert(sizeof(TpsQueue) == 48, "tps_smem_bytes reserves 48 bytes per warp");
+
+// Step-controller memory of one lane (last accepted step and its error, first-step / rejected-last flags, rejected-step
+// count): read and written once per step attempt, so it lives in shared memory, not in registers.
+struct __align__(16) TpsCtlRec {
+    float hacc, erracc;
+    int flags;                    // bit 0: at least one step accepted, bit 1: the last attempt was rejected
+    int nrej;
+};
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     if constexpr (CSMEM) sp += (size_t)TPS_BLOCK * P * 8;
     long long* const lane_sys = (long long*)sp;  sp += TPS_BLOCK * 8;             // system index of every lane
     double* const lane_p2 = (double*)sp;         sp += TPS_BLOCK * 8;             // |physical params|^2 (score_fit's l2 term)
+    TpsCtlRec* const lrec = (TpsCtlRec*)sp + threadIdx.x;  sp += TPS_BLOCK * sizeof(TpsCtlRec);
     volatile TpsQueue* const q = (volatile TpsQueue*)sp + wid;  sp += TPS_WARPS * sizeof(TpsQueue);
     double* ring_v = nullptr;                    // [TPS_RING][4]: ssr, sum |r|, sum r^2, |params|^2
     long long* ring_sys = nullptr;
@@ -327,12 +337,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
 
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
-    double* warp_traj = nullptr;
-    double* my_traj = nullptr;
-    if constexpr (!SCALAR) {
-        warp_traj = a.traj + ((size_t)blockIdx.x * TPS_BLOCK + (threadIdx.x & ~31)) * TN;
-        my_traj = warp_traj + (size_t)lane * TN;
-    }
+    // !SCALAR: trajectory slot of lane l of this CTA = a.traj + (blockIdx.x * TPS_BLOCK + l) * TN (recomputed where it is
+    // used: two pointers less to keep across the step body)
+    auto traj_slot = [&](int thread) { return a.traj + ((size_t)blockIdx.x * TPS_BLOCK + thread) * TN; };
 
     // ---- work queue state of the warp (uniform across its lanes; the rarely touched part lives in *q)
     int cur_cnt = 0, cur_taken = 0, pb = 0;
@@ -370,8 +377,8 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
     if constexpr (CSMEM) co.p = lane_coef + threadIdx.x;
     double y[N];
     double t = 0.0;
-    StepCtl ctl;
-    int kout = 0, nst = 0, nrej = 0, status = 0;
+    double hprop = 0.0;                       // step-size proposal of the controller
+    int kout = 0, natt = 0, status = 0;       // next output row, step attempts (accepted + rejected), status
 
     // SCALAR: write out the parked systems, one per lane
     auto flush_ring = [&]() {
@@ -481,7 +488,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 for (int i = 0; i < N; ++i) y[i] = y0[i];
                 if constexpr (!SCALAR) {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) my_traj[i] = y[i];
+                    for (int i = 0; i < N; ++i) traj_slot(threadIdx.x)[i] = y[i];
                 } else {
                     double acc_w = 0.0;
                     const int grp = (want_loss && a.group) ? a.group[sys] : 0;
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     ((int*)(lacc + 3 * TPS_BLOCK))[0] = grp;
                 }
                 t = tgrid[0];
-                nst = nrej = status = 0;
+                natt = status = 0;
                 kout = 1;
                 // initial step: 1% of the time scale max|y| / max|f|.  The maxima are taken on the high words of the doubles
                 // (monotone for non-negative values, 20 mantissa bits: plenty for a first guess the controller corrects).
@@ -513,8 +520,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     mf = max(mf, __double2hiint(f0[i]) & 0x7fffffff);
                 }
                 const float d0 = (float)__hiloint2double(my, 0), d1 = (float)__hiloint2double(mf, 0);
-                double h0 = (!(d0 > 1e-30f) || !(d1 > 1e-30f) || !(d0 < 3.0e38f) || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)__fdividef(d0, d1);
-                ctl = StepCtl{h0, (float)h0, 1.0f, 0, 0};
+                double h0 = (!(d0 > 1e-30f) || !(d1 > 1e-30f) || !(d0 < 3.0e38f) || !(d1 < 3.0e38f)) ? 1e-6 : 0.01 * (double)(d0 * rcp_ftz(d1));
+                hprop = h0;
+                *lrec = TpsCtlRec{(float)h0, 1.0f, 0, 0};
                 active = true;
             }
             cur_taken += min(__popc(need), avail);
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 if (!(rem > 0.0)) {
                     store = true;                                  // repeated output time
                 } else {
-                    double hh = ctl.h;
+                    double hh = hprop;
                     bool land = false;
                     if (LAND_STRETCH * hh >= rem) { hh = rem; land = true; }
                     else if (hh > 0.5 * rem) hh = 0.5 * rem;
@@ -577,27 +585,42 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         for (int i = 0; i < N; ++i) { yn[i] = fma(a.m.mu[6], v[i], yn[i]); er[i] = fma(a.m.eps[6], v[i], er[i]); }
                     }
                     float err = 0.0f;
-                    double chk = 0.0;                      // NaN/inf anywhere in y_new poisons the sum
+                    int ymax = 0;                          // largest |y_new| by its high word (integer pipe): NaN/inf and the FP32 range
                     const float rtolf = (float)a.rtol, floorf_ = (float)a.rtol_floor, kapf = (float)a.kappa, atolf = (float)a.atol;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         err = fmaxf(err, err_ratio_inc(er[i], y[i], yn[i], rtolf, floorf_, kapf, atolf));
-                        chk += yn[i];
+                        ymax = max(ymax, __double2hiint(yn[i]) & 0x7fffffff);
                     }
                     // Accept / reject without branches (a branch here splits the warp into landing and non-landing lanes
                     // that then walk the same code twice): everything is a select on `acc`.
-                    const bool finite = (fabs(chk) < 3.0e38) && (err < 3.0e38f);   // else NaN/inf, or beyond the FP32 range of the error scale
+                    // 0x47ec0000 = high word of 2.98e38: beyond it (or NaN/inf) the FP32 error scale is meaningless
+                    const bool finite = (ymax < 0x47ec0000) && (err < 3.0e38f);
                     const bool acc = finite && (err <= 1.0f);
-                    const double hprop = ctl.h;
-                    double hnew = ctl_step(ctl, hh, err, a.m.expo, acc);
+                    // step controller (pk_common.cuh: elementary + Gustafsson's predictive factor), state in *lrec
+                    TpsCtlRec rec = *lrec;
+                    float fac = ctl_factor(err, a.m.expo);
+                    const float hf = (float)hh;
+                    {
+                        const float r = err * err * rcp_ftz(rec.erracc);
+                        float fg = rec.hacc * rcp_ftz(hf) * pow_ftz(r, a.m.expo) * CTL_INV_SAFE;
+                        fg = fmaxf(CTL_FAC_GROW, fminf(CTL_FAC_SHRINK, fg));
+                        fac = (acc && (rec.flags & 1)) ? fmaxf(fac, fg) : fac;
+                    }
+                    double hnew = hh * (double)rcp_ftz(fac);
+                    hnew = (acc && (rec.flags & 2)) ? fmin(hnew, hh) : hnew;
                     if (acc && hh < hprop) hnew = fmax(hnew, fmin(hprop, 6.0 * hh));     // the output grid shortened this step
-                    ctl.h = hnew;
+                    hprop = hnew;
+                    rec.hacc = acc ? hf : rec.hacc;
+                    rec.erracc = acc ? fmaxf(1.0e-2f, err) : rec.erracc;
+                    rec.flags = acc ? 1 : (rec.flags | 2);
+                    rec.nrej += acc ? 0 : 1;
+                    *lrec = rec;
 #pragma unroll
                     for (int i = 0; i < N; ++i) y[i] = acc ? yn[i] : y[i];
                     t = acc ? (land ? tout : t + hh) : t;
                     store = acc && land;
-                    nst += acc ? 1 : 0;
-                    nrej += acc ? 0 : 1;
+                    ++natt;
                     if (!finite) status = 3;
                     else if (!acc && hnew < 1e-14 * fmax(1.0, fabs(t))) status = 2;
                 }
@@ -643,13 +666,13 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         }
                         lacc[TPS_BLOCK] = acc_1; lacc[2 * TPS_BLOCK] = acc_2;
                     } else {
-                        double* o = my_traj + kout * N;
+                        double* o = traj_slot(threadIdx.x) + kout * N;
 #pragma unroll
                         for (int i = 0; i < N; ++i) o[i] = y[i];
                     }
                     ++kout;
                 }
-                if (status == 0 && kout < T && nst + nrej >= a.max_steps) status = 1;      // outputs still missing
+                if (status == 0 && kout < T && natt >= a.max_steps) status = 1;      // outputs still missing
             }
             finished = (kout >= T) || (status != 0);
         }
@@ -665,7 +688,7 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                     ring_sys[slot] = lane_sys[threadIdx.x];
                     ring_v[slot * 4 + 0] = lacc[0]; ring_v[slot * 4 + 1] = lacc[TPS_BLOCK]; ring_v[slot * 4 + 2] = lacc[2 * TPS_BLOCK];
                     ring_v[slot * 4 + 3] = lane_p2[threadIdx.x];
-                    ring_i[slot * 4 + 0] = status; ring_i[slot * 4 + 1] = nst; ring_i[slot * 4 + 2] = nrej;
+                    ring_i[slot * 4 + 0] = status; ring_i[slot * 4 + 1] = natt - lrec->nrej; ring_i[slot * 4 + 2] = lrec->nrej;
                     active = false;
                 }
                 nfin += nnew;
@@ -677,10 +700,11 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             fin &= fin - 1;
             const int fstatus = __shfl_sync(FULL, status, f);
             const int fvalid = __shfl_sync(FULL, kout, f);          // outputs 0..fvalid-1 were produced
-            const int fnst = __shfl_sync(FULL, nst, f), fnrej = __shfl_sync(FULL, nrej, f);
+            const int fnatt = __shfl_sync(FULL, natt, f);
             __syncwarp();                                           // the owner's trajectory stores are visible
+            const int fnrej = lrec[f - lane].nrej, fnst = fnatt - fnrej;
             const size_t fsys = (size_t)lane_sys[(threadIdx.x & ~31) + f];
-            const double* tr = warp_traj + (size_t)f * TN;
+            const double* tr = traj_slot((threadIdx.x & ~31) + f);
             const double* y0 = a.y0 + (a.y0_stride ? fsys * (size_t)a.y0_stride : 0);
             const int g = (want_loss && a.group) ? a.group[fsys] : 0;
             const double* tg = want_loss ? a.target + (size_t)g * a.L : nullptr;
