@@ -346,6 +346,44 @@ def test_large_batch_properties(engine):
     assert float(drift.max()) < 1.0
 
 
+@pytest.mark.parametrize("model,ns", [("succmod", 5), ("distmod", 3)])
+def test_million_adversarial_draws_stay_inside_the_parity_bound(engine, model, ns):
+    """2^20 parameter sets drawn log-uniformly over the reference's fit box [1e-2, 20] (config.toml:189-195) — a quarter
+    with random per-system initial states, 5 % with zeroed rates (knockouts), 5 % with all rates equal to a few ulps
+    (confluent eigenvalues) — at the library defaults against a tight run of a DIFFERENT integrator (RODAS4 at 1e-10 /
+    1e-14), which is itself anchored to the oracle's exact solution (matrix exponential) on a sample.  Every state at
+    every output time within the parity bound 1e-6*|ref| + 1e-9."""
+    import torch
+    from phoskintime_b200.steady import initial_condition
+    B = 1 << 20
+    n, P, L = __import__("phoskintime_b200").local_dims(model, ns, 14)
+    gen = torch.Generator(device="cuda").manual_seed(2024 + ns)
+    lo, hi = np.log(1e-2), np.log(20.0)
+    p = torch.exp(torch.rand((B, P), generator=gen, device="cuda", dtype=torch.float64) * (hi - lo) + lo)
+    q = B // 20
+    zero = torch.rand((q, P), generator=gen, device="cuda", dtype=torch.float64) < 0.25
+    zero[:, 1] = False                                       # (B = 0: mRNA grows without bound; the reference never fits that)
+    p[:q] = torch.where(zero, torch.zeros((), device="cuda", dtype=torch.float64), p[:q])
+    p[q:2 * q] = p[q:2 * q, :1] * (1.0 + 4e-16 * torch.randint(-3, 4, (q, P), generator=gen, device="cuda").double())
+    y0 = torch.from_numpy(np.asarray(initial_condition(ns, model))).cuda().repeat(B, 1)
+    y0[-B // 4:] = torch.rand((B // 4, n), generator=gen, device="cuda", dtype=torch.float64) * 1.4 + 0.1
+    t = torch.from_numpy(T14).cuda()
+    r = engine.solve_local_batch(model, p, y0, ns, t, want=("sol",))
+    assert int((r["status"] != 0).sum()) == 0
+    ref = engine.solve_local_batch(model, p, y0, ns, t, want=("sol",), method="rodas4", rtol=1e-10, atol=1e-14)
+    assert int((ref["status"] != 0).sum()) == 0
+    ratio = ((r["sol"] - ref["sol"]).abs() / (1e-6 * ref["sol"].abs() + 1e-9)).amax(dim=(1, 2))
+    worst = float(ratio.max())
+    assert worst < 1.0, (worst, int(ratio.argmax()))
+    # anchor: the tight run against the oracle's exact solution on the 64 worst and 192 random systems
+    idx = torch.cat([ratio.topk(64).indices, torch.randint(0, B, (192,), generator=gen, device="cuda")]).cpu().numpy()
+    pc, yc, rc, dc = p[idx].cpu().numpy(), y0[idx].cpu().numpy(), ref["sol"][idx].cpu().numpy(), r["sol"][idx].cpu().numpy()
+    for j in range(len(idx)):
+        ex = om.exact_linear(model, pc[j], yc[j], ns, T14)
+        assert _close(rc[j], ex, 1e-7, 1e-10).all(), j
+        assert _close(dc[j], ex, 1e-6, 1e-9).all(), j
+
+
 def test_knockout_sweep_is_one_batched_launch(engine):
     """paramest/core.py:144-187: every knockout setting solved in one launch equals the oracle's solve of the
     same modified parameter vector."""

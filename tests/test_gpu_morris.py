@@ -50,6 +50,30 @@ def test_config1_morris_ranking_identical_to_reference_path(engine):
     assert np.allclose(Si["mu"], ref["mu"], rtol=1e-4, atol=1e-8)
 
 
+def test_config1_morris_full_size_n1000(engine):
+    """BASELINE configs[0] at FULL size: distributive, 3 psites, Morris N = 1000 trajectories x (D + 1) = 11 000 rows at the
+    14 experimental time points.  The same X goes through the reference path on the CPU (oracle port of `solve_ode`:
+    LSODA at its defaults + `_compute_Y`) and through ONE launch on the GPU; identical mu* / sigma ranking, Y within
+    the parity bound."""
+    from phoskintime_b200 import sensitivity
+    from phoskintime_b200.steady import initial_condition
+    ns, N, levels = 3, 1000, 400
+    theta = np.random.default_rng(1).uniform(0.05, 3.0, 10)
+    y0 = np.asarray(initial_condition(ns, "distmod"))
+    prob = sensitivity.define_sensitivity_problem_ds(ns, theta)
+    X = sensitivity.morris_sample(prob, N, levels, seed=42)
+    assert X.shape == (11000, 10)
+    Si, _ = sensitivity.sensitivity_analysis(theta, om.TIME_POINTS, ns, y0, "distmod", N=N, num_levels=levels,
+                                             X=X, engine=engine)
+    Y_ref = np.array([ol.compute_Y(om.solve_ode("distmod", x, y0, ns, om.TIME_POINTS)[0], ns) for x in X])
+    assert np.all(np.abs(Si["Y"] - Y_ref) <= 1e-6 * np.abs(Y_ref) + 1e-6)
+    ref = omor.analyze(X, Y_ref, 10, levels, scaled=True)
+    for k in ("mu_star", "sigma"):
+        assert np.array_equal(np.argsort(Si[k]), np.argsort(ref[k])), k
+        assert np.allclose(Si[k], ref[k], rtol=1e-4, atol=1e-9)
+    assert np.allclose(Si["mu"], ref["mu"], rtol=1e-4, atol=1e-8)
+
+
 def test_sensitivity_top_k_selection(engine):
     from phoskintime_b200 import sensitivity
     ns, N, levels = 3, 40, 400
