@@ -60,7 +60,7 @@ typedef struct pk_local_job {
     const double* y0;       /* [n] if y0_stride==0 else [B,n] with row stride y0_stride doubles  */
     int64_t y0_stride;
     const double* t;        /* [T] strictly increasing                                           */
-    double rtol, atol;      /* <=0 -> defaults of the method: ROS6L 2e-5 / 2e-9, ROS5L and RODAS4 2e-6 / 2e-9 */
+    double rtol, atol;      /* <=0 -> defaults of the method: ROS6L 2e-5 / 2e-11, ROS5L and RODAS4 2e-6 / 2e-9 */
     int32_t max_steps;      /* per system, <=0 -> 100000                                         */
     int32_t normalize;      /* NORMALIZE_MODEL_OUTPUT (models/distmod.py:115-122)                */
     int32_t log_params;     /* 1: params hold log-values, model uses exp(params) (normest.py:54) */
@@ -136,6 +136,21 @@ int pk_ros6l_coeffs(double gamma, double* mu7, double* eps7);   /* the seven-sol
  * runs on a second, high-priority stream while piece c+1 integrates — only the last piece's gather is exposed.
  * recv_dev [world*B] is filled rank-major (the layout pk_allgather_f64 produces).  Device buffers only. */
 int pk_local_solve_allgather(pk_handle_t h, const pk_local_job* job, int32_t which, int32_t chunks, double* recv_dev);
+
+/* Precondition of pk_local_solve_allgather: EVERY rank passes the same job->B (the piece boundaries and the send
+ * counts of the collectives are derived from it) and recv_dev holds world*B doubles; ranks with fewer systems pad. */
+
+/* The same collective WITHOUT a collective call — the replacement for the reference's pickled futures
+ * (sensitivity/analysis.py:241-259) when all ranks sit on one NVSwitch: every rank owns a symmetric buffer of
+ * [world][slots_per_rank] doubles, maps every peer's buffer (CUDA IPC; the 64-byte handles travel through the caller's
+ * process group), and the solve kernel stores each finished system's scalar straight into all `world` buffers over
+ * NVLink as the system completes.  No staging, no exposed tail; the call ends with an 8-byte rendezvous.  Ranks may
+ * pass different job->B (<= slots_per_rank): rank r's values land at [r*slots_per_rank, r*slots_per_rank + B). */
+int pk_sym_alloc(pk_handle_t h, int64_t slots_per_rank, char* handle_out64);
+int pk_sym_open(pk_handle_t h, const char* handles_world_x64);            /* rank-major, 64 bytes each */
+int pk_sym_buffer(pk_handle_t h, double** local_dev, int64_t* slots_per_rank);
+int pk_sym_free(pk_handle_t h);
+int pk_local_solve_gather_p2p(pk_handle_t h, const pk_local_job* job, int32_t which);
 
 int pk_nccl_unique_id(char* out128);
 int pk_nccl_init(pk_handle_t h, const char* id128, int world, int rank);

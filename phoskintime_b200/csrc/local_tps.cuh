@@ -420,13 +420,16 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 if (a.out_nsteps) a.out_nsteps[fs] = ring_i[lane * 4 + 1];
                 if (a.out_nrej) a.out_nrej[fs] = ring_i[lane * 4 + 2];
                 if (a.out_ssr) a.out_ssr[fs] = ssr;
+                double shared_v = ssr;                             // the scalar that also goes to the peers
                 if (a.out_score) {
                     // score_fit (config/config.py:176-226) with r = |target - pred| / L
                     const double invL = 1.0 / (double)a.L;
                     const double r1 = s1 * invL, r2 = s2 * invL * invL;
                     const double mean_r2 = r2 * invL, mae = r1 * invL;
-                    a.out_score[fs] = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                    const double sc = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
                                       a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
+                    a.out_score[fs] = sc;
+                    if (a.peer_which == 0) shared_v = sc;
                 }
                 if (a.out_Y) {
                     const double len = (double)TN, mean = s1 / len;
@@ -438,7 +441,10 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         default: yv = sqrt(s2); break;
                     }
                     a.out_Y[fs] = yv;
+                    if (a.peer_which == 2) shared_v = yv;
                 }
+                // fused gather: 8-byte stores straight into every rank's result buffer (NVLink peer memory)
+                for (int r = 0; r < a.n_peer; ++r) a.peer[r][a.peer_base + fs] = shared_v;
             }
             __syncwarp();
             nfin = 0;
@@ -787,13 +793,16 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 if (a.out_nsteps) a.out_nsteps[fsys] = fnst;
                 if (a.out_nrej) a.out_nrej[fsys] = fnrej;
                 if (a.out_ssr) a.out_ssr[fsys] = ssr;
+                double shared_v = ssr;
                 if (a.out_score) {
                     // score_fit (config/config.py:176-226) with r = |target - pred| / L
                     const double invL = 1.0 / (double)a.L;
                     const double r1 = sr * invL, r2 = sr2 * invL * invL;
                     const double mean_r2 = r2 * invL, mae = r1 * invL;
-                    a.out_score[fsys] = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
-                                        a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
+                    const double sc = a.w_delta * r2 + a.w_alpha * sqrt(mean_r2) + a.w_beta * mae +
+                                      a.w_gamma * (mean_r2 - mae * mae) + a.w_mu * sqrt(p2) / (double)P;
+                    a.out_score[fsys] = sc;
+                    if (a.peer_which == 0) shared_v = sc;
                 }
                 if (want_y) {
                     const double len = (double)TN, mean = s1 / len;
@@ -806,7 +815,9 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                         default: yv = sqrt(s2); break;
                     }
                     a.out_Y[fsys] = yv;
+                    if (a.peer_which == 2) shared_v = yv;
                 }
+                for (int r = 0; r < a.n_peer; ++r) a.peer[r][a.peer_base + fsys] = shared_v;
             }
         }
         if (finished) active = false;

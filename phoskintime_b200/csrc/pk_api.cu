@@ -265,12 +265,13 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw, &h->bar};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
                        &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
     for (DevBuf* b : gbufs) b->release();
     pkh::release_global_topologies(h);
+    pk_sym_free(h);
     if (h->counter) cudaFree(h->counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -375,7 +376,10 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     // solution — ROS5L/RODAS4 2e-6/2e-9, ROS6L 2e-5/2e-9 (error <= 0.15 of the parity bound at ~40 % fewer steps; the
     // absolute part stays at 2e-9: the parity bound's own absolute term is 1e-9, components that decay towards zero need it)
     a.rtol = j->rtol > 0 ? j->rtol : (ros6 ? 2e-5 : 2e-6);
-    a.atol = j->atol > 0 ? j->atol : 2e-9;
+    // ROS6L: atol 2e-11 — measured on the 1 M succ-5 bench systems (tools/dev/atol_scan.py): states down to 2e-8 occur, and the
+    // max PURE relative error (north star: <= 1e-6) is 2.5e-5 at atol 2e-9, 2.1e-6 at 1e-10, 3.4e-7 at 2e-11, for 42.1 ->
+    // 42.7 steps per solve (+2 % kernel time)
+    a.atol = j->atol > 0 ? j->atol : (ros6 ? 2e-11 : 2e-9);
     // ROS6L: tolerance tightened to rtol/20 where the solution is (nearly) stationary — err_ratio_inc, pk_common.cuh.
     // (kappa, floor) scanned on B200 over 2^18 restarts near steady state (tools/dbg_semigroup.py): worst deviation
     // 1.25 / 0.82 / 0.33 of the parity bound at (1e-2, 1/10) / (4e-3, 1/10) / (4e-3, 1/20); ROS5L at 2e-6: 0.55.
@@ -427,6 +431,13 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         a.params = j->params; a.y0 = j->y0; a.t = j->t;
         a.target = j->target; a.sigma = j->sigma; a.group = j->group;
         if (tps_path && want_loss) CK(tps_prep(a.target, a.sigma));
+        if (h->p2p_which >= 0) {
+            if (!tps_path) return fail("pk_local_solve_gather_p2p: only the thread-per-system kernels store to peer memory");
+            a.n_peer = h->world;
+            a.peer_which = h->p2p_which;
+            a.peer_base = (long long)h->rank * h->sym_slots;
+            for (int r = 0; r < h->world; ++r) a.peer[r] = h->sym_peer[r];
+        }
         a.out_sol = j->out_sol; a.out_flat = j->out_flat; a.out_Y = j->out_Y; a.out_ssr = j->out_ssr;
         a.out_score = j->out_score; a.out_status = j->out_status; a.out_nsteps = j->out_nsteps;
         a.out_nrej = j->out_nrej;
@@ -458,6 +469,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
             pk::LocalArgs ac = a;
             ac.B = (long long)cnt;
             ac.params += o * P;
+            ac.peer_base += (long long)o;
             if (j->y0_stride) ac.y0 += o * j->y0_stride;
             if (ac.group) ac.group += o;
             if (ac.out_sol) ac.out_sol += o * TN;
@@ -489,6 +501,15 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
             }
         }
         CK(cudaEventRecord(h->ev1, st));
+        if (h->p2p_which >= 0 && h->world > 1) {
+            // Closing rendezvous of the peer-memory gather: a kernel's peer stores are performed when the kernel
+            // completes, so once EVERY rank has passed this point every rank's buffer is complete.  One 8-byte NCCL
+            // all-gather on the compute stream is that rendezvous (the payload itself never goes through NCCL).
+            CK(h->bar.ensure(2 * (size_t)h->world * sizeof(double)));
+            double* bb = (double*)h->bar.p;
+            int r = g_nccl.AllGather(bb + h->world + h->rank, bb, 1, NCCL_FLOAT64, h->comm, st);
+            if (r != 0) return fail(std::string("ncclAllGather (rendezvous): ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+        }
         if (ag) {                                   // join the collective stream back into the compute stream
             CK(cudaEventRecord(h->ev_in[0], h->s_out));
             CK(cudaStreamWaitEvent(st, h->ev_in[0], 0));
@@ -729,6 +750,74 @@ int pk_local_solve_allgather(pk_handle_t h, const pk_local_job* job, int32_t whi
     h->ag_chunks = chunks > 0 ? chunks : 4;
     const int rc = pk_local_solve_batch(h, job);
     h->ag_recv = nullptr;
+    return rc;
+}
+
+// ---- peer-memory gather: symmetric buffers mapped through CUDA IPC, filled by the solve kernel itself
+int pk_sym_free(pk_handle_t h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (int r = 0; r < pk_handle_s::MAX_PEERS; ++r) {
+        if (h->sym_peer[r] && h->sym_peer[r] != h->sym_local) cudaIpcCloseMemHandle(h->sym_peer[r]);
+        h->sym_peer[r] = nullptr;
+    }
+    if (h->sym_local) cudaFree(h->sym_local);
+    h->sym_local = nullptr;
+    h->sym_slots = 0;
+    h->sym_mapped = false;
+    return 0;
+}
+
+int pk_sym_alloc(pk_handle_t h, int64_t slots_per_rank, char* handle_out64) {
+    if (!h || slots_per_rank < 1 || !handle_out64) return fail("pk_sym_alloc: bad argument");
+    if (h->world > pk_handle_s::MAX_PEERS) return fail("pk_sym_alloc: at most 8 ranks (one NVSwitch domain)");
+    pk_sym_free(h);
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc(&h->sym_local, (size_t)h->world * (size_t)slots_per_rank * sizeof(double)));
+    h->sym_slots = slots_per_rank;
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(mh) == 64, "CUDA IPC handles are 64 bytes");
+    CK(cudaIpcGetMemHandle(&mh, h->sym_local));
+    memcpy(handle_out64, &mh, 64);
+    if (h->world == 1) { h->sym_peer[0] = h->sym_local; h->sym_mapped = true; }
+    return 0;
+}
+
+int pk_sym_open(pk_handle_t h, const char* handles) {
+    if (!h || !handles) return fail("pk_sym_open: bad argument");
+    if (!h->sym_local) return fail("pk_sym_open: pk_sym_alloc first");
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) { h->sym_peer[r] = h->sym_local; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + 64 * (size_t)r, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->sym_peer[r] = (double*)p;
+    }
+    h->sym_mapped = true;
+    return 0;
+}
+
+int pk_sym_buffer(pk_handle_t h, double** local_dev, int64_t* slots_per_rank) {
+    if (!h) return fail("null handle");
+    if (local_dev) *local_dev = h->sym_local;
+    if (slots_per_rank) *slots_per_rank = h->sym_slots;
+    return 0;
+}
+
+int pk_local_solve_gather_p2p(pk_handle_t h, const pk_local_job* job, int32_t which) {
+    if (!h || !job) return fail("pk_local_solve_gather_p2p: null argument");
+    if (job->memspace != PK_DEVICE) return fail("pk_local_solve_gather_p2p needs device buffers");
+    if (which < 0 || which > 2) return fail("pk_local_solve_gather_p2p: which must be 0 (score), 1 (ssr) or 2 (Y)");
+    if ((which == 0 && !job->out_score) || (which == 1 && !job->out_ssr) || (which == 2 && !job->out_Y))
+        return fail("pk_local_solve_gather_p2p: the gathered output must be requested in the job");
+    if (!h->sym_mapped) return fail("pk_local_solve_gather_p2p: pk_sym_alloc / pk_sym_open first");
+    if (job->B > h->sym_slots) return fail("pk_local_solve_gather_p2p: job->B exceeds the slots per rank of the symmetric buffer");
+    if (h->world > 1 && !h->comm) return fail("pk_nccl_init was not called");
+    h->p2p_which = which;
+    const int rc = pk_local_solve_batch(h, job);
+    h->p2p_which = -1;
     return rc;
 }
 

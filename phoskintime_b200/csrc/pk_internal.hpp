@@ -71,6 +71,15 @@ struct pk_handle_s {
     int ag_which = 0, ag_chunks = 1;
     pkh::ncclComm_t comm = nullptr;
     int world = 1, rank = 0;
+    // symmetric result buffer of the peer-memory gather (pk_sym_*, pk_local_solve_gather_p2p): every rank owns
+    // [world][sym_slots] doubles and maps every peer's copy through CUDA IPC
+    static constexpr int MAX_PEERS = 8;
+    double* sym_local = nullptr;
+    double* sym_peer[MAX_PEERS] = {};
+    long long sym_slots = 0;
+    bool sym_mapped = false;
+    int p2p_which = -1;                        // >= 0 for the duration of one pk_local_solve_gather_p2p call
+    pkh::DevBuf bar;                           // 2 * world doubles: the closing rendezvous of the peer-memory gather
     std::vector<pkh::GlobalTopoHost*> topos;   // uploaded global networks (index = topology id)
 };
 

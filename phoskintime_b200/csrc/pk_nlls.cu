@@ -69,6 +69,7 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     cudaStream_t st = h->stream;
     const size_t B = (size_t)j->B, R = B * (size_t)(P + 1);
     const bool host = j->memspace == PK_HOST;
+    if (B > 0x7fffffffull / (size_t)(P + 1)) return fail("pk_local_nlls_batch: B*(P+1) exceeds 2^31");
     const size_t G = (size_t)j->n_groups;
     const size_t y0_elems = j->y0_stride ? (B - 1) * (size_t)j->y0_stride + n : (size_t)n;
 
@@ -97,7 +98,6 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     CK(ws.get(&d_state, B));
     if (j->group) { CK(ws.get(&d_pgroup, R)); CK(ws.get(&d_tgroup, B)); }
     CK(ws.get(&d_idx[0], B)); CK(ws.get(&d_idx[1], B));
-    if (B > 0x7fffffffull / (size_t)(P + 1)) return fail("pk_local_nlls_batch: B*(P+1) exceeds 2^31");
     CK(cudaMemcpyAsync(d_lb, j->lb, P * sizeof(double), cudaMemcpyHostToDevice, st));      // lb/ub/t: always host
     CK(cudaMemcpyAsync(d_ub, j->ub, P * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(ws.get(&d_t, j->T));
@@ -142,8 +142,13 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
 
     const int TB = 256;
     const unsigned gB = (unsigned)((B + TB - 1) / TB), gR = (unsigned)((R + TB - 1) / TB);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // timing events of this call: destroyed on every exit path
+    struct EventPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } evp;
+    CK(cudaEventCreate(&evp.a)); CK(cudaEventCreate(&evp.b));
+    cudaEvent_t& e0 = evp.a; cudaEvent_t& e1 = evp.b;
     CK(cudaEventRecord(e0, st));
     pk::nlls_init_kernel<<<gB, TB, 0, st>>>(a, j->mu0 > 0 ? j->mu0 : 1e-3, d_idx[0]);
     int launches = 1, iters_done = 0;
@@ -177,20 +182,19 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
         nA = (size_t)running;
         if (nA == 0) break;
     }
-    if (rc != 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    if (rc != 0) return rc;
     // final evaluation at the optimum: cost and score_fit (normest.py:293-306 ranks the starts by score_fit)
     {
         pk_local_job jf = base;
         jf.B = j->B; jf.params = d_theta; jf.group = d_group; jf.y0 = d_y0; jf.y0_stride = j->y0_stride;
         jf.out_ssr = d_tssr; jf.out_status = d_tstat; jf.out_score = d_score;
-        if ((rc = pk_local_solve_batch(h, &jf)) != 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+        if ((rc = pk_local_solve_batch(h, &jf)) != 0) return rc;
         launches += h->last_launches;
     }
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(std::string("pk_local_nlls_batch: ") + cudaGetErrorString(le));
 

@@ -16,7 +16,7 @@ from ._lib import (GLOBAL_METRIC_IDS, METHOD_IDS, MODEL_IDS, PK_DEVICE, PK_HOST,
                    PkGlobalJob, PkGlobalLossData, PkGlobalTopology, PkLocalJob)
 
 # Tolerances left at None select the LIBRARY defaults (rtol/atol <= 0 in the C ABI), which depend on the method the kernel
-# uses: ROS6L (thread-per-system kernels) 2e-5/2e-9, ROS5L (dense kernel) and the global network 2e-6/2e-9 — each
+# uses: ROS6L (thread-per-system kernels) 2e-5/2e-11, ROS5L (dense kernel) and the global network 2e-6/2e-9 — each
 # chosen from the measured error against the reference's tight solution (<= 0.15-0.27 of the 1e-6 parity bound on every
 # golden and on harsh parameter draws) — DESIGN.md §2/§5.  The two constants are the ROS5L / global values.
 DEFAULT_RTOL = 2e-6
@@ -40,9 +40,15 @@ def _is_torch(x):
 class Engine:
     """Owns one pk_handle (stream + device workspaces) on one GPU."""
 
+    _next_token = 0
+
     def __init__(self, device=0):
         self.lib = _lib.load()
         self.device = int(device)
+        # unique per Engine object for the life of the process: host-side caches (uploaded topologies, installed loss
+        # tables) are keyed by it — id(engine) can be reused by a later Engine after this one is collected
+        Engine._next_token += 1
+        self.token = Engine._next_token
         h = C.c_void_p()
         _lib.check(self.lib.pk_create(self.device, C.byref(h)))
         self._h = h
@@ -51,8 +57,10 @@ class Engine:
         _lib.check(self.lib.pk_device_info(self._h, C.byref(sm), C.byref(khz), name, 128))
         self.sm_count, self.clock_khz, self.device_name = sm.value, khz.value, name.value.decode()
         self.world, self.rank = 1, 0
+        self._sym = None            # torch view of the symmetric buffer of the peer-memory gather
 
     def close(self):
+        self._sym = None
         if getattr(self, "_h", None):
             self.lib.pk_destroy(self._h)
             self._h = None
@@ -86,7 +94,8 @@ class Engine:
     def solve_local_batch(self, model, params, init_cond, num_psites, t, want=("sol", "flat"), *,
                           target=None, sigma=None, group=None, lam=0.0, y_metric="total_signal",
                           rtol=None, atol=None, max_steps=0, normalize=False, log_params=False,
-                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True, method=None, gather=None):
+                          score_weights=(1.0, 1.0, 1.0, 1.0, 1.0), out=None, counters=True, method=None, gather=None,
+                          gather_p2p=None):
         """Solve B systems.  Returns a dict with the requested keys among
         sol[B,T,n], flat[B,L], Y[B], ssr[B], score[B] plus status/nsteps/nrej[B] (int32).
 
@@ -100,7 +109,11 @@ class Engine:
             'ros6l', 'ros5l' or 'rodas4' — DESIGN.md §2
         gather : (key, recv, chunks) — fuse the solve with the NCCL all-gather of the per-sample output `key`
             ('score', 'ssr' or 'Y'; torch CUDA path only): the batch is integrated in `chunks` pieces and piece c's
-            gather overlaps piece c+1 (`pk_local_solve_allgather`); recv [world*B] comes back rank-major
+            gather overlaps piece c+1 (`pk_local_solve_allgather`); recv [world*B] comes back rank-major.  Every rank
+            must pass the same B.
+        gather_p2p : key — the same gather WITHOUT a collective: the kernel stores every finished system's `key` straight
+            into all ranks' symmetric buffers over NVLink peer memory (`pk_local_solve_gather_p2p`, after `sym_setup`);
+            res['gathered'] is the [world, slots] view of this rank's buffer.  Ranks may pass different B.
         """
         want = tuple(want)
         unknown = set(want) - {"sol", "flat", "Y", "ssr", "score"}
@@ -194,13 +207,31 @@ class Engine:
 
         if dev:
             xp.sync()          # inputs produced on torch's stream must be visible to ours
+        if gather is not None and gather_p2p is not None:
+            raise ValueError("gather and gather_p2p are alternatives")
         if gather is not None:
             key, recv, chunks = gather
             if not dev or key not in res or key not in ("score", "ssr", "Y"):
                 raise ValueError("gather needs torch CUDA buffers and a requested per-sample output (score, ssr or Y)")
+            # precondition of pk_local_solve_allgather: the same B on every rank (pad the shorter shards), and a
+            # float64 landing buffer of world*B entries on this device
+            import torch
+            if not (_is_torch(recv) and recv.is_cuda and recv.dtype == torch.float64 and recv.is_contiguous()):
+                raise ValueError("gather: recv must be a contiguous torch CUDA float64 tensor")
+            if recv.device != params.device or recv.numel() < self.world * B:
+                raise ValueError(f"gather: recv must live on {params.device} and hold world*B = {self.world * B} entries "
+                                 "(every rank must pass the same B: pad uneven shards)")
             _lib.check(self.lib.pk_local_solve_allgather(self._h, C.byref(job), {"score": 0, "ssr": 1, "Y": 2}[key],
                                                          int(chunks), recv.data_ptr()))
             res["gathered"] = recv
+        elif gather_p2p is not None:
+            key = gather_p2p
+            if not dev or key not in res or key not in ("score", "ssr", "Y"):
+                raise ValueError("gather_p2p needs torch CUDA buffers and a requested per-sample output (score, ssr or Y)")
+            if self._sym is None:
+                raise PhoskinError("gather_p2p: call Engine.sym_setup (or ShardedRun.setup_p2p) first")
+            _lib.check(self.lib.pk_local_solve_gather_p2p(self._h, C.byref(job), {"score": 0, "ssr": 1, "Y": 2}[key]))
+            res["gathered"] = self._sym          # [world, slots_per_rank]: row r = rank r's values (first B_r entries)
         else:
             _lib.check(self.lib.pk_local_solve_batch(self._h, C.byref(job)))
         del keep
@@ -484,6 +515,27 @@ class Engine:
         buf = C.create_string_buffer(128)
         _lib.check(self.lib.pk_nccl_unique_id(buf))
         return buf.raw
+
+    def sym_setup(self, slots_per_rank, exchange):
+        """Allocate this rank's symmetric buffer [world, slots_per_rank] (float64), exchange the CUDA IPC handles with
+        `exchange(bytes) -> list of bytes, rank-major` (e.g. torch.distributed.all_gather_object) and map every peer's
+        buffer.  Returns the torch view of the local buffer."""
+        import torch
+        buf = C.create_string_buffer(64)
+        _lib.check(self.lib.pk_sym_alloc(self._h, int(slots_per_rank), buf))
+        handles = exchange(buf.raw)
+        if len(handles) != self.world:
+            raise PhoskinError("sym_setup: one handle per rank expected")
+        if self.world > 1:
+            _lib.check(self.lib.pk_sym_open(self._h, b"".join(handles)))
+        ptr, slots = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.pk_sym_buffer(self._h, C.byref(ptr), C.byref(slots)))
+
+        class _Raw:                    # zero-copy torch view of library-owned device memory
+            __cuda_array_interface__ = {"shape": (self.world, slots.value), "typestr": "<f8", "data": (ptr.value, False),
+                                        "version": 2}
+        self._sym = torch.as_tensor(_Raw(), device=torch.device("cuda", self.device))
+        return self._sym
 
     def allgather_f64(self, send, recv):
         """NCCL all-gather of torch CUDA float64 tensors (recv.numel() == world * send.numel())."""

@@ -22,10 +22,20 @@ METRIC_BASE_TIMES = (0.0, 4.0, 0.0)       # simulate.py:116-118: protein, RNA (t
 
 
 def _topology(sys_, engine):
-    key = id(engine)
+    key = engine.token
     if key not in sys_._topo_id:
         sys_._topo_id[key] = engine.global_upload(sys_)
     return sys_._topo_id[key]
+
+
+def _loss_fingerprint(loss_data):
+    """Digest of the loss tables' contents (a few KB: cheap next to one solve)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for k in sorted(loss_data):
+        a = np.ascontiguousarray(loss_data[k])
+        h.update(k.encode()); h.update(str(a.dtype).encode()); h.update(a.tobytes())
+    return h.digest()
 
 
 def simulate_batch(sys_, params, t_eval, want=("Y",), *, y0=None, rtol=None, atol=None, mxstep=0, theta_mode=False,
@@ -38,9 +48,11 @@ def simulate_batch(sys_, params, t_eval, want=("Y",), *, y0=None, rtol=None, ato
     """
     eng = engine or get_engine()
     topo = _topology(sys_, eng)
-    if loss_data is not None and sys_._loss_key.get(id(eng)) is not loss_data:
-        eng.global_set_loss_data(topo, loss_data)
-        sys_._loss_key[id(eng)] = loss_data
+    if loss_data is not None:
+        fp = _loss_fingerprint(loss_data)               # content, not identity: in-place edits of the dict are seen
+        if sys_._loss_key.get(eng.token) != fp:
+            eng.global_set_loss_data(topo, loss_data)
+            sys_._loss_key[eng.token] = fp
     if "F" in want:
         eng.global_set_prior(topo, sys_.pack_params(sys_.defaults) if lambda_prior else None)
     if y0 is None:
@@ -125,7 +137,7 @@ def LOSS_FN(Y, p_prot, t_prot, obs_prot, w_prot, p_rna, t_rna, obs_rna, w_rna, p
     eng = engine or get_engine()
     prot_map = np.ascontiguousarray(prot_map, dtype=np.int32)
     comb = int(model) == 2
-    key = (id(eng), comb, prot_map.tobytes())
+    key = (eng.token, comb, prot_map.tobytes())
     topo = _LOSS_TOPOS.get(key)
     if topo is None:
         from .network import GlobalSystem

@@ -56,6 +56,19 @@ class ShardedRun:
             dist.broadcast_object_list(ids, src=0)
             engine.init_nccl(self.world, self.rank, ids[0])
 
+    def setup_p2p(self, slots_per_rank):
+        """Symmetric result buffers for `solve_local_batch(..., gather_p2p=key)`: every rank's [world, slots_per_rank]
+        buffer is mapped into every other rank through CUDA IPC (handles travel through the process group)."""
+        def exchange(handle):
+            if self.world == 1:
+                return [handle]
+            out = [None] * self.world
+            self.dist.all_gather_object(out, handle)
+            return out
+        view = self.engine.sym_setup(slots_per_rank, exchange)
+        self.barrier()                 # every rank has mapped every buffer before anyone launches
+        return view
+
     def bounds(self, total, align=1):
         return shard_bounds(total, self.world, self.rank, align)
 

@@ -237,7 +237,7 @@ def test_combinatorial_full_size_and_uncoupled(engine):
     u = synthetic_system(seed=8, N=6, K=3, max_sites=4, tf_density=0.0, model=2)
     tu = np.array([0.0, 0.5, 1.0, 4.0, 16.0, 60.0, 960.0])
     r = simulate_batch(u, u.pack_params()[None, :], tu, ("Y",), engine=engine)
-    assert r["status"][0] == 0 and engine.global_dims(u._topo_id[id(engine)])["n_reg"] == 0
+    assert r["status"][0] == 0 and engine.global_dims(u._topo_id[engine.token])["n_reg"] == 0
     assert _ratio(r["Y"][0], og.simulate_exact_buckets(2, u.as_dict(), tu), 1e-6, 1e-9) <= 1.0
 
 
@@ -376,7 +376,7 @@ def test_network_without_transcriptional_coupling(engine):
     net = s.as_dict()
     t = np.array([0.0, 0.5, 1.0, 4.0, 16.0, 60.0, 960.0])
     r = simulate_batch(s, s.pack_params()[None, :], t, ("Y",), engine=engine)
-    assert r["status"][0] == 0 and engine.global_dims(s._topo_id[id(engine)])["n_reg"] == 0
+    assert r["status"][0] == 0 and engine.global_dims(s._topo_id[engine.token])["n_reg"] == 0
     ref = og.simulate_exact_buckets(1, net, t)
     assert _ratio(r["Y"][0], ref, 1e-6, 1e-9) <= 1.0
 

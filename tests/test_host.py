@@ -110,6 +110,24 @@ def test_initial_condition_closed_forms():
         initial_condition(2, "testmod")
 
 
+def test_initial_condition_matches_reference_goldens():
+    """phoskintime_b200.steady.initial_condition (the PRODUCT's closed form / linear solve) against the values the
+    unmodified reference's SLSQP formulation converged to (tests/golden/steady.npz, written by oracle/gen_golden.py from
+    steady/initdist.py:9-50, initsucc.py:9-55, initrand.py:10-77)."""
+    from conftest import GOLDEN
+    from phoskintime_b200.steady import initial_condition
+    g = np.load(os.path.join(GOLDEN, "steady.npz"))
+    checked = 0
+    for key in g.files:
+        if key == "versions":
+            continue
+        model, ns = key.split("_ns")
+        got = np.asarray(initial_condition(int(ns), model))
+        assert got.shape == g[key].shape and np.abs(got - g[key]).max() < 1e-12, key
+        checked += 1
+    assert checked >= 9
+
+
 def test_morris_sample_and_problem_definitions():
     prob = sensitivity.define_sensitivity_problem_ds(3, np.linspace(0.5, 2, 10))
     assert prob["names"] == ["A", "B", "C", "D", "S1", "S2", "S3", "D1", "D2", "D3"]

@@ -81,7 +81,7 @@ mt = metric_time_indices(T15, T14, [4.0, 8.0, 15.0, 30.0, 60.0, 120.0, 240.0, 48
 y0g = torch.from_numpy(s.y0()).to(dev)
 ms, res = timed(lambda: simulate_batch(s, P, T15, ("metric", "loss"), y0=y0g, loss_data=ld, metric_times=mt, engine=eng), reps=2)
 report("cfg5 global network N=120 K=40 state_dim=%d, fused metric+loss" % s.idx.state_dim, B, ms, res,
-       {"dims": eng.global_dims(s._topo_id[id(eng)])})
+       {"dims": eng.global_dims(s._topo_id[eng.token])})
 # the same network with the combinatorial kinetic model (one state per phosphorylation pattern, ~1000 states)
 s2 = synthetic_system(seed=5, N=120, K=40, max_sites=4, model=2)
 B2 = 4096 if not args.quick else 296
@@ -90,6 +90,6 @@ ld2 = synthetic_loss_data(s2, T15, seed=12)
 y0g2 = torch.from_numpy(s2.y0()).to(dev)
 ms, res = timed(lambda: simulate_batch(s2, P2, T15, ("metric", "loss"), y0=y0g2, loss_data=ld2, metric_times=mt, engine=eng), reps=2)
 report("cfg5-comb global network, combinatorial model N=120 K=40 state_dim=%d, fused metric+loss" % s2.idx.state_dim, B2, ms, res,
-       {"dims": eng.global_dims(s2._topo_id[id(eng)])})
+       {"dims": eng.global_dims(s2._topo_id[eng.token])})
 if args.out:
     json.dump({"device": eng.device_name, "rows": rows}, open(args.out, "w"), indent=1)

@@ -22,7 +22,7 @@ for f in sorted(glob.glob("tests/golden/global_*.npz")):
         e_s = np.abs(Y - stock) / (1e-6 * np.abs(stock) + 1e-7)
         e_st = np.abs(stock - tight) / (1e-6 * np.abs(tight) + 1e-9)
         print(f"{os.path.basename(f)[7:-4]:10s} rtol {rtol:g} status {np.bincount(r['status'], minlength=4)} steps {r['nsteps'].mean():.0f} rej {r['nrej'].mean():.1f} "
-              f"| vs tight {np.nanmax(e_t):.3g} | vs stock {np.nanmax(e_s):.3g} | stock vs tight {e_st.max():.3g} | dims {eng.global_dims(s._topo_id[id(eng)])} [{dt*1e3:.1f} ms, kernel {eng.last_launch_info()[1]:.2f} ms]", flush=True)
+              f"| vs tight {np.nanmax(e_t):.3g} | vs stock {np.nanmax(e_s):.3g} | stock vs tight {e_st.max():.3g} | dims {eng.global_dims(s._topo_id[eng.token])} [{dt*1e3:.1f} ms, kernel {eng.last_launch_info()[1]:.2f} ms]", flush=True)
 if small:
     sys.exit(0)
 t = np.array([0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 15.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])
@@ -35,5 +35,5 @@ for N, K, B in ((36, 12, 1184), (120, 40, 148), (120, 40, 1184)):
         r = simulate_batch(s, P, t, ("metric",), rtol=rtol, atol=atol, engine=eng,
                            metric_times={"t_prot": np.arange(15), "t_rna": np.arange(5, 15), "t_pho": np.arange(15), "prot_b": 0, "rna_b": 5, "pho_b": 0})
         ms = eng.last_launch_info()[1]
-        print(f"N={N} B={B} rtol {rtol:g}: dims {eng.global_dims(s._topo_id[id(eng)])} status {np.bincount(r['status'], minlength=4)} steps {r['nsteps'].mean():.0f} rej {r['nrej'].mean():.1f} "
+        print(f"N={N} B={B} rtol {rtol:g}: dims {eng.global_dims(s._topo_id[eng.token])} status {np.bincount(r['status'], minlength=4)} steps {r['nsteps'].mean():.0f} rej {r['nrej'].mean():.1f} "
               f"kernel {ms:.1f} ms -> {B / ms * 1e3:.0f} solves/s, {ms * 1e3 / (r['nsteps'] + r['nrej']).sum() * min(B, 148):.1f} us/step/CTA", flush=True)

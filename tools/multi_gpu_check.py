@@ -47,5 +47,21 @@ recv = torch.full((run.world * Bq,), -1.0, dtype=torch.float64, device="cuda")
 fused = eng.solve_local_batch("succmod", pq, y0q, 5, tq, want=("score",), target=tgq, gather=("score", recv, 4))
 assert torch.equal(fused["score"], plain) and torch.equal(recv, ref)
 assert torch.equal(recv[run.rank * Bq:(run.rank + 1) * Bq], plain)
+# peer-memory gather (pk_local_solve_gather_p2p): the kernel writes each score into every rank's symmetric buffer over
+# NVLink; ragged shard sizes (rank r solves Bq - 1000 r systems); every rank ends up with every rank's scores
+view = run.setup_p2p(Bq)
+for rep in range(3):
+    view.fill_(-7.0)
+    torch.cuda.synchronize()
+    run.barrier()
+    Br = Bq - 1000 * run.rank
+    r3 = eng.solve_local_batch("succmod", pq[:Br], y0q, 5, tq, want=("score", "ssr"), target=tgq, gather_p2p="score")
+    assert torch.equal(r3["score"], plain[:Br])
+    g = r3["gathered"]
+    assert g.shape == (run.world, Bq)
+    for r in range(run.world):
+        assert torch.equal(g[r, :Bq - 1000 * r], ref[r * Bq:r * Bq + Bq - 1000 * r]), (rep, r)
+        assert bool((g[r, Bq - 1000 * r:] == -7.0).all())
+    run.barrier()
 run.barrier()
-print(f"rank {run.rank}/{run.world}: fused gather identical to the plain all-gather; sharded local Morris Y and global Morris indices identical to single-GPU", flush=True)
+print(f"rank {run.rank}/{run.world}: peer-memory gather and fused gather identical to the plain all-gather; sharded local Morris Y and global Morris indices identical to single-GPU", flush=True)
