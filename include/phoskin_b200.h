@@ -84,6 +84,8 @@ typedef struct pk_local_job {
     int32_t sigma_len;
     double lam;             /* regularisation lambda (normest.py:56, 421)                        */
     double score_w[5];      /* alpha(rmse) beta(mae) gamma(var) delta(mse) mu(l2); config.toml:212-217 */
+    const double* lam_group;/* NULL (lam for every system) or [G]: lambda of every group — the lambda scan of
+                               normest.py:22-165 (10 lambdas x weight options) becomes groups of ONE call */
 } pk_local_job;
 
 int pk_abi_version(void);
@@ -205,6 +207,7 @@ typedef struct pk_nlls_job {
     int32_t* out_status;    /* [B]                                                               */
     int32_t* out_iters;     /* [B]                                                               */
     int32_t* out_nfev;      /* [B] ODE solves spent on the problem                               */
+    const double* lam_group;/* NULL or [G] (memspace of target): per-group lambda, see pk_local_job      */
 } pk_nlls_job;
 void pk_nlls_job_init(pk_nlls_job* job);
 int pk_sizeof_nlls_job(void);

@@ -35,7 +35,7 @@ class PkLocalJob(C.Structure):
         ("out_nsteps", C.c_void_p), ("out_nrej", C.c_void_p),
         ("target", C.c_void_p), ("sigma", C.c_void_p), ("group", C.c_void_p),
         ("n_groups", C.c_int32), ("sigma_len", C.c_int32), ("lam", C.c_double),
-        ("score_w", C.c_double * 5),
+        ("score_w", C.c_double * 5), ("lam_group", C.c_void_p),
     ]
 
 
@@ -52,7 +52,7 @@ class PkNllsJob(C.Structure):
         ("rtol", C.c_double), ("atol", C.c_double), ("max_steps", C.c_int32), ("method", C.c_int32),
         ("score_w", C.c_double * 5),
         ("out_cost", C.c_void_p), ("out_score", C.c_void_p), ("out_status", C.c_void_p), ("out_iters", C.c_void_p),
-        ("out_nfev", C.c_void_p),
+        ("out_nfev", C.c_void_p), ("lam_group", C.c_void_p),
     ]
 
 

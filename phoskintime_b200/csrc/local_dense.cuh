@@ -504,10 +504,11 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
         }
         if (want_loss) {
             double ssr = e.ssr;
-            if (a.lam != 0.0) {
+            const double lam = a.lam_group ? a.lam_group[grp] : a.lam;
+            if (lam != 0.0) {
                 for (int i = lane; i < P; i += NT) {
                     double th = a.params[sys * P + i];
-                    double ww = a.lam / (double)P * th * th;
+                    double ww = lam / (double)P * th * th;
                     if (sg && a.sigma_len > a.L) ww /= __ldg(sg + a.L + i);
                     ssr = fma(ww, ww, ssr);
                 }

@@ -498,13 +498,14 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
                 } else {
                     double acc_w = 0.0;
                     const int grp = (want_loss && a.group) ? a.group[sys] : 0;
-                    if (want_loss && a.lam != 0.0) {
+                    const double lam = (want_loss && a.lam_group) ? a.lam_group[grp] : a.lam;
+                    if (want_loss && lam != 0.0) {
                         // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423); theta = the caller's
                         // (possibly logarithmic) parameters
                         const double* th = a.params + (size_t)sys * P;
                         const double* sgr = (a.isigma && a.sigma_len > a.L) ? a.isigma + (size_t)grp * a.sigma_len + a.L : nullptr;
                         for (int i = 0; i < P; ++i) {
-                            double w = a.lam / (double)P * th[i] * th[i];
+                            double w = lam / (double)P * th[i] * th[i];
                             if (sgr) w *= __ldg(sgr + i);
                             acc_w = fma(w, w, acc_w);
                         }
@@ -775,12 +776,13 @@ __global__ void __launch_bounds__(TPS_BLOCK, MIN_BLOCKS) local_tps_kernel(const 
             }
             const double p2 = lane_p2[(threadIdx.x & ~31) + f];      // computed by the owner when it loaded the parameters
             if (want_loss) {
-                if (a.lam != 0.0) {
+                const double lam = a.lam_group ? a.lam_group[g] : a.lam;
+                if (lam != 0.0) {
                     // the lam/P*theta^2 rows of normest's model_func (paramest/normest.py:403-423)
                     const double* sgr = (sg && a.sigma_len > a.L) ? sg + a.L : nullptr;
                     for (int i = lane; i < P; i += 32) {
                         const double th = a.params[fsys * P + i];
-                        double w = a.lam / (double)P * th * th;
+                        double w = lam / (double)P * th * th;
                         if (sgr) w *= __ldg(sgr + i);
                         ssr = fma(w, w, ssr);
                     }

@@ -30,6 +30,7 @@ struct NllsArgs {
     long long B;
     int P, L, sigma_len, log_params;
     double lam, fd_rel, ftol, xtol, gtol;
+    const double* lam_group;       // NULL or [n_groups]
     const double *lb, *ub;   // [P]
     const double* target;    // [G,L]
     const double* sigma;     // [G,sigma_len] or nullptr
@@ -167,10 +168,11 @@ __global__ void nlls_step_kernel(const NllsArgs a, int warps_per_cta, int Lp) {
     }
     __syncwarp();
     for (int j = lane; j < P; j += 32) {
-        if (a.lam != 0.0) {
+        const double lam = a.lam_group ? a.lam_group[grp] : a.lam;
+        if (lam != 0.0) {
             const double is = (sg && a.sigma_len > L) ? 1.0 / sg[L + j] : 1.0;
-            const double rr = a.lam / (double)P * th[j] * th[j] * is;
-            const double dj = 2.0 * a.lam / (double)P * th[j] * is;
+            const double rr = lam / (double)P * th[j] * th[j] * is;
+            const double dj = 2.0 * lam / (double)P * th[j] * is;
             A[j * P + j] = fma(dj, dj, A[j * P + j]);
             g[j] = fma(dj, rr, g[j]);
         }

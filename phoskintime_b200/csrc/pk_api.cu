@@ -265,7 +265,7 @@ int pk_destroy(pk_handle_t h) {
     cudaSetDevice(h->device);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     DevBuf* bufs[] = {&h->params, &h->y0, &h->t, &h->sol, &h->flat, &h->Y, &h->ssr, &h->score, &h->status,
-                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw, &h->bar};
+                      &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw, &h->bar, &h->lamg};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
                        &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
@@ -430,6 +430,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     if (!host) {
         a.params = j->params; a.y0 = j->y0; a.t = j->t;
         a.target = j->target; a.sigma = j->sigma; a.group = j->group;
+        a.lam_group = want_loss ? j->lam_group : nullptr;
         if (tps_path && want_loss) CK(tps_prep(a.target, a.sigma));
         if (h->p2p_which >= 0) {
             if (!tps_path) return fail("pk_local_solve_gather_p2p: only the thread-per-system kernels store to peer memory");
@@ -532,6 +533,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     WS(target, want_loss, G * L * sizeof(double), a.target);
     WS(sigma, want_loss && j->sigma, G * (size_t)j->sigma_len * sizeof(double), a.sigma);
     WS(group, want_loss && j->group, B * sizeof(int32_t), a.group);
+    WS(lamg, want_loss && j->lam_group, G * sizeof(double), a.lam_group);
     WS(sol, j->out_sol, B * TN * sizeof(double), a.out_sol);
     WS(flat, j->out_flat, B * L * sizeof(double), a.out_flat);
     WS(Y, j->out_Y, B * sizeof(double), a.out_Y);
@@ -556,6 +558,8 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
         if (j->sigma)
             CK(cudaMemcpyAsync((void*)a.sigma, j->sigma, G * (size_t)j->sigma_len * sizeof(double),
                                cudaMemcpyHostToDevice, sin));
+        if (j->lam_group)
+            CK(cudaMemcpyAsync((void*)a.lam_group, j->lam_group, G * sizeof(double), cudaMemcpyHostToDevice, sin));
         CK(cudaEventRecord(h->ev_in[PIPE_MAX_CHUNKS - 1], sin));
     }
     size_t lo[PIPE_MAX_CHUNKS + 1];

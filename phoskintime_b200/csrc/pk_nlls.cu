@@ -89,7 +89,7 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     a.lam = j->lam; a.fd_rel = j->fd_rel > 0 ? j->fd_rel : 1e-4;
     a.ftol = j->ftol; a.xtol = j->xtol; a.gtol = j->gtol;
     double *d_lb, *d_ub, *d_t, *d_y0, *d_target, *d_sigma = nullptr, *d_theta, *d_pert, *d_h, *d_flat, *d_ssr, *d_dscale,
-           *d_trial, *d_tssr, *d_score = nullptr;
+           *d_trial, *d_tssr, *d_score = nullptr, *d_lamg = nullptr;
     int *d_group = nullptr, *d_pgroup = nullptr, *d_tgroup = nullptr, *d_sstat, *d_tstat, *d_run, *d_idx[2];
     pk::NllsState* d_state;
     CK(ws.get(&d_lb, P)); CK(ws.get(&d_ub, P)); CK(ws.get(&d_pert, R * P)); CK(ws.get(&d_h, B * P));
@@ -115,10 +115,14 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
             CK(ws.get(&d_group, B));
             CK(cudaMemcpyAsync(d_group, j->group, B * sizeof(int), cudaMemcpyHostToDevice, st));
         }
+        if (j->lam_group) {
+            CK(ws.get(&d_lamg, G));
+            CK(cudaMemcpyAsync(d_lamg, j->lam_group, G * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
         if (j->out_score) CK(ws.get(&d_score, B));
     } else {
         d_theta = j->theta; d_y0 = (double*)j->y0; d_target = (double*)j->target; d_sigma = (double*)j->sigma;
-        d_group = (int*)j->group; d_score = j->out_score;
+        d_group = (int*)j->group; d_score = j->out_score; d_lamg = (double*)j->lam_group;
     }
     // per-system y0 rows follow their problem into the (compacted) perturbed and trial batches
     double *d_y0p = nullptr, *d_y0t = nullptr;
@@ -126,7 +130,7 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
         CK(ws.get(&d_y0p, R * (size_t)n));
         CK(ws.get(&d_y0t, B * (size_t)n));
     }
-    a.lb = d_lb; a.ub = d_ub; a.target = d_target; a.sigma = d_sigma; a.group = d_group;
+    a.lb = d_lb; a.ub = d_ub; a.target = d_target; a.sigma = d_sigma; a.group = d_group; a.lam_group = d_lamg;
     a.theta = d_theta; a.pert = d_pert; a.pert_group = d_pgroup; a.hstep = d_h; a.flat = d_flat; a.ssr = d_ssr;
     a.solve_status = d_sstat; a.dscale = d_dscale; a.trial = d_trial; a.trial_ssr = d_tssr; a.trial_status = d_tstat;
     a.st = d_state; a.n_running = d_run;
@@ -137,7 +141,7 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* j) {
     base.model = j->model; base.n_sites = j->n_sites; base.T = j->T; base.memspace = PK_DEVICE;
     base.t = d_t; base.rtol = j->rtol; base.atol = j->atol; base.max_steps = j->max_steps; base.log_params = j->log_params;
     base.method = j->method; base.target = d_target; base.sigma = d_sigma; base.n_groups = j->n_groups;
-    base.sigma_len = j->sigma ? j->sigma_len : 0; base.lam = j->lam;
+    base.sigma_len = j->sigma ? j->sigma_len : 0; base.lam = j->lam; base.lam_group = d_lamg;
     for (int i = 0; i < 5; ++i) base.score_w[i] = j->score_w[i];
 
     const int TB = 256;

@@ -148,7 +148,8 @@ class Engine:
         job.rtol = 0.0 if rtol is None else float(rtol)          # 0 -> the method's library default
         job.atol = 0.0 if atol is None else float(atol)
         job.max_steps, job.normalize, job.log_params = int(max_steps), int(bool(normalize)), int(bool(log_params))
-        job.lam = float(lam)
+        lam_arr = None if np.ndim(lam) == 0 else xp.f64(lam).reshape(-1)      # per-group lambda [G]
+        job.lam = float(lam) if lam_arr is None else 0.0
         job.method = METHOD_IDS[method]
         for i, w in enumerate(score_weights):
             job.score_w[i] = float(w)
@@ -196,6 +197,11 @@ class Engine:
                 keep.append(gr)
             elif G != 1:
                 raise ValueError("several target rows need `group`")
+            if lam_arr is not None:
+                if lam_arr.shape[0] != G:
+                    raise ValueError(f"per-group lam must have {G} entries")
+                job.lam_group = xp.ptr(lam_arr)
+                keep.append(lam_arr)
             if "ssr" in want:
                 job.out_ssr = alloc("ssr", (B,))
             if "score" in want:
@@ -297,7 +303,15 @@ class Engine:
             keep.append(gr)
         elif G != 1:
             raise ValueError("several target rows need `group`")
-        job.lam, job.log_params, job.max_iter = float(lam), int(bool(log_params)), int(max_iter)
+        if np.ndim(lam) == 0:
+            job.lam = float(lam)
+        else:                                     # per-group lambda [G] (the lambda scan as groups of one call)
+            lam_arr = xp.f64(lam).reshape(-1)
+            if lam_arr.shape[0] != G:
+                raise ValueError(f"per-group lam must have {G} entries")
+            job.lam, job.lam_group = 0.0, xp.ptr(lam_arr)
+            keep.append(lam_arr)
+        job.log_params, job.max_iter = int(bool(log_params)), int(max_iter)
         job.ftol, job.xtol, job.gtol = float(ftol), float(xtol), float(gtol)
         if fd_rel is not None:
             job.fd_rel = float(fd_rel)

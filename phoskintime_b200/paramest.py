@@ -13,7 +13,8 @@ normest.py:293-306 does.  SciPy's TRF itself is optimiser policy outside the par
 """
 import numpy as np
 
-from .engine import get_engine
+from .engine import get_engine, local_dims
+from .models.weights import early_emphasis, get_weight_options
 
 
 def multistart_points(base_p0, lb, ub, n_starts=48, jitter_frac=0.10, seed=42, gene=""):
@@ -92,3 +93,86 @@ def best_per_group(values, group, n_groups):
     first = np.r_[True, group[order][1:] != group[order][:-1]]
     best[group[order][first]] = order[first]
     return best
+
+
+def find_best_lambda(gene, target, p0, time_points, free_bounds, init_cond, num_psites, p_data, pr_data,
+                     lambdas=np.logspace(-2, 0, 10), *, model=None, ms_gauss_weights=None, use_custom_weights=None,
+                     engine=None, return_table=False, **nlls_kw):
+    """`find_best_lambda` / `worker_find_lambda` (paramest/normest.py:22-165): for every lambda of the scan and every
+    sigma option of `get_weight_options` one bounded fit from `p0`, ranked by `score_fit` at the optimum; returns
+    (best_lambda, best_weight_key).
+
+    The reference farms the 10 lambdas to a process pool and loops over the weight options inside each worker —
+    10 x W sequential `curve_fit`s.  Here every (lambda, weight option) pair is one GROUP of a single
+    `pk_local_nlls_batch` call: its own sigma row [L+P] and its own lambda (`lam_group`), all fits advancing together
+    on the device.  `target` may be [L] (one protein) or [G,L] with `p_data` / `pr_data` / `ms_gauss_weights` lists of
+    the same length: then the proteins are batched too and lists are returned.
+    `ms_gauss_weights`: the measurement uncertainties the reference reads from its CSV files (`get_protein_weights`,
+    models/weights.py:80-146); None -> ones."""
+    from .models import ODE_MODEL
+    model = model or ODE_MODEL
+    eng = engine or get_engine()
+    t = np.asarray(time_points, dtype=np.float64)
+    targets = np.atleast_2d(np.asarray(target, dtype=np.float64))
+    single = np.ndim(target) == 1
+    G = targets.shape[0]
+    listify = lambda v: [v] if single else list(v)
+    p_list, pr_list = listify(p_data), listify(pr_data)
+    ms_list = [None] * G if ms_gauss_weights is None else listify(ms_gauss_weights)
+    lb, ub = (np.asarray(b, dtype=np.float64) for b in free_bounds)
+    p0 = np.broadcast_to(np.asarray(p0, dtype=np.float64), (G, lb.size))
+    lambdas = np.asarray(lambdas, dtype=np.float64)
+    L = targets.shape[1]
+    sig_rows, tg_rows, lam_rows, starts, keys = [], [], [], [], []
+    for g in range(G):
+        early = early_emphasis(pr_list[g], p_list[g], t, num_psites)
+        ms = np.ones(L - 9) if ms_list[g] is None else np.asarray(ms_list[g], dtype=np.float64)
+        opts = get_weight_options(targets[g], t, num_psites, True, lb.size, early, ms, use_custom_weights)
+        for lam in lambdas:
+            for key, sigma in opts.items():
+                if np.size(sigma) != L + lb.size:
+                    # the time-index based options of the reference are built over num_psites*n_times entries
+                    # (models/weights.py:186), one block short of the protein + site layout: curve_fit rejects such a
+                    # sigma ("sigma has incorrect shape") and the reference's worker dies on it — they are skipped
+                    continue
+                sig_rows.append(sigma); tg_rows.append(targets[g]); lam_rows.append(lam); starts.append(p0[g])
+                keys.append((g, float(lam), key))
+    n = len(keys)
+    res = eng.nlls_local_batch(model, np.asarray(starts), init_cond, num_psites, t, np.asarray(tg_rows), lb, ub,
+                               sigma=np.asarray(sig_rows), group=np.arange(n, dtype=np.int32), lam=np.asarray(lam_rows),
+                               log_params=(model == "randmod"), **nlls_kw)
+    score = np.where((res["status"] > 0) & np.isfinite(res["score"]), res["score"], np.inf)
+    out = []
+    for g in range(G):
+        idx = [i for i, k in enumerate(keys) if k[0] == g]
+        # the reference keeps the first strictly smaller score, walking lambdas in completion order (unordered); ties
+        # are broken here by the scan order (lambda ascending, options in dict order)
+        best = idx[int(np.argmin(score[idx]))]
+        out.append((keys[best][1], keys[best][2]) if np.isfinite(score[best]) else (None, None))
+    table = {"keys": keys, "score": score, "theta": res["theta"], "status": res["status"], "cost": res["cost"]}
+    result = out[0] if single else out
+    return (result, table) if return_table else result
+
+
+def bootstrap_refit(model, popt_best, lb, ub, init_cond, num_psites, time_points, target_fit, *, n_boot, sigma=None, lam=0.0,
+                    noise_sd=0.05, rng=None, engine=None, **nlls_kw):
+    """The bootstrap loop of `normest` (paramest/normest.py:488-523): `n_boot` refits from `popt_best` against
+    `target_fit * (1 + N(0, noise_sd))`, all in ONE `pk_local_nlls_batch` call (every bootstrap replicate is a group
+    with its own noisy target row).  `target_fit` = [target | zeros(P)] as the reference builds it (the regularisation
+    targets stay zero under multiplicative noise).  Returns dict(popt_mean[P], estimates[n_boot,P], ok[n_boot])."""
+    eng = engine or get_engine()
+    rng = rng or np.random.default_rng()
+    lb = np.asarray(lb, dtype=np.float64)
+    P = lb.size
+    target_fit = np.asarray(target_fit, dtype=np.float64)
+    L = local_dims(model, num_psites, len(time_points))[2]          # target_fit = [target (L) | zeros (P)] or just target
+    if target_fit.size not in (L, L + P):
+        raise ValueError(f"target_fit must have {L} or {L + P} entries")
+    noisy = target_fit[None, :] * (1.0 + rng.normal(0.0, noise_sd, size=(n_boot, target_fit.size)))
+    sg = None if sigma is None else np.broadcast_to(np.asarray(sigma, dtype=np.float64), (n_boot, np.size(sigma)))
+    res = eng.nlls_local_batch(model, np.tile(np.asarray(popt_best, dtype=np.float64), (n_boot, 1)), init_cond, num_psites,
+                               time_points, noisy[:, :L], lb, ub, sigma=sg, group=np.arange(n_boot, dtype=np.int32),
+                               lam=lam, log_params=(model == "randmod"), **nlls_kw)
+    ok = res["status"] > 0
+    est = np.where(ok[:, None], res["theta"], np.asarray(popt_best, dtype=np.float64)[None, :])   # a failed refit keeps popt_best
+    return {"popt_mean": est.mean(axis=0), "estimates": est, "ok": ok, "score": res["score"], "cost": res["cost"]}

@@ -216,3 +216,27 @@ def test_sharded_gather_world2_gloo(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2, out.stdout          # both ranks finished (lines may interleave)
+
+
+def test_sigma_builders_match_reference_goldens():
+    """phoskintime_b200.models.weights (early_emphasis, full_weight, get_weight_options) against the unmodified
+    reference's models/weights.py:10-76, 148-240 (tests/golden/weights.npz, oracle/gen_golden_weights.py): every one
+    of the 17 sigma options, with and without USE_CUSTOM_WEIGHTS, 1 / 3 / 5 sites."""
+    from conftest import GOLDEN
+    from phoskintime_b200.models import weights as W
+    g = np.load(os.path.join(GOLDEN, "weights.npz"))
+    t = g["t"]
+    for custom in (1, 0):
+        for ns in (1, 3, 5):
+            tag = f"ns{ns}_c{custom}"
+            early = W.early_emphasis(g[f"{tag}_pr"], g[f"{tag}_p"], t, ns)
+            assert np.allclose(early, g[f"{tag}_early"], rtol=1e-15, atol=0)
+            opts = W.get_weight_options(g[f"{tag}_target"], t, ns, True, 4 + 2 * ns, early, g[f"{tag}_ms"],
+                                        use_custom_weights=bool(custom))
+            assert list(opts.keys()) == [str(k) for k in g[f"{tag}_keys"]]
+            assert len(opts) == (17 if custom else 1)
+            for k, v in opts.items():
+                # (inverse_moving_avg divides by x - mean3(x): SciPy's running-sum filter and a direct 3-term sum round
+                #  differently, amplified by the cancellation -> 1e-12 instead of 1e-14)
+                assert v.shape == g[f"{tag}_opt_{k}"].shape and np.allclose(v, g[f"{tag}_opt_{k}"], rtol=1e-12, atol=0), (tag, k)
+            assert np.array_equal(W.full_weight(g[f"{tag}_ms"], False, 4 + 2 * ns), g[f"{tag}_full_noreg"])
