@@ -314,6 +314,18 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* job);
 int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const double* Y, int64_t B, int32_t T,
                          int32_t loss_mode, double* out_loss);
 
+/* f(t, y) and the analytic Jacobian df/dy for B (parameter vector, state, time) triples of one uploaded network — the
+ * device form of the reference's `fun(t, y)` closures (global_model/model_ivp.py:49-277: make_solve_ivp_fun_*), of
+ * `rhs_odeint` (jacspeedup.py:175-375) and of `fd_jacobian_odeint` (jacspeedup.py:397-588; here analytic, not a finite
+ * difference).  params [B,P] (raw thetas with theta_mode = 1), Y [B,state_dim], t_host [B] HOST (selects the kinase
+ * bucket, utils.py:210-225), out_f [B,state_dim], out_J [B,state_dim,state_dim] row-major (J[i][j] = df_i/dy_j) or NULL.
+ * Direct mode = the exact argument list of make_solve_ivp_fun_* (model_ivp.py:49-61): tf_direct [B,N] (the TF_inputs the
+ * closure receives) and S_direct [B,total_sites] (its S_all / the S_cache column) replace the topology's kinase and TF
+ * matrices (t_host may be NULL); the TF input is then squashed once, as the block kernels do (models.py:52). */
+int pk_global_rhs_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, int64_t B, const double* params, int32_t theta_mode,
+                        const double* Y, const double* t_host, double* out_f, double* out_J, const double* tf_direct,
+                        const double* S_direct);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,17 +46,22 @@ def stub_modules(model, loss_mode):
     sys.modules["global_model.config"] = gc
 
 
-def run_case(model, N, K, max_sites, seed, B=4):
+def build_reference_system(model, N, K, max_sites, seed):
+    """(host mirror system, UNMODIFIED reference System, reference modules) around one synthetic topology; checks that the
+    reference's own odeint_args() equals the host mirror's, array by array."""
     from scipy import sparse
-    from scipy.integrate import odeint
-    from phoskintime_b200.global_model import synthetic_system, synthetic_loss_data
+    from phoskintime_b200.global_model import synthetic_system
     stub_modules(model, 0)
     import importlib
     network = importlib.import_module("global_model.network")
     simulate = importlib.import_module("global_model.simulate")
     jac = importlib.import_module("global_model.jacspeedup")
-
     s = synthetic_system(seed=seed, N=N, K=K, max_sites=max_sites, model=model)
+    ref, args = _reference_system(model, N, K, s, network, jac, sparse)
+    return s, ref, simulate, jac
+
+
+def _reference_system(model, N, K, s, network, jac, sparse):
     names = [f"P{i:03d}" for i in range(N)]
     kin_names = [f"K{k:03d}" for k in range(K)]
     p2i = {n: i for i, n in enumerate(names)}
@@ -87,6 +92,13 @@ def run_case(model, N, K, max_sites, seed, B=4):
         for a, b in zip(args, s.odeint_args()):
             assert np.array_equal(np.asarray(a), np.asarray(b)), "odeint_args wire format mismatch"
 
+    return ref, args
+
+
+def run_case(model, N, K, max_sites, seed, B=4):
+    from scipy.integrate import odeint
+    from phoskintime_b200.global_model import synthetic_loss_data
+    s, ref, simulate, jac = build_reference_system(model, N, K, max_sites, seed)
     rng = np.random.default_rng(seed + 100)
     P = np.empty((B, s.n_params))
     Ys, Yt = [], []

@@ -512,6 +512,10 @@ __device__ __forceinline__ void eval_rhs_comb(const GlobalCtx& cx, const double*
 
 // f(src) -> dst.  With FACTOR: also the transcription gains g_i, the per-protein tree factorisation of
 // A = I - c J_blk, the unit responses w = A^-1 e_R and m_i.  Two phases, thread per protein.
+template <bool FACTOR>
+__device__ __forceinline__ void block_kinetics(const GlobalCtx& cx, const double* src, double* dst, double c, int i,
+                                               double synth, double dsdv, double itd);
+
 template <bool FACTOR, bool COMB>
 __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src, double* dst, double c) {
     const int N = cx.N, model = cx.model;
@@ -532,13 +536,24 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
     }
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
-        const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
         double v = 0.0;
         for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) v = fma(cx.tfdata[q], cx.pvec[cx.tfidx[q]], v);
         const double itd = cx.tfdeg[i];                               // 1/tf_deg, inverted once at staging
         v *= itd;
         double synth, dsdv;
         synth_rate(model, v, cx.cA[i], cx.tfs, synth, dsdv);
+        block_kinetics<FACTOR>(cx, src, dst, c, i, synth, dsdv, itd);
+    }
+    __syncthreads();
+}
+
+// Block kinetics of protein i (models 0 / 1 / 4) given its mRNA synthesis rate: the part of eval_rhs after the TF input.
+template <bool FACTOR>
+__device__ __forceinline__ void block_kinetics(const GlobalCtx& cx, const double* src, double* dst, double c, int i,
+                                               double synth, double dsdv, double itd) {
+    const int model = cx.model;
+    {
+        const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
         const double R = src[st], P = src[st + 1];
         const double Bi = cx.cB[i], Ci = cx.cC[i], Di = cx.cD[i], Ei = cx.cE[i];
         dst[st] = fma(-Bi, R, synth);
@@ -622,7 +637,6 @@ __device__ __forceinline__ void eval_rhs(const GlobalCtx& cx, const double* src,
             cx.m[i] = msum;
         }
     }
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1305,6 +1319,171 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
             const double mv = metric_value(tp, traj, n, a.metric, a.n_mt_prot, a.n_mt_rna, a.n_mt_pho, a.mt_prot, a.mt_rna,
                                            a.mt_pho, a.mb_prot, a.mb_rna, a.mb_pho, cx.red, a.out_fc, a.nfc, &s_sys);
             if (threadIdx.x == 0 && a.out_metric) a.out_metric[sys] = mv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RHS / analytic Jacobian export (pk_global_rhs_batch) — the device form of the reference's `fun(t, y)` closures
+// (global_model/model_ivp.py:49-277) and of `rhs_odeint` / `fd_jacobian_odeint` (jacspeedup.py:175-375, 397-588):
+// one CTA per (parameter vector, state, time bucket) triple.  f comes from the integrator's OWN eval_rhs (so this is a
+// direct window on what global_net_kernel integrates); J[i][j] = d f_i / d y_j is the analytic Jacobian the Rosenbrock
+// kernel factorises implicitly (block part + transcription coupling), written out densely.
+// ------------------------------------------------------------------------------------------------
+struct GlobalRjArgs {
+    GlobalTopoDev tp;
+    long long B;
+    int P;
+    const double* params;             // [B,P] physical values (raw thetas are transformed by softplus_kernel first)
+    const double* Y;                  // [B,n]
+    const int* bucket;                // [B] kinase bucket of each evaluation time
+    double* out_f;                    // [B,n]
+    double* out_J;                    // [B,n,n] row-major or nullptr
+    // direct mode (the model_ivp.py closures): the caller supplies the TF inputs [B,N] and the phosphorylation rates
+    // S_all [B,S] themselves; the kinase / TF matrices of the topology are not consulted and the TF input is squashed
+    // once (models.py:52), not twice
+    const double* tf_direct;
+    const double* S_direct;
+};
+
+__global__ void softplus_kernel(const double* in, double* out, long long n) {     // params.py:106-132
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = softplus_d(in[i]);
+}
+
+template <bool COMB>
+__global__ void __launch_bounds__(GLOBAL_BLOCK) global_rhsjac_kernel(const GlobalRjArgs a) {
+    extern __shared__ double smem[];
+    const GlobalTopoDev& tp = a.tp;
+    const int n = tp.n, N = tp.N, K = tp.K, S = tp.S, P = a.P;
+    double* par = smem;
+    double* Kt = par + P;
+    double* Sall = Kt + K;
+    double* pvec = Sall + S;
+    double* y = pvec + N;
+    double* dst = y + n;
+    double* itd = dst + n;                         // 1 / tf_deg
+    int* sprot = (int*)(itd + N);
+    GlobalCtx cx{tp, par, Kt, Sall, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pvec, nullptr, nullptr, nullptr,
+                 nullptr, nullptr, nullptr, nullptr, 0, n, N, tp.nQ, tp.model,
+                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                 tp.offset_y, tp.offset_s, tp.n_sites, tp.driver_map, tp.TF_indptr, tp.TF_indices, tp.qlist, tp.qpos, sprot,
+                 nullptr, tp.TF_data, itd, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cx.cA = par + K; cx.cB = cx.cA + N; cx.cC = cx.cB + N; cx.cD = cx.cC + N; cx.cDp = cx.cD + N; cx.cE = cx.cDp + S;
+    for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+        itd[i] = 1.0 / tp.tf_deg[i];               // (the same division global_net_kernel performs when it stages the topology)
+        const int st = tp.offset_y[i], bl = COMB ? 1 + (1 << tp.n_sites[i]) : 2 + tp.n_sites[i];
+        for (int j = 0; j < bl; ++j) sprot[st + j] = i;
+    }
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += GLOBAL_BLOCK) par[i] = a.params[(size_t)b * P + i];
+        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) y[i] = a.Y[(size_t)b * n + i];
+        __syncthreads();
+        cx.tfs = par[P - 1];
+        const bool direct = a.tf_direct != nullptr;
+        if (direct) {
+            for (int s2 = threadIdx.x; s2 < S; s2 += GLOBAL_BLOCK) Sall[s2] = a.S_direct[(size_t)b * S + s2];
+            __syncthreads();
+            for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+                double synth, dsdv;
+                synth_rate(4, a.tf_direct[(size_t)b * N + i], cx.cA[i], cx.tfs, synth, dsdv);     // one squash (k = 1)
+                if constexpr (COMB) dst[cx.offy[i]] = fma(-cx.cB[i], y[cx.offy[i]], synth);
+                else block_kinetics<false>(cx, y, dst, 0.0, i, synth, 0.0, 0.0);
+            }
+            if constexpr (COMB) {
+                for (int s2 = threadIdx.x; s2 < n; s2 += GLOBAL_BLOCK) {
+                    const int i = sprot[s2], m = s2 - cx.offy[i] - 1;
+                    if (m >= 0) dst[s2] = comb_state_rhs(cx, y, i, m);
+                }
+            }
+            __syncthreads();
+        } else {
+            const int jb = a.bucket[b];
+            for (int k = threadIdx.x; k < K; k += GLOBAL_BLOCK) Kt[k] = tp.kin_Kmat[(size_t)k * tp.nb + jb] * par[k];
+            __syncthreads();
+            for (int s2 = threadIdx.x; s2 < S; s2 += GLOBAL_BLOCK) {
+                double acc = 0.0;
+                for (int q = tp.W_indptr[s2]; q < tp.W_indptr[s2 + 1]; ++q) acc = fma(tp.W_data[q], Kt[tp.W_indices[q]], acc);
+                Sall[s2] = acc;
+            }
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, y, dst, 0.0);               // ends with a barrier; pvec holds the TF inputs' sources
+        }
+        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) a.out_f[(size_t)b * n + i] = dst[i];
+        if (!a.out_J) continue;
+        double* J = a.out_J + (size_t)b * n * n;
+        for (size_t e = threadIdx.x; e < (size_t)n * n; e += GLOBAL_BLOCK) J[e] = 0.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+            const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
+            double* rowR = J + (size_t)st * n;
+            // mRNA row: -B on the diagonal, transcription gain times the TF row over every state that enters the
+            // regulator's total protein (driven regulators follow the kinase trace instead: no state dependence)
+            if (!direct) {
+                double v = 0.0;
+                for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) v = fma(cx.tfdata[q], pvec[cx.tfidx[q]], v);
+                v *= itd[i];
+                double synth, dsdv;
+                synth_rate(COMB ? 2 : cx.model, v, cx.cA[i], cx.tfs, synth, dsdv);
+                const double g = dsdv * itd[i];
+                for (int q = cx.tfptr[i]; q < cx.tfptr[i + 1]; ++q) {
+                    const int r = cx.tfidx[q];
+                    if (!COMB && cx.drv[r] >= 0) continue;
+                    const int rs = cx.offy[r], cnt = COMB ? (1 << cx.ns[r]) : 1 + cx.ns[r];
+                    for (int k = 0; k < cnt; ++k) rowR[rs + 1 + k] += g * cx.tfdata[q];
+                }
+            }
+            rowR[st] += -cx.cB[i];
+            const double R = y[st], Pp = y[st + 1];
+            const double Ci = cx.cC[i], Di = cx.cD[i], Ei = cx.cE[i];
+            if constexpr (COMB) {
+                const int nstt = 1 << ns;
+                for (int m = 0; m < nstt; ++m) {
+                    double* row = J + (size_t)(st + 1 + m) * n + st + 1;
+                    double out = (m == 0) ? Di : 0.0;
+                    for (int j = 0; j < ns; ++j) {
+                        const int bit = 1 << j;
+                        const double sj = Sall[ss + j];
+                        if (m & bit) { out += Ei + cx.cDp[ss + j] + Di; row[m ^ bit] += sj; }
+                        else { out += sj; row[m | bit] += Ei; }
+                    }
+                    row[m] += -out;
+                    if (m == 0) J[(size_t)(st + 1) * n + st] += Ci;
+                }
+            } else {
+                double* rowP = J + (size_t)(st + 1) * n;
+                const int model = cx.model;
+                if (model == 0 || model == 4) {
+                    const double iP2 = (model == 4) ? fast_rcp((1.0 + Pp) * (1.0 + Pp)) : 1.0;
+                    const double iR2 = (model == 4) ? fast_rcp((1.0 + R) * (1.0 + R)) : 1.0;
+                    double sumS = 0.0;
+                    for (int j = 0; j < ns; ++j) {
+                        const double sj = Sall[ss + j];
+                        sumS += sj;
+                        double* rowS = J + (size_t)(st + 2 + j) * n;
+                        rowS[st + 1] += sj * iP2;
+                        rowS[st + 2 + j] += -(Ei + cx.cDp[ss + j] + Di);
+                        rowP[st + 2 + j] += Ei;
+                    }
+                    rowP[st] += Ci * iR2;
+                    rowP[st + 1] += -Di - sumS * iP2;
+                } else {                                          // sequential chain
+                    rowP[st] += Ci;
+                    if (ns == 0) rowP[st + 1] += -Di;
+                    else {
+                        rowP[st + 1] += -(Di + Sall[ss]);
+                        rowP[st + 2] += Ei;
+                        for (int j = 0; j < ns; ++j) {
+                            double* rowS = J + (size_t)(st + 2 + j) * n;
+                            double out = Ei + cx.cDp[ss + j] + Di;
+                            rowS[st + 1 + j] += Sall[ss + j];
+                            if (j < ns - 1) { rowS[st + 3 + j] += Ei; out += Sall[ss + j + 1]; }
+                            rowS[st + 2 + j] += -out;
+                        }
+                    }
+                }
+            }
         }
     }
 }

@@ -589,8 +589,76 @@ int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const
     return 0;
 }
 
-#ifdef PK_GLOBAL_TRACE
 // debug build only: per-phase cycle totals of CTA 0 (see PH() in global_net.cuh); reading clears them
+int pk_global_rhs_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, int64_t B, const double* params, int32_t theta_mode,
+                        const double* Y, const double* t_host, double* out_f, double* out_J, const double* tf_direct,
+                        const double* S_direct) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_rhs_batch: unknown topology id");
+    if ((tf_direct == nullptr) != (S_direct == nullptr)) return fail("pk_global_rhs_batch: tf_direct and S_direct go together");
+    if (B < 0 || !params || !Y || (!t_host && !tf_direct) || !out_f) return fail("pk_global_rhs_batch: params, Y, t and out_f are required");
+    h->last_launches = 0;
+    if (B == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const pk::GlobalTopoDev& d = th->dev;
+    const int n = d.n, P = th->P;
+    const bool host = memspace == PK_HOST;
+    cudaStream_t st = h->stream;
+    std::vector<int> bucket((size_t)B);
+    for (int64_t b = 0; b < B && t_host; ++b) bucket[(size_t)b] = pkh::bucket_of(t_host[b], th->kin_grid);   // utils.py:210-225
+    pk::GlobalRjArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tp = d; a.B = B; a.P = P;
+    CK(h->g_stops.ensure((size_t)B * sizeof(int)));
+    CK(cudaMemcpy(h->g_stops.p, bucket.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice));
+    a.bucket = (const int*)h->g_stops.p;
+    const size_t nf = (size_t)B * n, nJ = out_J ? (size_t)B * n * n : 0;
+    if (host) {
+        CK(h->g_params.ensure((size_t)B * P * sizeof(double)));
+        CK(h->g_y0.ensure(nf * sizeof(double)));
+        CK(h->g_Y.ensure((nf + nJ) * sizeof(double)));
+        CK(cudaMemcpyAsync(h->g_params.p, params, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->g_y0.p, Y, nf * sizeof(double), cudaMemcpyHostToDevice, st));
+        a.params = (const double*)h->g_params.p; a.Y = (const double*)h->g_y0.p;
+        a.out_f = (double*)h->g_Y.p; a.out_J = out_J ? (double*)h->g_Y.p + nf : nullptr;
+        if (tf_direct) {
+            const size_t ntf = (size_t)B * d.N, nS = (size_t)B * d.S;
+            CK(h->g_traj.ensure((ntf + nS) * sizeof(double)));
+            CK(cudaMemcpyAsync(h->g_traj.p, tf_direct, ntf * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync((double*)h->g_traj.p + ntf, S_direct, nS * sizeof(double), cudaMemcpyHostToDevice, st));
+            a.tf_direct = (const double*)h->g_traj.p;
+            a.S_direct = (const double*)h->g_traj.p + ntf;
+        }
+    } else {
+        a.params = params; a.Y = Y; a.out_f = out_f; a.out_J = out_J;
+        a.tf_direct = tf_direct; a.S_direct = S_direct;
+    }
+    if (theta_mode) {              // raw decision vectors -> physical parameters (params.py:106-132), in a scratch copy
+        const long long np_ = (long long)B * P;
+        CK(h->g_F.ensure((size_t)np_ * sizeof(double)));
+        pk::softplus_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, st>>>(a.params, (double*)h->g_F.p, np_);
+        a.params = (const double*)h->g_F.p;
+    }
+    const size_t smem = ((size_t)P + d.K + d.S + 2 * (size_t)d.N + 2 * (size_t)n) * sizeof(double) + (size_t)n * sizeof(int);
+    auto kern = d.model == 2 ? pk::global_rhsjac_kernel<true> : pk::global_rhsjac_kernel<false>;
+    if (smem > 227 * 1024) return fail("pk_global_rhs_batch: network too large for one CTA's shared memory");
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)h->sm_count * 4);
+    CK(cudaEventRecord(h->ev0, st));
+    kern<<<grid, pk::GLOBAL_BLOCK, smem, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->last_launches = 1;
+    if (host) {
+        CK(cudaMemcpyAsync(out_f, a.out_f, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (out_J) CK(cudaMemcpyAsync(out_J, a.out_J, nJ * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+#ifdef PK_GLOBAL_TRACE
 int pk_global_trace_read(unsigned long long* out16) {
     unsigned long long zero[16] = {0};
     if (cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(zero)) != cudaSuccess) return fail("trace read failed");

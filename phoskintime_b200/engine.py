@@ -520,6 +520,56 @@ class Engine:
                                                  int(loss_mode), xp.ptr(out)))
         return out
 
+    def global_rhs_batch(self, topo, params, Y, t=None, *, theta_mode=False, want_jac=False, tf_inputs=None, S_all=None):
+        """f(t, y) (and the analytic Jacobian df/dy) of one uploaded network for B (parameter vector, state, time)
+        triples — `pk_global_rhs_batch`.  params [B,P] or [P] (broadcast), Y [B,n], t scalar or [B].  With `tf_inputs`
+        [B,N] and `S_all` [B,total_sites] the call has the semantics of the reference's model_ivp closures (the kinase /
+        TF matrices are not consulted).  Returns f[B,n] or (f, J[B,n,n])."""
+        dev = _is_torch(Y)
+        xp = _TorchOps(Y.device) if dev else _NumpyOps()
+        Y = xp.f64(Y)
+        Y = Y.reshape(1, -1) if Y.ndim == 1 else Y
+        B, n = int(Y.shape[0]), int(Y.shape[1])
+        dims = self.global_dims(topo)
+        if n != dims["state_dim"]:
+            raise ValueError(f"Y must have {dims['state_dim']} columns")
+        params = xp.f64(params)
+        if params.ndim == 1:
+            params = params.reshape(1, -1)
+        if params.shape[0] == 1 and B > 1:
+            params = xp.f64(params.repeat(B, 1) if dev else np.repeat(params, B, axis=0))
+        if tuple(params.shape) != (B, dims["n_params"]):
+            raise ValueError(f"params must be [{B},{dims['n_params']}]")
+        direct = tf_inputs is not None or S_all is not None
+        keep = [params, Y]
+        tf_p = s_p = t_p = None
+        if direct:
+            if tf_inputs is None or S_all is None:
+                raise ValueError("tf_inputs and S_all go together")
+            cnt = dims
+            tf_a, s_a = xp.f64(tf_inputs), xp.f64(S_all)
+            tf_a = tf_a.reshape(1, -1) if tf_a.ndim == 1 else tf_a
+            s_a = s_a.reshape(1, -1) if s_a.ndim == 1 else s_a
+            if tuple(tf_a.shape) != (B, cnt["n_proteins"]) or tuple(s_a.shape) != (B, cnt["total_sites"]):
+                raise ValueError(f"tf_inputs must be [{B},{cnt['n_proteins']}] and S_all [{B},{cnt['total_sites']}]")
+            keep += [tf_a, s_a]
+            tf_p, s_p = xp.ptr(tf_a), xp.ptr(s_a)
+        else:
+            if t is None:
+                raise ValueError("t is required")
+            t_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=np.float64), (B,)))
+            keep.append(t_arr)
+            t_p = t_arr.ctypes.data_as(C.c_void_p)
+        f = xp.empty((B, n), "f64")
+        J = xp.empty((B, n, n), "f64") if want_jac else None
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_global_rhs_batch(self._h, int(topo), PK_DEVICE if dev else PK_HOST, B, xp.ptr(params),
+                                                int(bool(theta_mode)), xp.ptr(Y), t_p, xp.ptr(f), xp.ptr(J) if want_jac else None,
+                                                tf_p, s_p))
+        del keep
+        return (f, J) if want_jac else f
+
     # ------------------------------------------------------------------------- multi-GPU
     def init_nccl(self, world, rank, id_bytes):
         _lib.check(self.lib.pk_nccl_init(self._h, id_bytes, int(world), int(rank)))

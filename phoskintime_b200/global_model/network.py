@@ -77,6 +77,24 @@ class GlobalSystem:
         self._topo_id = {}          # engine id -> uploaded topology id
         self._loss_key = {}         # engine id -> loss-table dict currently installed
 
+    @classmethod
+    def shell(cls, model, n_sites, offset_y=None, offset_s=None):
+        """A network with the block layout only (one dummy kinase, no W / TF edges): what the loss-only and the
+        direct-mode RHS calls need.  `offset_y` / `offset_s`, when given, must be the packed layout."""
+        n_sites = np.ascontiguousarray(n_sites, dtype=np.int32)
+        N, S = n_sites.size, int(n_sites.sum())
+        z = np.zeros(N)
+        sh = cls(n_sites=n_sites, W_indptr=np.zeros(S + 1, np.int32), W_indices=[], W_data=[],
+                 TF_indptr=np.zeros(N + 1, np.int32), TF_indices=[], TF_data=[], kin_grid=[0.0], kin_Kmat=np.ones((1, 1)),
+                 tf_deg=np.ones(N), driver_map=np.full(N, -1),
+                 defaults={"c_k": [1.0], "A_i": z, "B_i": z, "C_i": z, "D_i": z, "Dp_i": np.zeros(S), "E_i": z, "tf_scale": 0.0},
+                 model=model)
+        if offset_y is not None and not np.array_equal(np.asarray(offset_y), sh.idx.offset_y):
+            raise ValueError("offset_y must be the packed per-protein block layout (network.py:28-167)")
+        if offset_s is not None and not np.array_equal(np.asarray(offset_s), sh.idx.offset_s):
+            raise ValueError("offset_s must be the running sum of n_sites")
+        return sh
+
     # ---- reference surface -----------------------------------------------------------------
     def update(self, c_k, A_i, B_i, C_i, D_i, Dp_i, E_i, tf_scale):
         """network.py:293-302 — in-place parameter write-through."""

@@ -431,3 +431,75 @@ def test_fold_change_tables_and_metrics_match_reference(engine, path):
         r = simulate_batch(s, g["phys"], g["t_grid"], ("metric",), rtol=1e-5, atol=1e-7, mxstep=5000, metric=str(name),
                            metric_times=mt, engine=engine)
         assert np.all(np.abs(r["metric"] - g["metrics"][:, m]) <= 3e-5 * np.abs(g["metrics"][:, m])), name
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RHS / Jacobian export (pk_global_rhs_batch) and the model_ivp closures against the UNMODIFIED reference
+# (tests/golden/globalrhs_*.npz, oracle/gen_golden_rhs.py: rhs_odeint, fd_jacobian_odeint, make_solve_ivp_fun_*).
+RHS_FILES = sorted(glob.glob(os.path.join(GOLDEN, "globalrhs_*.npz")))
+RHS_IDS = [os.path.basename(f)[10:-4] for f in RHS_FILES]
+
+
+@pytest.mark.parametrize("path", RHS_FILES, ids=RHS_IDS)
+def test_rhs_and_jacobian_match_reference(engine, path):
+    """f = the integrator's own eval_rhs vs the reference's rhs_odeint (1e-12: the reference kernels are numba fastmath);
+    analytic J vs the reference's forward-difference Jacobian (step 1e-8*max(1,|y|): 1e-6 relative to the row scale),
+    and vs a central difference of the device RHS itself (1e-8)."""
+    from phoskintime_b200.global_model import make_solve_ivp_fun
+    g = np.load(path)
+    s = synthetic_system(seed=int(g["seed"]), N=int(g["N"]), K=int(g["K"]), max_sites=int(g["max_sites"]), model=int(g["model"]))
+    fun = make_solve_ivp_fun(s, engine=engine)
+    B, n = g["Y"].shape
+    f, J = engine.global_rhs_batch(fun_topology(s, engine), g["params"], g["Y"], g["t"], want_jac=True)
+    assert f.shape == (B, n) and J.shape == (B, n, n)
+    assert np.all(np.abs(f - g["f"]) <= 1e-12 * np.abs(g["f"]) + 1e-13), float(np.max(np.abs(f - g["f"])))
+    scale = np.maximum(np.abs(g["J_fd"]).max(axis=2, keepdims=True), 1.0)
+    assert np.all(np.abs(J - g["J_fd"]) <= 2e-6 * scale), float(np.max(np.abs(J - g["J_fd"]) / scale))
+    assert np.array_equal(J != 0, np.abs(g["J_fd"]) > 1e-7 * scale) or np.mean((J != 0) == (np.abs(g["J_fd"]) > 1e-7 * scale)) > 0.995
+    # central difference of the device RHS: rounding-level agreement with the analytic Jacobian
+    b = 3
+    y0, h = g["Y"][b], 1e-6 * np.maximum(1.0, np.abs(g["Y"][b]))
+    Yp = np.concatenate([y0[None, :] + np.diag(h), y0[None, :] - np.diag(h)])
+    fp = engine.global_rhs_batch(fun_topology(s, engine), g["params"][b], Yp, float(g["t"][b]))
+    Jc = ((fp[:n] - fp[n:]) / (2 * h)[:, None]).T
+    assert np.all(np.abs(J[b] - Jc) <= 1e-7 * scale[b]), float(np.max(np.abs(J[b] - Jc) / scale[b]))
+    # the closure form: current parameters of the system, one state
+    s.update(**s.unpack_params(g["params"][0]))
+    assert np.array_equal(fun(float(g["t"][0]), g["Y"][0]), f[0]) and np.array_equal(fun.jac(float(g["t"][0]), g["Y"][0]), J[0])
+
+
+def fun_topology(s, engine):
+    from phoskintime_b200.global_model.simulate import _topology
+    return _topology(s, engine)
+
+
+@pytest.mark.parametrize("path", RHS_FILES, ids=RHS_IDS)
+def test_model_ivp_closures_match_reference(engine, path):
+    """make_solve_ivp_fun_{distributive,sequential,combinatorial,saturating} (model_ivp.py:49-277): same keyword
+    signature, caller-supplied TF inputs and S_all, dy within 1e-12 of the reference closure."""
+    from phoskintime_b200.global_model import (make_solve_ivp_fun_combinatorial, make_solve_ivp_fun_distributive,
+                                               make_solve_ivp_fun_saturating, make_solve_ivp_fun_sequential)
+    g = np.load(path)
+    model = int(g["model"])
+    s = synthetic_system(seed=int(g["seed"]), N=int(g["N"]), K=int(g["K"]), max_sites=int(g["max_sites"]), model=model)
+    p = s.unpack_params(g["ivp_params"])
+    kw = dict(A_i=p["A_i"], B_i=p["B_i"], C_i=p["C_i"], D_i=p["D_i"], Dp_i=p["Dp_i"], E_i=p["E_i"], tf_scale=p["tf_scale"],
+              tf_input=g["ivp_tf"], offset_y=s.idx.offset_y, offset_s=s.idx.offset_s, n_sites=s.idx.n_sites, engine=engine)
+    if model == 2:
+        fun = make_solve_ivp_fun_combinatorial(S_cache=g["ivp_S_cache"], jb=int(g["ivp_jb"]), n_states=s.idx.n_states, **kw)
+    else:
+        fun = {0: make_solve_ivp_fun_distributive, 1: make_solve_ivp_fun_sequential, 4: make_solve_ivp_fun_saturating}[model](
+            S_all=g["ivp_S_all"], **kw)
+    for y, ref in zip(g["ivp_Y"], g["ivp_f"]):
+        dy = fun(1.0, y)
+        assert np.all(np.abs(dy - ref) <= 1e-12 * np.abs(ref) + 1e-13), float(np.max(np.abs(dy - ref)))
+    dyb = fun.batch(1.0, g["ivp_Y"])
+    assert np.allclose(dyb, g["ivp_f"], rtol=1e-12, atol=1e-13)
+    # a callable TF input (time and state dependent) is honoured per state
+    fun2_kw = dict(kw, tf_input=lambda t, y=None: g["ivp_tf"] * (1.0 + 0.0 * t))
+    if model != 2:
+        fun2 = {0: make_solve_ivp_fun_distributive, 1: make_solve_ivp_fun_sequential, 4: make_solve_ivp_fun_saturating}[model](
+            S_all=g["ivp_S_all"], **fun2_kw)
+        assert np.array_equal(fun2(1.0, g["ivp_Y"][0]), fun(1.0, g["ivp_Y"][0]))
+    Jb = fun.jac(1.0, g["ivp_Y"][1])
+    assert Jb.shape == (s.idx.state_dim, s.idx.state_dim) and np.isfinite(Jb).all()
