@@ -1352,7 +1352,7 @@ __global__ void softplus_kernel(const double* in, double* out, long long n) {   
 }
 
 template <bool COMB>
-__global__ void __launch_bounds__(GLOBAL_BLOCK) global_rhsjac_kernel(const GlobalRjArgs a) {
+__global__ void __launch_bounds__(GLOBAL_BLOCK, 2) global_rhsjac_kernel(const GlobalRjArgs a) {
     extern __shared__ double smem[];
     const GlobalTopoDev& tp = a.tp;
     const int n = tp.n, N = tp.N, K = tp.K, S = tp.S, P = a.P;
