@@ -314,6 +314,15 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* job);
 int pk_global_loss_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, const double* Y, int64_t B, int32_t T,
                          int32_t loss_mode, double* out_loss);
 
+/* The reference's CUSTOM solver — `solve_custom(sys, y0, t_eval, rtol, atol)` (global_model/jacspeedup.py:31-67) ->
+ * `adaptive_rk45_model01` / `adaptive_rk45_model2` (global_model/solvers.py:292-758) — reproduced step for step on the
+ * device for B parameter vectors: explicit Dormand-Prince 5(4), PI control, dt <= 1, landing on kinase-bucket
+ * boundaries, cubic-Hermite outputs (rtol/atol <= 0 -> the reference's 1e-5 / 1e-7, max_steps <= 0 -> 2 000 000).
+ * out_Y [B,T,state_dim]; status 0 ok, 1 max steps, 3 non-finite.  (pk_global_solve_batch is the accurate default.) */
+int pk_global_solve_custom(pk_handle_t h, int32_t topo_id, int32_t memspace, int64_t B, const double* params, int32_t theta_mode,
+                           const double* y0, int64_t y0_stride, const double* t_eval_host, int32_t T, double rtol, double atol,
+                           int32_t max_steps, double* out_Y, int32_t* out_status, int32_t* out_nsteps, int32_t* out_nrej);
+
 /* f(t, y) and the analytic Jacobian df/dy for B (parameter vector, state, time) triples of one uploaded network — the
  * device form of the reference's `fun(t, y)` closures (global_model/model_ivp.py:49-277: make_solve_ivp_fun_*), of
  * `rhs_odeint` (jacspeedup.py:175-375) and of `fd_jacobian_odeint` (jacspeedup.py:397-588; here analytic, not a finite

@@ -57,11 +57,20 @@ def run_case(model, N, K, max_sites, seed):
                  4: ivp.make_solve_ivp_fun_saturating}[model]
         fun = maker(S_all=S_all, **kw)
         extra = {"ivp_S_all": S_all}
+    # the reference's custom DOPRI5 solver (jacspeedup.py:31-67 -> solvers.py:292-758) at two tolerance pairs
+    custom = {}
+    for tag, (rt, at) in (("a", (1e-5, 1e-7)), ("b", (1e-4, 1e-6))):
+        outs = []
+        for b in (0, 1, 3):
+            ref.update(**s.unpack_params(g["params"][b]))
+            outs.append(np.array(jac.solve_custom(ref, ref.y0(), g["t"], rt, at), copy=True))
+        custom[f"custom_Y_{tag}"] = np.array(outs)
+        custom[f"custom_tol_{tag}"] = np.array([rt, at])
     ivp_Y = np.array([g["Y"][1][k] for k in (0, 5, 10)])
     ivp_F = np.array([fun(1.0, np.ascontiguousarray(y)) for y in ivp_Y])
     np.savez_compressed(os.path.join(OUT, f"globalrhs_m{model}_N{N}.npz"), model=model, N=N, K=K, max_sites=max_sites, seed=seed,
                         params=np.array(P), Y=np.array(Y), t=np.array(T), f=np.array(F), J_fd=np.array(J),
-                        ivp_params=g["params"][1], ivp_tf=tf_in, ivp_Y=ivp_Y, ivp_f=ivp_F, **extra)
+                        ivp_params=g["params"][1], ivp_tf=tf_in, ivp_Y=ivp_Y, ivp_f=ivp_F, custom_rows=np.array([0, 1, 3]), custom_t=g["t"], **custom, **extra)
     print(f"model {model} N={N}: |f| max {np.abs(np.array(F)).max():.3g}, J nnz fraction {np.mean(np.abs(np.array(J)) > 0):.3f}")
 
 

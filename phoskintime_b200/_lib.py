@@ -131,6 +131,9 @@ SYMBOLS = {
     "pk_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "pk_local_solve_allgather": (C.c_int, [C.c_void_p, C.POINTER(PkLocalJob), C.c_int32, C.c_int32, C.c_void_p]),
     "pk_allgather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pk_global_solve_custom": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "pk_global_rhs_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pk_sym_alloc": (C.c_int, [C.c_void_p, C.c_int64, C.c_char_p]),

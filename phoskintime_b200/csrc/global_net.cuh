@@ -1488,4 +1488,210 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, 2) global_rhsjac_kernel(const Gl
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The reference's CUSTOM solver (USE_CUSTOM_SOLVER branch: jacspeedup.py:31-67 -> solvers.py:292-573 / :576-758):
+// explicit Dormand-Prince 5(4) with FSAL, err = max_i |diff_i| / max(atol + rtol max(|y|,|y_new|), 1e-12), accepted when
+// err <= 1, PI step control (beta 0.04, alpha 0.16, safety 0.9, factor in [0.2, 5], dt_init 0.05, dt in [1e-6, 1.0]),
+// steps shortened to land on kinase-bucket boundaries (k1 re-evaluated there, err_prev reset), outputs by cubic Hermite
+// interpolation between accepted steps.  One CTA per system, the seven stage vectors in shared memory, the RHS is the
+// integrator's eval_rhs.  This reproduces the reference function's SEMANTICS (same step sequence up to rounding),
+// including its ~1e-4..1e-5 output error from the third-order interpolant and the dt <= 1 cap (>= 960 steps per solve);
+// `solve_custom(..., method="rosenbrock")` remains the accurate default.
+// ------------------------------------------------------------------------------------------------
+struct GlobalRkArgs {
+    GlobalTopoDev tp;
+    long long B;
+    int P, T, theta_mode, max_steps;
+    const double* params;             // [B,P]
+    const double* y0;                 // [n] or [B, y0_stride]
+    long long y0_stride;
+    const double* t_eval;             // [T]
+    double rtol, atol;
+    double* out_Y;                    // [B,T,n]
+    int *out_status, *out_nsteps, *out_nrej;
+};
+
+template <bool COMB>
+__global__ void __launch_bounds__(GLOBAL_BLOCK, 2) global_dopri5_kernel(const GlobalRkArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double red[GLOBAL_WARPS];
+    const GlobalTopoDev& tp = a.tp;
+    const int n = tp.n, N = tp.N, K = tp.K, S = tp.S, P = a.P, T = a.T, nb = tp.nb;
+    double* par = smem;
+    double* Kt = par + P;
+    double* Sall = Kt + K;
+    double* pvec = Sall + S;
+    double* itd = pvec + N;
+    double* y = itd + N;
+    double* yt = y + n;
+    double* k[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) k[q] = yt + (size_t)(q + 1) * n;
+    int* sprot = (int*)(yt + (size_t)8 * n);
+    GlobalCtx cx{tp, par, Kt, Sall, y, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pvec, nullptr, nullptr, nullptr,
+                 nullptr, nullptr, red, nullptr, 0, n, N, tp.nQ, tp.model,
+                 nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
+                 tp.offset_y, tp.offset_s, tp.n_sites, tp.driver_map, tp.TF_indptr, tp.TF_indices, tp.qlist, tp.qpos, sprot,
+                 nullptr, tp.TF_data, itd, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cx.cA = par + K; cx.cB = cx.cA + N; cx.cC = cx.cB + N; cx.cD = cx.cC + N; cx.cDp = cx.cD + N; cx.cE = cx.cDp + S;
+    for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+        itd[i] = 1.0 / tp.tf_deg[i];
+        const int st = tp.offset_y[i], bl = COMB ? 1 + (1 << tp.n_sites[i]) : 2 + tp.n_sites[i];
+        for (int j = 0; j < bl; ++j) sprot[st + j] = i;
+    }
+    // Dormand-Prince coefficients (solvers.py:351-386)
+    constexpr double a21 = 0.2, a31 = 0.075, a32 = 0.225, a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9,
+                     a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729,
+                     a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656,
+                     b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84,
+                     e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525,
+                     e7 = -1.0 / 40;
+    constexpr double beta = 0.04, alpha = 0.2 - beta, safety = 0.9, dt_init = 0.05, dt_min = 1e-6, dt_max = 1.0;
+    const double* grid = tp.kin_grid;
+
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += GLOBAL_BLOCK) {
+            const double v = a.params[(size_t)b * P + i];
+            par[i] = a.theta_mode ? softplus_d(v) : v;
+        }
+        const double* y0 = a.y0 + (a.y0_stride ? (size_t)b * a.y0_stride : 0);
+        double* Y = a.out_Y + (size_t)b * T * n;
+        for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) { y[i] = y0[i]; Y[i] = y0[i]; }
+        __syncthreads();
+        cx.tfs = par[P - 1];
+        auto set_bucket = [&](int jb) {           // Kt = Kmat[:, jb] * c_k ; S = W Kt  (solvers.py:46-120)
+            __syncthreads();
+            for (int q = threadIdx.x; q < K; q += GLOBAL_BLOCK) Kt[q] = tp.kin_Kmat[(size_t)q * nb + jb] * par[q];
+            __syncthreads();
+            for (int s2 = threadIdx.x; s2 < S; s2 += GLOBAL_BLOCK) {
+                double acc = 0.0;
+                for (int q = tp.W_indptr[s2]; q < tp.W_indptr[s2 + 1]; ++q) acc = fma(tp.W_data[q], Kt[tp.W_indices[q]], acc);
+                Sall[s2] = acc;
+            }
+            __syncthreads();
+        };
+        int jb = 0, next_eval = 1, steps = 0, nacc = 0, nrej = 0, status = 0;
+        double tcur = a.t_eval[0];
+        const double t_final = a.t_eval[T - 1];
+        while (jb + 1 < nb && tcur >= grid[jb + 1]) ++jb;
+        set_bucket(jb);
+        eval_rhs<false, COMB>(cx, y, k[0], 0.0);
+        double dt = dt_init, err_prev = 1.0;
+        bool hit_boundary = false;
+        while (tcur < t_final && next_eval < T) {
+            if (++steps > a.max_steps) { status = 1; break; }
+            bool moved = false;
+            while (jb + 1 < nb && tcur >= grid[jb + 1]) { ++jb; hit_boundary = true; moved = true; }
+            if (moved) set_bucket(jb);
+            if (hit_boundary) {
+                eval_rhs<false, COMB>(cx, y, k[0], 0.0);
+                hit_boundary = false;
+                err_prev = 1.0;
+            }
+            double dt_use = dt, dist_bnd = 1e9;
+            if (jb + 1 < nb) {
+                dist_bnd = grid[jb + 1] - tcur;
+                if (dist_bnd > 1e-15 && dt_use > dist_bnd) dt_use = dist_bnd;
+            }
+            const double rem = t_final - tcur;
+            if (dt_use > rem) dt_use = rem;
+            if (dt_use < dt_min) dt_use = dt_min;
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) yt[i] = y[i] + dt_use * (a21 * k[0][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[1], 0.0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) yt[i] = y[i] + dt_use * (a31 * k[0][i] + a32 * k[1][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[2], 0.0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) yt[i] = y[i] + dt_use * (a41 * k[0][i] + a42 * k[1][i] + a43 * k[2][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[3], 0.0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK)
+                yt[i] = y[i] + dt_use * (a51 * k[0][i] + a52 * k[1][i] + a53 * k[2][i] + a54 * k[3][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[4], 0.0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK)
+                yt[i] = y[i] + dt_use * (a61 * k[0][i] + a62 * k[1][i] + a63 * k[2][i] + a64 * k[3][i] + a65 * k[4][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[5], 0.0);
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK)
+                yt[i] = y[i] + dt_use * (b1 * k[0][i] + b3 * k[2][i] + b4 * k[3][i] + b5 * k[4][i] + b6 * k[5][i]);
+            __syncthreads();
+            eval_rhs<false, COMB>(cx, yt, k[6], 0.0);
+            double errl = 0.0;
+            bool badl = false;
+            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
+                const double diff = dt_use * (e1 * k[0][i] + e3 * k[2][i] + e4 * k[3][i] + e5 * k[4][i] + e6 * k[5][i] + e7 * k[6][i]);
+                double sc = a.atol + a.rtol * fmax(fabs(y[i]), fabs(yt[i]));
+                if (sc < 1e-12) sc = 1e-12;
+                const double ratio = fabs(diff) / sc;
+                badl |= !(ratio < 1e300);
+                errl = fmax(errl, ratio);
+            }
+            // block-wide max (all threads get the same value): warp shuffle, then across the warps through `red`
+            for (int o = 16; o > 0; o >>= 1) errl = fmax(errl, __shfl_xor_sync(0xffffffffu, errl, o));
+            const int anybad = __syncthreads_or(badl ? 1 : 0);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = errl;
+            __syncthreads();
+            double err = red[0];
+#pragma unroll
+            for (int w = 1; w < GLOBAL_WARPS; ++w) err = fmax(err, red[w]);
+            __syncthreads();
+            if (anybad) { status = 3; break; }
+            if (err <= 1.0) {
+                ++nacc;
+                const double t_next = tcur + dt_use;
+                while (next_eval < T && a.t_eval[next_eval] <= t_next) {
+                    const double te = a.t_eval[next_eval];
+                    if (te >= tcur) {                                  // cubic Hermite (solvers.py:262-286)
+                        double* out = Y + (size_t)next_eval * n;
+                        const double h = t_next - tcur;
+                        if (h < 1e-16) {
+                            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) out[i] = yt[i];
+                        } else {
+                            const double tau = (te - tcur) / h, tau2 = tau * tau, tau3 = tau2 * tau;
+                            const double h00 = 2 * tau3 - 3 * tau2 + 1, h10 = tau3 - 2 * tau2 + tau, h01 = -2 * tau3 + 3 * tau2,
+                                         h11 = tau3 - tau2;
+                            for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK)
+                                out[i] = h00 * y[i] + h10 * h * k[0][i] + h01 * yt[i] + h11 * h * k[6][i];
+                        }
+                    }
+                    ++next_eval;
+                }
+                const bool at_bnd = fabs(dt_use - dist_bnd) < 1e-14;
+                for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) {
+                    y[i] = yt[i];
+                    if (!at_bnd) k[0][i] = k[6][i];                    // FSAL
+                }
+                __syncthreads();
+                tcur = t_next;
+                if (at_bnd) hit_boundary = true;                       // derivatives re-evaluated after the jump
+                double fac = (err < 1e-12) ? 5.0 : safety * pow(err, -alpha) * pow(err_prev, beta);
+                if (fac > 5.0) fac = 5.0;
+                if (fac < 0.2) fac = 0.2;
+                dt = dt * fac;
+                if (dt > dt_max) dt = dt_max;
+                err_prev = err < 1e-4 ? 1e-4 : err;
+            } else {
+                ++nrej;
+                double fac = safety * pow(err, -0.2);
+                if (fac < 0.1) fac = 0.1;
+                dt = dt_use * fac;
+                if (dt < dt_min) dt = dt_min;
+                err_prev = 1.0;
+            }
+        }
+        if (status != 0) {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            for (int kk = next_eval; kk < T; ++kk)
+                for (int i = threadIdx.x; i < n; i += GLOBAL_BLOCK) Y[(size_t)kk * n + i] = qnan;
+        }
+        if (threadIdx.x == 0) {
+            if (a.out_status) a.out_status[b] = status;
+            if (a.out_nsteps) a.out_nsteps[b] = nacc;
+            if (a.out_nrej) a.out_nrej[b] = nrej;
+        }
+    }
+}
+
 }  // namespace pk

@@ -658,6 +658,69 @@ int pk_global_rhs_batch(pk_handle_t h, int32_t topo_id, int32_t memspace, int64_
     return 0;
 }
 
+int pk_global_solve_custom(pk_handle_t h, int32_t topo_id, int32_t memspace, int64_t B, const double* params, int32_t theta_mode,
+                           const double* y0, int64_t y0_stride, const double* t_eval_host, int32_t T, double rtol, double atol,
+                           int32_t max_steps, double* out_Y, int32_t* out_status, int32_t* out_nsteps, int32_t* out_nrej) {
+    GlobalTopoHost* th = pkh::topo_of(h, topo_id);
+    if (!th) return fail("pk_global_solve_custom: unknown topology id");
+    if (B < 0 || T < 1 || !params || !y0 || !t_eval_host || !out_Y) return fail("pk_global_solve_custom: params, y0, t_eval and out_Y are required");
+    for (int k = 1; k < T; ++k)
+        if (!(t_eval_host[k] > t_eval_host[k - 1])) return fail("t_eval must be strictly increasing");
+    h->last_launches = 0;
+    if (B == 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const pk::GlobalTopoDev& d = th->dev;
+    const int n = d.n, P = th->P;
+    const bool host = memspace == PK_HOST;
+    cudaStream_t st = h->stream;
+    pk::GlobalRkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tp = d; a.B = B; a.P = P; a.T = T; a.theta_mode = theta_mode;
+    a.max_steps = max_steps > 0 ? max_steps : 2000000;                       // solvers.py:294
+    a.rtol = rtol > 0 ? rtol : 1e-5; a.atol = atol > 0 ? atol : 1e-7;        // solvers.py:293
+    a.y0_stride = y0_stride;
+    CK(h->g_t.ensure((size_t)T * sizeof(double)));
+    CK(cudaMemcpy(h->g_t.p, t_eval_host, (size_t)T * sizeof(double), cudaMemcpyHostToDevice));
+    a.t_eval = (const double*)h->g_t.p;
+    const size_t nY = (size_t)B * T * n, ny0 = y0_stride ? ((size_t)B - 1) * (size_t)y0_stride + n : (size_t)n;
+    if (host) {
+        CK(h->g_params.ensure((size_t)B * P * sizeof(double)));
+        CK(h->g_y0.ensure(ny0 * sizeof(double)));
+        CK(h->g_Y.ensure(nY * sizeof(double)));
+        CK(h->g_status.ensure((size_t)B * sizeof(int)));
+        CK(h->g_nsteps.ensure((size_t)B * sizeof(int)));
+        CK(h->g_nrej.ensure((size_t)B * sizeof(int)));
+        CK(cudaMemcpyAsync(h->g_params.p, params, (size_t)B * P * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(h->g_y0.p, y0, ny0 * sizeof(double), cudaMemcpyHostToDevice, st));
+        a.params = (const double*)h->g_params.p; a.y0 = (const double*)h->g_y0.p; a.out_Y = (double*)h->g_Y.p;
+        a.out_status = (int*)h->g_status.p; a.out_nsteps = (int*)h->g_nsteps.p; a.out_nrej = (int*)h->g_nrej.p;
+    } else {
+        a.params = params; a.y0 = y0; a.out_Y = out_Y;
+        a.out_status = out_status; a.out_nsteps = out_nsteps; a.out_nrej = out_nrej;
+    }
+    const size_t smem = ((size_t)P + d.K + d.S + 2 * (size_t)d.N + 9 * (size_t)n) * sizeof(double) + (size_t)n * sizeof(int);
+    auto kern = d.model == 2 ? pk::global_dopri5_kernel<true> : pk::global_dopri5_kernel<false>;
+    if (smem > 227 * 1024) return fail("pk_global_solve_custom: network too large for one CTA's shared memory");
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pk::GLOBAL_BLOCK, smem));
+    const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)h->sm_count * std::max(per_sm, 1));
+    CK(cudaEventRecord(h->ev0, st));
+    kern<<<grid, pk::GLOBAL_BLOCK, smem, st>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, st));
+    h->last_launches = 1;
+    if (host) {
+        CK(cudaMemcpyAsync(out_Y, a.out_Y, nY * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (out_status) CK(cudaMemcpyAsync(out_status, a.out_status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (out_nsteps) CK(cudaMemcpyAsync(out_nsteps, a.out_nsteps, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (out_nrej) CK(cudaMemcpyAsync(out_nrej, a.out_nrej, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
 #ifdef PK_GLOBAL_TRACE
 int pk_global_trace_read(unsigned long long* out16) {
     unsigned long long zero[16] = {0};

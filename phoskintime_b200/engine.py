@@ -520,6 +520,35 @@ class Engine:
                                                  int(loss_mode), xp.ptr(out)))
         return out
 
+    def global_solve_custom(self, topo, params, y0, t_eval, *, rtol=None, atol=None, max_steps=0, theta_mode=False):
+        """The reference's custom DOPRI5 solver (`solve_custom`, jacspeedup.py:31-67 / solvers.py:292-758) for B parameter
+        vectors — `pk_global_solve_custom`.  Returns dict(Y[B,T,n], status, nsteps, nrej)."""
+        dev = _is_torch(params)
+        xp = _TorchOps(params.device) if dev else _NumpyOps()
+        params = xp.f64(params)
+        params = params.reshape(1, -1) if params.ndim == 1 else params
+        B = int(params.shape[0])
+        dims = self.global_dims(topo)
+        n = dims["state_dim"]
+        if params.shape[1] != dims["n_params"]:
+            raise ValueError(f"params must have {dims['n_params']} columns")
+        y0a = xp.f64(y0)
+        stride = 0 if y0a.ndim == 1 else n
+        if (y0a.ndim == 1 and y0a.shape[0] != n) or (y0a.ndim == 2 and tuple(y0a.shape) != (B, n)):
+            raise ValueError(f"y0 must be [{n}] or [{B},{n}]")
+        t_arr = np.ascontiguousarray(np.asarray(t_eval, dtype=np.float64).reshape(-1))
+        T = t_arr.shape[0]
+        res = {"Y": xp.empty((B, T, n), "f64"), "status": xp.empty((B,), "i32"), "nsteps": xp.empty((B,), "i32"),
+               "nrej": xp.empty((B,), "i32")}
+        if dev:
+            xp.sync()
+        _lib.check(self.lib.pk_global_solve_custom(self._h, int(topo), PK_DEVICE if dev else PK_HOST, B, xp.ptr(params),
+                                                   int(bool(theta_mode)), xp.ptr(y0a), stride, t_arr.ctypes.data_as(C.c_void_p),
+                                                   T, 0.0 if rtol is None else float(rtol), 0.0 if atol is None else float(atol),
+                                                   int(max_steps), xp.ptr(res["Y"]), xp.ptr(res["status"]), xp.ptr(res["nsteps"]),
+                                                   xp.ptr(res["nrej"])))
+        return res
+
     def global_rhs_batch(self, topo, params, Y, t=None, *, theta_mode=False, want_jac=False, tf_inputs=None, S_all=None):
         """f(t, y) (and the analytic Jacobian df/dy) of one uploaded network for B (parameter vector, state, time)
         triples — `pk_global_rhs_batch`.  params [B,P] or [P] (broadcast), Y [B,n], t scalar or [B].  With `tf_inputs`

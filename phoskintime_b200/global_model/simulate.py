@@ -69,13 +69,30 @@ def simulate_odeint(sys, t_eval, rtol, atol, mxstep):
     return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
 
 
-def solve_custom(sys, y0, t_eval, rtol, atol):
+def solve_custom(sys, y0, t_eval, rtol, atol, *, method="dopri5", engine=None):
     """Reference signature of the `USE_CUSTOM_SOLVER` branch (global_model/jacspeedup.py:31-67, used at
-    simulate.py:55-58): explicit y0, current parameters of `sys` -> Y[T, state_dim].  The reference integrates
-    this branch with its Numba DOPRI5 (solvers.py:292-758); here it is the same kernel as `simulate_odeint`."""
-    res = simulate_batch(sys, sys.pack_params()[None, :], np.asarray(t_eval, dtype=np.float64), ("Y",),
-                         y0=np.asarray(y0, dtype=np.float64), rtol=rtol, atol=atol)
-    return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
+    simulate.py:55-58): explicit y0, current parameters of `sys` -> Y[T, state_dim].
+
+    method="dopri5" (default) reproduces the reference function: its Numba DOPRI5(4) with PI control, dt <= 1,
+    bucket landing and cubic-Hermite output (solvers.py:292-758), step for step on the device
+    (`pk_global_solve_custom`) — including that solver's own output error (third-order interpolant: ~1e-5 relative
+    at its default tolerances).  method="rosenbrock" integrates the same problem with the implicit kernel of
+    `simulate_odeint` (lands on every output time; ~1e-7 of the tight solution) for callers that want the branch's
+    signature but not its error."""
+    if method == "rosenbrock":
+        res = simulate_batch(sys, sys.pack_params()[None, :], np.asarray(t_eval, dtype=np.float64), ("Y",),
+                             y0=np.asarray(y0, dtype=np.float64), rtol=rtol, atol=atol, engine=engine)
+        return np.ascontiguousarray(res["Y"][0], dtype=np.float64)
+    if method != "dopri5":
+        raise ValueError("method must be 'dopri5' or 'rosenbrock'")
+    return solve_custom_batch(sys, sys.pack_params()[None, :], y0, t_eval, rtol, atol, engine=engine)["Y"][0]
+
+
+def solve_custom_batch(sys_, params, y0, t_eval, rtol=None, atol=None, *, max_steps=0, theta_mode=False, engine=None):
+    """`solve_custom` for B parameter vectors in one launch: dict(Y[B,T,n], status, nsteps, nrej)."""
+    eng = engine or get_engine()
+    return eng.global_solve_custom(_topology(sys_, eng), params, np.asarray(y0, dtype=np.float64) if not hasattr(y0, "device") else y0,
+                                   t_eval, rtol=rtol, atol=atol, max_steps=max_steps, theta_mode=theta_mode)
 
 
 def metric_time_indices(times, t_points_p, t_points_r, t_points_pho):
