@@ -15,13 +15,15 @@
 
 namespace pk {
 
-struct DenseLayout {       // per-warp shared-memory carve-up, in doubles
+struct DenseLayout {       // per-system shared-memory carve-up, in doubles
     int n, ld, P, nobs;
+    int xtra;              // register-tile variant: exchange buffers of reg_invert / reg_apply (6 * 32 * TR doubles)
     __host__ __device__ int W() const { return 0; }
     __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..4: y, v, y_new, err, v'
     __host__ __device__ int par() const { return n * ld + 5 * n; }
     __host__ __device__ int prev() const { return par() + P; }
-    __host__ __device__ int total() const { return prev() + nobs; }
+    __host__ __device__ int xbuf() const { return prev() + nobs; }
+    __host__ __device__ int total() const { return xbuf() + xtra; }
 };
 
 // NT threads (1, 2 or 4 warps) cooperate on one system.
@@ -255,6 +257,98 @@ __device__ __forceinline__ void dense_apply(int n, int ld, const double* Winv, c
     dsync<NT>();
 }
 
+// ------------------------------------------------------------------ register-resident inverse (TR x TC tile per thread)
+// 128 threads own the matrix as a 32 x 4 grid: lane l holds rows l + 32a (a < TR), warp w holds columns w + 4b (b < TC).
+// The shared-memory kernel above is bound by shared-memory bandwidth (every FMA of the inversion and of the six
+// mat-vecs per step reads and writes shared memory); here W is assembled in shared memory once per inversion, loaded
+// into registers, inverted there (Gauss-Jordan without pivoting: the pivot ROW reaches the threads by warp shuffle —
+// row k lives in lane k & 31 of every warp — the pivot COLUMN through a double-buffered 32*TR-entry shared array
+// written by its owner warp at the end of the previous column step: one block barrier per column), and the six Krylov
+// mat-vecs of a step run from registers (x by broadcast loads, the four column groups reduced through shared memory).
+// The outer loop over the column slot is unrolled, so the register slots of the pivot row (b >> 3) and of the pivot
+// column (b) are compile-time constants.
+template <int TR, int TC>
+__device__ __forceinline__ void reg_load(int n, int ld, const double* W, double (&Wt)[TR][TC], int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int a = 0; a < TR; ++a)
+#pragma unroll
+        for (int b = 0; b < TC; ++b) {
+            const int i = lane + 32 * a, j = warp + 4 * b;
+            Wt[a][b] = (i < n && j < n) ? W[i * ld + j] : 0.0;
+        }
+}
+
+template <int TR, int TC>
+__device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* colbuf, int tid) {
+    constexpr int RS = 32 * TR;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+#pragma unroll
+        for (int a = 0; a < TR; ++a) colbuf[lane + 32 * a] = Wt[a][0];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int bk = 0; bk < TC; ++bk) {
+        const int ak = bk >> 3;                        // row k = wk + 4 bk sits in slot k >> 5 = bk >> 3
+#pragma unroll 1
+        for (int wk = 0; wk < 4; ++wk) {
+            const int k = wk + 4 * bk;
+            if (k >= n) break;                         // uniform over the block
+            const double* cb = colbuf + (k & 1) * RS;
+            const int lk = k & 31;
+            double m[TR];
+            const double ip = fast_rcp(cb[k]);
+#pragma unroll
+            for (int a = 0; a < TR; ++a) m[a] = (lane + 32 * a == k) ? 0.0 : -cb[lane + 32 * a] * ip;
+            const bool own = warp == wk;
+#pragma unroll
+            for (int b = 0; b < TC; ++b) {
+                const double r = __shfl_sync(0xffffffffu, Wt[ak < TR ? ak : 0][b], lk);     // W[k][w + 4b] before this step
+                const bool isk = own && b == bk;
+                const double rr = isk ? 0.0 : r;
+#pragma unroll
+                for (int a = 0; a < TR; ++a) Wt[a][b] = fma(m[a], rr, Wt[a][b]);
+                if (lane == lk) Wt[ak < TR ? ak : 0][b] = isk ? ip : r * ip;                 // row k <- row / pivot, pivot <- 1 / pivot
+            }
+            if (own) {                                 // column k <- -column / pivot
+#pragma unroll
+                for (int a = 0; a < TR; ++a)
+                    if (lane + 32 * a != k) Wt[a][bk] = m[a];
+            }
+            const int k1 = k + 1;                      // publish column k + 1 (its values are final now) for the next step
+            if (k1 < n && warp == (k1 & 3)) {
+                double* nb = colbuf + (k1 & 1) * RS;
+#pragma unroll
+                for (int a = 0; a < TR; ++a) nb[lane + 32 * a] = (wk < 3) ? Wt[a][bk] : Wt[a][bk + 1 < TC ? bk + 1 : bk];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// dst = Winv * src (both in shared memory); red = 4 * 32 * TR doubles
+template <int TR, int TC>
+__device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], const double* src, double* dst, double* red, int tid) {
+    constexpr int RS = 32 * TR;
+    const int lane = tid & 31, warp = tid >> 5;
+    double acc[TR];
+#pragma unroll
+    for (int a = 0; a < TR; ++a) acc[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < TC; ++b) {
+        const int j = warp + 4 * b;
+        const double xj = j < n ? src[j] : 0.0;        // same address across the warp: a broadcast load
+#pragma unroll
+        for (int a = 0; a < TR; ++a) acc[a] = fma(Wt[a][b], xj, acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < TR; ++a) red[warp * RS + lane + 32 * a] = acc[a];
+    __syncthreads();
+    for (int i = tid; i < n; i += 128) dst[i] = (red[i] + red[RS + i]) + (red[2 * RS + i] + red[3 * RS + i]);
+    __syncthreads();
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -294,11 +388,15 @@ __device__ __forceinline__ double dense_max(double v, double* red) {
     return v;
 }
 
-template <int MODEL, int NT>
-__global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+template <int MODEL, int NT, int TR = 0, int TC = 0>
+__global__ void __launch_bounds__(NT, TR ? 3 : 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+    static_assert(TR == 0 || NT == 128, "the register tile is laid out over 128 threads");
+    constexpr bool REG = TR > 0;
+    double Wt[REG ? TR : 1][REG ? TC : 1];        // REG: (I - h gamma M)^-1, register resident
     extern __shared__ double smem[];
     __shared__ double red[4];
     __shared__ double coef[64];           // scratch + results of rosl_coeffs<6|7>
+    __shared__ double smu[8], seps[8];    // REG: coefficients of the step in flight
     __shared__ unsigned long long s_idx;
     const int lane = threadIdx.x;                 // thread index inside the group that owns one system
     const int n = a.n, ns = a.ns, ld = lay.ld, T = a.T, P = a.P, nobs = lay.nobs;
@@ -310,6 +408,7 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
     double* v2 = smem + lay.vec(4);
     double* p = smem + lay.par();
     double* prev = smem + lay.prev();
+    double* xbuf = smem + lay.xbuf();             // REG: [2][32 TR] pivot-column exchange | [4][32 TR] mat-vec partial sums
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
@@ -401,9 +500,18 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
             // step SHORTENED by the output grid (landing / halving) uses it too, as the ROS5L member with
             // gamma' = gamma*h_inv/hh (pk_common.cuh: ros5l_coeffs) — so inversions only happen when the controller
             // moves to another level of the step-size grid.
-            double mu[7], eps[7];
+            // the step's coefficients: 28 registers in the shared-memory variant; the register-tile variant keeps them in
+            // shared memory (smu / seps) — its registers hold the inverse
+            double mu_r[REG ? 1 : 7], eps_r[REG ? 1 : 7];
+            if constexpr (REG) {
+                __syncthreads();
+                if (lane < 7) { smu[lane] = a.m.mu[lane]; seps[lane] = a.m.eps[lane]; }
+            } else {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) { mu[k] = a.m.mu[k]; eps[k] = a.m.eps[k]; }
+                for (int k = 0; k < 7; ++k) { mu_r[k] = a.m.mu[k]; eps_r[k] = a.m.eps[k]; }
+            }
+            auto MU = [&](int k) -> double { if constexpr (REG) return smu[k]; else return mu_r[k]; };
+            auto EPS = [&](int k) -> double { if constexpr (REG) return seps[k]; else return eps_r[k]; };
             const bool seven = a.m.nsol > 6;          // ROS6L: seven solves per step
             const bool forced = hh != ctl.h;          // hh was set by the output grid, not by the controller
             bool reuse = hh == h_inv;
@@ -412,7 +520,12 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
                 // invert at the controller's grid value when it covers this (forced) step, else at the step itself
                 const double hnew = (a.m.family == 1 && forced && hh <= 1.03 * ctl.h && hh * 16.0 >= ctl.h) ? ctl.h : hh;
                 dense_fillW<MODEL, NT>(ns, n, ld, p, hnew * a.m.gamma, W, lane);
-                dense_invert<NT>(n, ld, W, v2, v, lane);
+                if constexpr (REG) {
+                    reg_load<TR, TC>(n, ld, W, Wt, lane);
+                    reg_invert<TR, TC>(n, Wt, xbuf, lane);
+                } else {
+                    dense_invert<NT>(n, ld, W, v2, v, lane);
+                }
                 h_inv = hnew;
 #ifdef PK_DENSE_COUNT_INV
                 ++nrej;
@@ -424,37 +537,49 @@ __global__ void __launch_bounds__(NT, 640 / NT) local_dense_kernel(const LocalAr
                     else rosl_coeffs<6>(a.m.gamma * h_inv / hh, coef);
                 }
                 dsync<NT>();
-                if (seven) {
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) { mu[k] = coef[48 + k]; eps[k] = coef[55 + k]; }
+                if constexpr (REG) {
+                    if (lane < 7) {
+                        if (seven) { smu[lane] = coef[48 + lane]; seps[lane] = coef[55 + lane]; }
+                        else if (lane < 6) { smu[lane] = coef[36 + lane]; seps[lane] = coef[42 + lane]; }
+                    }
                 } else {
+                    if (seven) {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) { mu[k] = coef[36 + k]; eps[k] = coef[42 + k]; }
+                        for (int k = 0; k < 7; ++k) { mu_r[k] = coef[48 + k]; eps_r[k] = coef[55 + k]; }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) { mu_r[k] = coef[36 + k]; eps_r[k] = coef[42 + k]; }
+                    }
                 }
                 dsync<NT>();
             }
+            if constexpr (REG) __syncthreads();
 
+            auto apply = [&](const double* src, double* dst) {
+                if constexpr (REG) reg_apply<TR, TC>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
+                else dense_apply<NT>(n, ld, W, src, dst, lane);
+            };
             // v_0 = h f(y); v_k = W^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
             dense_rhs<MODEL, NT>(ns, n, p, y, v2, lane);
             for (int i = lane; i < n; i += NT) v2[i] *= hh;
             dsync<NT>();
-            dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) w[i] = fma(mu[0], v[i], y[i]);
-            dense_apply<NT>(n, ld, W, v, v2, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[1], v2[i], w[i]); E[i] = eps[1] * v2[i]; }
-            dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[2], v[i], w[i]); E[i] = fma(eps[2], v[i], E[i]); }
-            dense_apply<NT>(n, ld, W, v, v2, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[3], v2[i], w[i]); E[i] = fma(eps[3], v2[i], E[i]); }
-            dense_apply<NT>(n, ld, W, v2, v, lane);
-            for (int i = lane; i < n; i += NT) { w[i] = fma(mu[4], v[i], w[i]); E[i] = fma(eps[4], v[i], E[i]); }
-            dense_apply<NT>(n, ld, W, v, v2, lane);
+            apply(v2, v);
+            for (int i = lane; i < n; i += NT) w[i] = fma(MU(0), v[i], y[i]);
+            apply(v, v2);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(MU(1), v2[i], w[i]); E[i] = EPS(1) * v2[i]; }
+            apply(v2, v);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(MU(2), v[i], w[i]); E[i] = fma(EPS(2), v[i], E[i]); }
+            apply(v, v2);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(MU(3), v2[i], w[i]); E[i] = fma(EPS(3), v2[i], E[i]); }
+            apply(v2, v);
+            for (int i = lane; i < n; i += NT) { w[i] = fma(MU(4), v[i], w[i]); E[i] = fma(EPS(4), v[i], E[i]); }
+            apply(v, v2);
             const double* vl = v2;                    // last Krylov vector and its coefficients
-            double mul = mu[5], epl = eps[5];
+            double mul = MU(5), epl = EPS(5);
             if (seven) {
-                for (int i = lane; i < n; i += NT) { w[i] = fma(mu[5], v2[i], w[i]); E[i] = fma(eps[5], v2[i], E[i]); }
-                dense_apply<NT>(n, ld, W, v2, v, lane);
-                vl = v; mul = mu[6]; epl = eps[6];
+                for (int i = lane; i < n; i += NT) { w[i] = fma(MU(5), v2[i], w[i]); E[i] = fma(EPS(5), v2[i], E[i]); }
+                apply(v2, v);
+                vl = v; mul = MU(6); epl = EPS(6);
             }
             float err = 0.0f;
             bool bad = false;

@@ -1,20 +1,23 @@
 // Dense (shared-memory matrix) kernels: random model and the distributive / successive models beyond 8 sites.
 #include "pk_internal.hpp"
 
+#include <cstdlib>
+
 #include "local_dense.cuh"
 
 namespace pkh {
 namespace {
 
-template <int MODEL, int NT>
+template <int MODEL, int NT, int TR = 0, int TC = 0>
 cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
     pk::DenseLayout lay;
     lay.n = a.n;
     lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
     lay.P = a.P;
     lay.nobs = 2 + a.ns;
+    lay.xtra = TR ? 6 * 32 * TR : 0;
     size_t smem = (size_t)lay.total() * sizeof(double);
-    auto kern = pk::local_dense_kernel<MODEL, NT>;
+    auto kern = pk::local_dense_kernel<MODEL, NT, TR, TC>;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -33,6 +36,10 @@ cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
 // so larger systems get more threads each to keep the SM's issue slots busy
 template <int MODEL>
 cudaError_t launch_dense(pk_handle_s* h, const pk::LocalArgs& a) {
+    // 41..68 states (rand-6: 65): the inverse lives in registers (3 x 17 tile per thread), see local_dense.cuh
+    if constexpr (MODEL == 2) {
+        if (a.n > 40 && a.n <= 68 && !getenv("PK_DENSE_SMEM")) return launch_dense_nt<MODEL, 128, 3, 17>(h, a);
+    }
     if (a.n >= 40) return launch_dense_nt<MODEL, 128>(h, a);
     if (a.n >= 24) return launch_dense_nt<MODEL, 64>(h, a);
     return launch_dense_nt<MODEL, 32>(h, a);

@@ -1,4 +1,4 @@
-"""`fun(t, y)` factories for `scipy.integrate.solve_ivp`-style solvers — device mirror of the reference's
+"""`fun(t, y)` factories for solve_ivp-style host solvers — device mirror of the reference's
 `global_model/model_ivp.py` (:49-277).
 
 The reference closes the block-kinetics kernels (`distributive_rhs`, `sequential_rhs`, `saturating_rhs`,

@@ -36,7 +36,7 @@ def full_weight(p_data_weight, use_regularization, reg_len):
 
 
 def _uniform_filter3(x):
-    """scipy.ndimage.uniform_filter1d(x, 3) with its default 'reflect' boundary (the edge sample repeats)."""
+    """uniform_filter1d(x, 3) of SciPy's ndimage with its default 'reflect' boundary (the edge sample repeats)."""
     x = np.asarray(x, dtype=np.float64)
     if x.size == 0:
         return x.copy()
