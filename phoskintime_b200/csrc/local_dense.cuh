@@ -152,6 +152,8 @@ __device__ __forceinline__ void dense_fillW(int ns, int n, int ld, const double*
 // largest value of the step-size grid 2^(j*lg), j integer, that is <= h
 __device__ __forceinline__ double dense_quantize_h(double h, double lg) {
     if (!(h > 0.0) || !(h < 1.0e300)) return h;
+    // power-of-two grid (the default): clear the mantissa — FP64 log2 / exp2 cost ~400 instructions per step otherwise
+    if (lg == 1.0 && h > 1.0e-300) return __longlong_as_double(__double_as_longlong(h) & 0x7ff0000000000000LL);
     return exp2(floor(log2(h) / lg) * lg);
 }
 
@@ -288,43 +290,70 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
         for (int a = 0; a < TR; ++a) colbuf[lane + 32 * a] = Wt[a][0];
     }
     __syncthreads();
+    // ONE loop body for all columns (a fully unrolled version is ~45 KB of code and starves on instruction fetch): the
+    // register slots ROTATE instead — after the four columns w + 4 bk of a slot are done the column slots shift by one,
+    // so the pivot column is always physical slot 0; the row slots shift when k passes a multiple of 32, so the pivot
+    // row is always physical slot 0 too.  TC column rotations and TR row rotations in total restore the layout.
+    int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
+    auto rotate_rows = [&]() {
 #pragma unroll
+        for (int b = 0; b < TC; ++b) {
+            const double t0 = Wt[0][b];
+#pragma unroll
+            for (int a = 0; a + 1 < TR; ++a) Wt[a][b] = Wt[a + 1][b];
+            Wt[TR - 1][b] = t0;
+        }
+        rot_r = rot_r + 1 == TR ? 0 : rot_r + 1;
+    };
+#pragma unroll 1
     for (int bk = 0; bk < TC; ++bk) {
-        const int ak = bk >> 3;                        // row k = wk + 4 bk sits in slot k >> 5 = bk >> 3
 #pragma unroll 1
         for (int wk = 0; wk < 4; ++wk) {
             const int k = wk + 4 * bk;
             if (k >= n) break;                         // uniform over the block
+            if ((k & 31) == 0 && k > 0) rotate_rows();
             const double* cb = colbuf + (k & 1) * RS;
             const int lk = k & 31;
-            double m[TR];
             const double ip = fast_rcp(cb[k]);
+            int row[TR];
+            double m[TR];
 #pragma unroll
-            for (int a = 0; a < TR; ++a) m[a] = (lane + 32 * a == k) ? 0.0 : -cb[lane + 32 * a] * ip;
+            for (int a = 0; a < TR; ++a) {
+                int la = a + rot_r;
+                if (la >= TR) la -= TR;
+                row[a] = lane + 32 * la;
+                // row k itself: W[k][j] <- W[k][j] / pivot = W[k][j] + (1/pivot - 1) W[k][j] — the same FMA as every other row
+                m[a] = (row[a] == k) ? ip - 1.0 : -cb[row[a]] * ip;
+            }
             const bool own = warp == wk;
 #pragma unroll
             for (int b = 0; b < TC; ++b) {
-                const double r = __shfl_sync(0xffffffffu, Wt[ak < TR ? ak : 0][b], lk);     // W[k][w + 4b] before this step
-                const bool isk = own && b == bk;
-                const double rr = isk ? 0.0 : r;
+                const double r = __shfl_sync(0xffffffffu, Wt[0][b], lk);     // W[k][.] before this step (pivot row: slot 0)
+                const double rr = (b == 0 && own) ? 0.0 : r;                 // the pivot column itself is rewritten below
 #pragma unroll
                 for (int a = 0; a < TR; ++a) Wt[a][b] = fma(m[a], rr, Wt[a][b]);
-                if (lane == lk) Wt[ak < TR ? ak : 0][b] = isk ? ip : r * ip;                 // row k <- row / pivot, pivot <- 1 / pivot
             }
-            if (own) {                                 // column k <- -column / pivot
+            if (own) {                                 // column k <- -column / pivot, pivot <- 1 / pivot
 #pragma unroll
-                for (int a = 0; a < TR; ++a)
-                    if (lane + 32 * a != k) Wt[a][bk] = m[a];
+                for (int a = 0; a < TR; ++a) Wt[a][0] = (row[a] == k) ? ip : m[a];
             }
             const int k1 = k + 1;                      // publish column k + 1 (its values are final now) for the next step
             if (k1 < n && warp == (k1 & 3)) {
                 double* nb = colbuf + (k1 & 1) * RS;
 #pragma unroll
-                for (int a = 0; a < TR; ++a) nb[lane + 32 * a] = (wk < 3) ? Wt[a][bk] : Wt[a][bk + 1 < TC ? bk + 1 : bk];
+                for (int a = 0; a < TR; ++a) nb[row[a]] = (wk < 3) ? Wt[a][0] : Wt[a][TC > 1 ? 1 : 0];
             }
             __syncthreads();
         }
+#pragma unroll
+        for (int a = 0; a < TR; ++a) {                 // next column slot becomes slot 0
+            const double t0 = Wt[a][0];
+#pragma unroll
+            for (int b = 0; b + 1 < TC; ++b) Wt[a][b] = Wt[a][b + 1];
+            Wt[a][TC - 1] = t0;
+        }
     }
+    while (rot_r != 0) rotate_rows();
 }
 
 // dst = Winv * src (both in shared memory); red = 4 * 32 * TR doubles
@@ -388,8 +417,11 @@ __device__ __forceinline__ double dense_max(double v, double* red) {
     return v;
 }
 
+#ifndef PK_DENSE_REG_BLOCKS
+#define PK_DENSE_REG_BLOCKS 2          // resident CTAs per SM of the register-tile variant (zero spill at <= 255 registers)
+#endif
 template <int MODEL, int NT, int TR = 0, int TC = 0>
-__global__ void __launch_bounds__(NT, TR ? 3 : 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
+__global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
     static_assert(TR == 0 || NT == 128, "the register tile is laid out over 128 threads");
     constexpr bool REG = TR > 0;
     double Wt[REG ? TR : 1][REG ? TC : 1];        // REG: (I - h gamma M)^-1, register resident
