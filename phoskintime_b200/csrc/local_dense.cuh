@@ -282,6 +282,17 @@ __device__ __forceinline__ void reg_load(int n, int ld, const double* W, double 
 }
 
 template <int TR, int TC>
+__device__ __forceinline__ void reg_rotate_rows(double (&Wt)[TR][TC]) {
+#pragma unroll
+    for (int b = 0; b < TC; ++b) {
+        const double t0 = Wt[0][b];
+#pragma unroll
+        for (int a = 0; a + 1 < TR; ++a) Wt[a][b] = Wt[a + 1][b];
+        Wt[TR - 1][b] = t0;
+    }
+}
+
+template <int TR, int TC>
 __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* colbuf, int tid) {
     constexpr int RS = 32 * TR;
     const int lane = tid & 31, warp = tid >> 5;
@@ -295,23 +306,13 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
     // so the pivot column is always physical slot 0; the row slots shift when k passes a multiple of 32, so the pivot
     // row is always physical slot 0 too.  TC column rotations and TR row rotations in total restore the layout.
     int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
-    auto rotate_rows = [&]() {
-#pragma unroll
-        for (int b = 0; b < TC; ++b) {
-            const double t0 = Wt[0][b];
-#pragma unroll
-            for (int a = 0; a + 1 < TR; ++a) Wt[a][b] = Wt[a + 1][b];
-            Wt[TR - 1][b] = t0;
-        }
-        rot_r = rot_r + 1 == TR ? 0 : rot_r + 1;
-    };
 #pragma unroll 1
     for (int bk = 0; bk < TC; ++bk) {
 #pragma unroll 1
         for (int wk = 0; wk < 4; ++wk) {
             const int k = wk + 4 * bk;
             if (k >= n) break;                         // uniform over the block
-            if ((k & 31) == 0 && k > 0) rotate_rows();
+            if ((k & 31) == 0 && k > 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
             const double* cb = colbuf + (k & 1) * RS;
             const int lk = k & 31;
             const double ip = fast_rcp(cb[k]);
@@ -353,7 +354,7 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
             Wt[a][TC - 1] = t0;
         }
     }
-    while (rot_r != 0) rotate_rows();
+    while (rot_r != 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
 }
 
 // dst = Winv * src (both in shared memory); red = 4 * 32 * TR doubles
@@ -595,6 +596,28 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
             dense_rhs<MODEL, NT>(ns, n, p, y, v2, lane);
             for (int i = lane; i < n; i += NT) v2[i] *= hh;
             dsync<NT>();
+            const double* vl;                         // last Krylov vector and its coefficients
+            double mul, epl;
+            if constexpr (REG) {
+                // one rolled loop over the solves (a single inlined copy of the register mat-vec; the coefficients are
+                // read from shared memory by index)
+                const int nsol = seven ? 7 : 6;
+                double* src = v2;
+                double* dst = v;
+#pragma unroll 1
+                for (int ks = 0; ks < nsol; ++ks) {
+                    reg_apply<TR, TC>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
+                    if (ks + 1 < nsol) {
+                        const double muk = smu[ks], epk = seps[ks];           // eps_0 = 0: E starts at zero
+                        for (int i = lane; i < n; i += NT) {
+                            w[i] = fma(muk, dst[i], ks == 0 ? y[i] : w[i]);
+                            E[i] = ks == 0 ? 0.0 : fma(epk, dst[i], E[i]);
+                        }
+                    }
+                    double* tmp = src; src = dst; dst = tmp;
+                }
+                vl = src; mul = smu[nsol - 1]; epl = seps[nsol - 1];
+            } else {
             apply(v2, v);
             for (int i = lane; i < n; i += NT) w[i] = fma(MU(0), v[i], y[i]);
             apply(v, v2);
@@ -606,12 +629,13 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
             apply(v2, v);
             for (int i = lane; i < n; i += NT) { w[i] = fma(MU(4), v[i], w[i]); E[i] = fma(EPS(4), v[i], E[i]); }
             apply(v, v2);
-            const double* vl = v2;                    // last Krylov vector and its coefficients
-            double mul = MU(5), epl = EPS(5);
+            vl = v2;
+            mul = MU(5); epl = EPS(5);
             if (seven) {
                 for (int i = lane; i < n; i += NT) { w[i] = fma(MU(5), v2[i], w[i]); E[i] = fma(EPS(5), v2[i], E[i]); }
                 apply(v2, v);
                 vl = v; mul = MU(6); epl = EPS(6);
+            }
             }
             float err = 0.0f;
             bool bad = false;
