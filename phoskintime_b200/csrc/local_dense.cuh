@@ -18,9 +18,11 @@ namespace pk {
 struct DenseLayout {       // per-system shared-memory carve-up, in doubles
     int n, ld, P, nobs;
     int xtra;              // register-tile variant: exchange buffers of reg_invert / reg_apply (6 * 32 * TR doubles)
+    int nv;                // stride of the work vectors (n; register-tile variant: 4 TC >= n, the tail stays zero so that the
+                           // mat-vec can read whole column groups without a bounds test)
     __host__ __device__ int W() const { return 0; }
-    __host__ __device__ int vec(int k) const { return n * ld + k * n; }   // k = 0..4: y, v, y_new, err, v'
-    __host__ __device__ int par() const { return n * ld + 5 * n; }
+    __host__ __device__ int vec(int k) const { return n * ld + k * nv; }   // k = 0..4: y, v, y_new, err, v'
+    __host__ __device__ int par() const { return n * ld + 5 * nv; }
     __host__ __device__ int prev() const { return par() + P; }
     __host__ __device__ int xbuf() const { return prev() + nobs; }
     __host__ __device__ int total() const { return xbuf() + xtra; }
@@ -269,8 +271,15 @@ __device__ __forceinline__ void dense_apply(int n, int ld, const double* Winv, c
 // mat-vecs of a step run from registers (x by broadcast loads, the four column groups reduced through shared memory).
 // The outer loop over the column slot is unrolled, so the register slots of the pivot row (b >> 3) and of the pivot
 // column (b) are compile-time constants.
+__device__ __forceinline__ int fresh_tid() {           // re-read where it is used: the compiler otherwise hoists every index
+    int t;                                             // derived from the thread id out of the time loop and keeps dozens of
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));    // loop-invariant addresses alive in registers across the inversion
+    return t;
+}
+
 template <int TR, int TC>
-__device__ __forceinline__ void reg_load(int n, int ld, const double* W, double (&Wt)[TR][TC], int tid) {
+__device__ __forceinline__ void reg_load(int n, int ld, const double* W, double (&Wt)[TR][TC], int) {
+    const int tid = fresh_tid();
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int a = 0; a < TR; ++a)
@@ -292,83 +301,112 @@ __device__ __forceinline__ void reg_rotate_rows(double (&Wt)[TR][TC]) {
     }
 }
 
+// cyclic shift of the column slots: slot b <- slot (b + SH) mod TC, in place along the cycles of the permutation (one
+// temporary per cycle: a scratch copy of a whole row would cost 2 TC registers)
+__host__ __device__ constexpr int reg_gcd(int a, int b) { return b == 0 ? a : reg_gcd(b, a % b); }
+template <int TR, int TC, int SH>
+__device__ __forceinline__ void reg_rotate_cols(double (&Wt)[TR][TC]) {
+    constexpr int G = reg_gcd(TC, SH % TC == 0 ? TC : SH % TC), LEN = TC / G;
+    if constexpr (SH % TC != 0) {
+#pragma unroll
+        for (int a = 0; a < TR; ++a) {
+#pragma unroll
+            for (int c = 0; c < G; ++c) {
+                const double t0 = Wt[a][c];
+                int j = c;
+#pragma unroll
+                for (int s = 0; s + 1 < LEN; ++s) {
+                    const int nj = (j + SH) % TC;
+                    Wt[a][j] = Wt[a][nj];
+                    j = nj;
+                }
+                Wt[a][j] = t0;
+            }
+        }
+    }
+}
+
 template <int TR, int TC>
-__device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* colbuf, int tid) {
+__device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* colbuf, int) {
     constexpr int RS = 32 * TR;
+    const int tid = fresh_tid();
     const int lane = tid & 31, warp = tid >> 5;
     if (warp == 0) {
 #pragma unroll
         for (int a = 0; a < TR; ++a) colbuf[lane + 32 * a] = Wt[a][0];
     }
     __syncthreads();
-    // ONE loop body for all columns (a fully unrolled version is ~45 KB of code and starves on instruction fetch): the
-    // register slots ROTATE instead — after the four columns w + 4 bk of a slot are done the column slots shift by one,
-    // so the pivot column is always physical slot 0; the row slots shift when k passes a multiple of 32, so the pivot
-    // row is always physical slot 0 too.  TC column rotations and TR row rotations in total restore the layout.
+    // A fully unrolled loop over the column slots is ~45 KB of code and starves on instruction fetch; a single body with
+    // the pivot column always in slot 0 pays a register rotation (2 TR TC moves) per slot.  Middle ground: the body is
+    // unrolled over U = 4 consecutive slots (static register indices 0..3), then the column slots rotate by U; the row
+    // slots rotate when k passes a multiple of 32, so the pivot row is always physical row slot 0.  A final static
+    // rotation restores the layout (total column shift = 0 mod TC, TR row rotations).
+    constexpr int U = TC >= 2 ? 2 : 1;
     int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
 #pragma unroll 1
-    for (int bk = 0; bk < TC; ++bk) {
+    for (int bq = 0; bq < TC; bq += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int bk = bq + u;                     // logical column slot, held in physical slot u
 #pragma unroll 1
-        for (int wk = 0; wk < 4; ++wk) {
-            const int k = wk + 4 * bk;
-            if (k >= n) break;                         // uniform over the block
-            if ((k & 31) == 0 && k > 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
-            const double* cb = colbuf + (k & 1) * RS;
-            const int lk = k & 31;
-            const double ip = fast_rcp(cb[k]);
-            int row[TR];
-            double m[TR];
+            for (int wk = 0; wk < 4; ++wk) {
+                const int k = wk + 4 * bk;
+                if (bk >= TC || k >= n) break;         // uniform over the block
+                if ((k & 31) == 0 && k > 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
+                const double* cb = colbuf + (k & 1) * RS;
+                const int lk = k & 31;
+                const double ip = fast_rcp(cb[k]);
+                int row[TR];
+                double m[TR];
 #pragma unroll
-            for (int a = 0; a < TR; ++a) {
-                int la = a + rot_r;
-                if (la >= TR) la -= TR;
-                row[a] = lane + 32 * la;
-                // row k itself: W[k][j] <- W[k][j] / pivot = W[k][j] + (1/pivot - 1) W[k][j] — the same FMA as every other row
-                m[a] = (row[a] == k) ? ip - 1.0 : -cb[row[a]] * ip;
+                for (int a = 0; a < TR; ++a) {
+                    int la = a + rot_r;
+                    if (la >= TR) la -= TR;
+                    row[a] = lane + 32 * la;
+                    // row k itself: W[k][j] <- W[k][j] / pivot = W[k][j] + (1/pivot - 1) W[k][j] — the same FMA as every other row
+                    m[a] = (row[a] == k) ? ip - 1.0 : -cb[row[a]] * ip;
+                }
+                const bool own = warp == wk;
+#pragma unroll
+                for (int b = 0; b < TC; ++b) {
+                    const double r = __shfl_sync(0xffffffffu, Wt[0][b], lk);     // W[k][.] before this step (pivot row: slot 0)
+                    const double rr = (b == u && own) ? 0.0 : r;                 // the pivot column itself is rewritten below
+#pragma unroll
+                    for (int a = 0; a < TR; ++a) Wt[a][b] = fma(m[a], rr, Wt[a][b]);
+                }
+                if (own) {                             // column k <- -column / pivot, pivot <- 1 / pivot
+#pragma unroll
+                    for (int a = 0; a < TR; ++a) Wt[a][u] = (row[a] == k) ? ip : m[a];
+                }
+                const int k1 = k + 1;                  // publish column k + 1 (its values are final now) for the next step
+                if (k1 < n && warp == (k1 & 3)) {
+                    double* nb = colbuf + (k1 & 1) * RS;
+#pragma unroll
+                    for (int a = 0; a < TR; ++a) nb[row[a]] = (wk < 3) ? Wt[a][u] : Wt[a][u + 1 < TC ? u + 1 : u];
+                }
+                __syncthreads();
             }
-            const bool own = warp == wk;
-#pragma unroll
-            for (int b = 0; b < TC; ++b) {
-                const double r = __shfl_sync(0xffffffffu, Wt[0][b], lk);     // W[k][.] before this step (pivot row: slot 0)
-                const double rr = (b == 0 && own) ? 0.0 : r;                 // the pivot column itself is rewritten below
-#pragma unroll
-                for (int a = 0; a < TR; ++a) Wt[a][b] = fma(m[a], rr, Wt[a][b]);
-            }
-            if (own) {                                 // column k <- -column / pivot, pivot <- 1 / pivot
-#pragma unroll
-                for (int a = 0; a < TR; ++a) Wt[a][0] = (row[a] == k) ? ip : m[a];
-            }
-            const int k1 = k + 1;                      // publish column k + 1 (its values are final now) for the next step
-            if (k1 < n && warp == (k1 & 3)) {
-                double* nb = colbuf + (k1 & 1) * RS;
-#pragma unroll
-                for (int a = 0; a < TR; ++a) nb[row[a]] = (wk < 3) ? Wt[a][0] : Wt[a][TC > 1 ? 1 : 0];
-            }
-            __syncthreads();
         }
-#pragma unroll
-        for (int a = 0; a < TR; ++a) {                 // next column slot becomes slot 0
-            const double t0 = Wt[a][0];
-#pragma unroll
-            for (int b = 0; b + 1 < TC; ++b) Wt[a][b] = Wt[a][b + 1];
-            Wt[a][TC - 1] = t0;
-        }
+        reg_rotate_cols<TR, TC, U>(Wt);                // the next U column slots become slots 0..U-1
     }
+    constexpr int DONE = ((TC + U - 1) / U) * U % TC;  // net column shift so far
+    if constexpr (DONE != 0) reg_rotate_cols<TR, TC, TC - DONE>(Wt);
     while (rot_r != 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
 }
 
 // dst = Winv * src (both in shared memory); red = 4 * 32 * TR doubles
 template <int TR, int TC>
-__device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], const double* src, double* dst, double* red, int tid) {
+__device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], const double* src, double* dst, double* red, int) {
     constexpr int RS = 32 * TR;
+    const int tid = fresh_tid();
     const int lane = tid & 31, warp = tid >> 5;
     double acc[TR];
 #pragma unroll
     for (int a = 0; a < TR; ++a) acc[a] = 0.0;
 #pragma unroll
     for (int b = 0; b < TC; ++b) {
-        const int j = warp + 4 * b;
-        const double xj = j < n ? src[j] : 0.0;        // same address across the warp: a broadcast load
+        const double xj = src[warp + 4 * b];           // same address across the warp: a broadcast load; the padded tail
+                                                       // of the vector is zero and so are the padded columns of Wt
 #pragma unroll
         for (int a = 0; a < TR; ++a) acc[a] = fma(Wt[a][b], xj, acc[a]);
     }
@@ -445,6 +483,9 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
     const bool want_loss = (a.out_ssr != nullptr) || (a.out_score != nullptr);
     const bool want_y = a.out_Y != nullptr;
     const int rna_len = T > RNA_OFFSET ? T - RNA_OFFSET : 0;
+    if constexpr (REG) {
+        for (int i = lane; i < 5 * lay.nv; i += NT) smem[lay.vec(0) + i] = 0.0;     // incl. the padded tails (never written again)
+    }
 
     for (;;) {
         dsync<NT>();
@@ -468,7 +509,14 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
         const int grp = a.group ? a.group[sys] : 0;
         const double* tg = a.target ? a.target + (size_t)grp * a.L : nullptr;
         const double* sg = a.sigma ? a.sigma + (size_t)grp * a.sigma_len : nullptr;
-        EpiAcc e{0, 0, 0, 0, 0, 0};
+        // fused-output accumulators of this thread: registers, or (register-tile variant, whose registers hold the
+        // inverse) a shared-memory record behind the exchange buffers
+        EpiAcc e_loc{0, 0, 0, 0, 0, 0};
+        EpiAcc& e = [&]() -> EpiAcc& {
+            if constexpr (REG) return ((EpiAcc*)(xbuf + 6 * 32 * TR))[lane];
+            else return e_loc;
+        }();
+        if constexpr (REG) e = EpiAcc{0, 0, 0, 0, 0, 0};
         double t = a.t[0];
         int nst = 0, nrej = 0, status = 0, kout = 1;
         double h_inv = -1.0;            // step size whose (I - h gamma M)^-1 currently sits in W

@@ -15,7 +15,9 @@ cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
     lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
     lay.P = a.P;
     lay.nobs = 2 + a.ns;
-    lay.xtra = TR ? 6 * 32 * TR : 0;
+    lay.xtra = TR ? 6 * 32 * TR + 6 * NT : 0;          // exchange buffers + one EpiAcc (6 doubles) per thread
+    lay.nv = TR ? 4 * TC : a.n;
+    if (TR && (a.n > 4 * TC || a.n > 32 * TR)) return cudaErrorInvalidValue;
     size_t smem = (size_t)lay.total() * sizeof(double);
     auto kern = pk::local_dense_kernel<MODEL, NT, TR, TC>;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
