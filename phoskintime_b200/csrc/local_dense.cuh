@@ -345,6 +345,10 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
     int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
 #pragma unroll 1
     for (int bq = 0; bq < TC; bq += U) {
+        static_assert(8 % U == 0, "row rotations happen at column slots 8, 16, ... (k = 32, 64, ...): U must divide 8");
+        // k = 4 bq passes a multiple of 32: the next row slot becomes the pivot-row slot (once per 8 column slots — kept
+        // out of the column loop, where the compiler turns it into ~100 predicated moves per column)
+        if (bq > 0 && (bq & 7) == 0 && 4 * bq < n) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int bk = bq + u;                     // logical column slot, held in physical slot u
@@ -352,7 +356,6 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
             for (int wk = 0; wk < 4; ++wk) {
                 const int k = wk + 4 * bk;
                 if (bk >= TC || k >= n) break;         // uniform over the block
-                if ((k & 31) == 0 && k > 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
                 const double* cb = colbuf + (k & 1) * RS;
                 const int lk = k & 31;
                 const double ip = fast_rcp(cb[k]);
