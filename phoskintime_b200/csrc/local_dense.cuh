@@ -156,6 +156,13 @@ __device__ __forceinline__ double dense_quantize_h(double h, double lg) {
     if (!(h > 0.0) || !(h < 1.0e300)) return h;
     // power-of-two grid (the default): clear the mantissa — FP64 log2 / exp2 cost ~400 instructions per step otherwise
     if (lg == 1.0 && h > 1.0e-300) return __longlong_as_double(__double_as_longlong(h) & 0x7ff0000000000000LL);
+    if ((lg == 2.0 || lg == 3.0 || lg == 4.0) && h > 1.0e-300) {       // grids of ratio 4, 8, 16: floor the exponent to a multiple
+        const int L = (int)lg;
+        const int E = (int)((__double_as_longlong(h) >> 52) & 0x7ff) - 1023;
+        int q = E / L;
+        if (E < 0 && q * L != E) --q;                                  // floor division
+        return __longlong_as_double((long long)(q * L + 1023) << 52);
+    }
     return exp2(floor(log2(h) / lg) * lg);
 }
 
@@ -341,7 +348,7 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
     // unrolled over U = 4 consecutive slots (static register indices 0..3), then the column slots rotate by U; the row
     // slots rotate when k passes a multiple of 32, so the pivot row is always physical row slot 0.  A final static
     // rotation restores the layout (total column shift = 0 mod TC, TR row rotations).
-    constexpr int U = TC >= 2 ? 2 : 1;
+    constexpr int U = TC >= 4 ? 4 : 1;
     int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
 #pragma unroll 1
     for (int bq = 0; bq < TC; bq += U) {

@@ -4,6 +4,8 @@
 // hosts without it and reuses the copy PyTorch already mapped).
 #include "pk_internal.hpp"
 
+#include <cstdlib>
+
 #include "pk_common.cuh"
 
 namespace pkh {
@@ -389,6 +391,7 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     // ratio 4 -> 1.76e5 at 119 steps (inversions saved ~ mat-vecs added), ratio 2.83 -> 1.67e5; ratios above the
     // controller's growth limit (6) stall.
     a.hgrid_log2 = 1.0;
+    if (const char* e = getenv("PK_DENSE_HGRID")) a.hgrid_log2 = atof(e);      // development override
     a.max_steps = j->max_steps > 0 ? j->max_steps : 100000;
     a.normalize = j->normalize; a.log_params = j->log_params;
     a.y_metric = j->out_Y ? j->y_metric : -1;
