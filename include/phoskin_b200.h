@@ -229,7 +229,8 @@ int pk_local_nlls_batch(pk_handle_t h, const pk_nlls_job* job);
  *                              (simulate.py:105-182).
  * Kinetic models (global_model/models.py): 0 distributive, 1 sequential, 4 saturating with the block
  * [mRNA, P0, site_1..site_ns]; 2 combinatorial with the block [mRNA, pattern_0 .. pattern_{2^ns-1}]
- * (network.py:131-149; at most 4 sites per protein; driver_map is ignored as in jacspeedup.py:318-325; the
+ * (network.py:131-149; at most 8 sites per protein - blocks up to 16 patterns are inverted in registers, larger
+ * ones by one warp in an L2-resident scratch; driver_map is ignored as in jacspeedup.py:318-325; the
  * reference's per-bucket rate table S_cache, jacspeedup.py:114-145, is recomputed on the device).
  * -----------------------------------------------------------------------------------------------*/
 typedef struct pk_global_topology {
@@ -248,7 +249,10 @@ typedef struct pk_global_topology {
     const double* kin_Kmat;      /* [K, n_bins] row-major                                           */
     const double* tf_deg;        /* [N]                                                             */
     const int32_t* driver_map;   /* [N] kinase index driving protein i's TF activity, or -1         */
-    int32_t force_generic_schur; /* testing: 1 = shared-memory LU path even when the register path fits */
+    int32_t force_generic_schur; /* testing: 1 = shared-memory LU path even when the register path fits;
+                                    2 = additionally all large per-system arrays in the per-CTA global scratch
+                                    (the capacity fallback chosen automatically for networks beyond one CTA's
+                                    shared memory) */
     int32_t reserved0;
 } pk_global_topology;
 

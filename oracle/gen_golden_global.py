@@ -24,7 +24,9 @@ OUT = os.path.join(ROOT, "tests", "golden")
 T_EVAL = np.array([0.0, 0.5, 0.75, 1.0, 2.0, 4.0, 8.0, 15.0, 16.0, 30.0, 60.0, 120.0, 240.0, 480.0, 960.0])
 CASES = [(0, 10, 5, 3, 11), (0, 36, 12, 4, 12), (1, 14, 6, 4, 13), (4, 14, 6, 3, 14),   # model, N, K, max_sites, seed
          (0, 120, 40, 4, 5, 2),     # BASELINE configs[4] shape (state_dim ~ 500), 2 parameter vectors
-         (2, 10, 5, 3, 21), (2, 24, 8, 4, 22)]   # combinatorial: one state per phosphorylation pattern
+         (2, 10, 5, 3, 21), (2, 24, 8, 4, 22),   # combinatorial: one state per phosphorylation pattern
+         (2, 7, 4, 6, 27),          # combinatorial blocks of 32 and 64 patterns (sites [1 5 0 2 6 1 4]): the warp-per-block inverse
+         (0, 300, 60, 4, 6, 2)]     # capacity case: 1371 states, 254 regulators -> Schur block and stage vectors leave shared memory
 
 
 def stub_modules(model, loss_mode):

@@ -77,7 +77,13 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
     int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff, i_cord;
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
+    int ovf_total;                    // capacity fallback: doubles of per-CTA global (L2-resident) scratch; an array whose offset is
+                                      // >= OVF_BASE lives there (at offset - OVF_BASE) instead of in shared memory
+    int n_big;                        // model 2: proteins with more than 4 sites (first n_big entries of the size order)
+    int big_nst;                      // model 2: largest pattern block (states) among them, 0 if none
+    int binv_total;                   // model 2: sum of 4^ns (doubles); the 8 pivot-row snapshots of the big path follow it
 };
+constexpr int OVF_BASE = 1 << 28;
 
 struct GlobalArgs {
     GlobalTopoDev tp;
@@ -102,6 +108,7 @@ struct GlobalArgs {
     double* traj;                     // [grid][T][n] scratch when out_Y is not requested
     double* binv;                     // [grid][binv_stride] model 2: inverses of the per-protein pattern blocks
     long long binv_stride;
+    double* ovf;                      // [grid][sm.ovf_total] arrays that did not fit into shared memory (OVF instantiations)
     unsigned long long* counter;
 };
 
@@ -339,6 +346,7 @@ struct GlobalCtx {
     const int* boff;
     const int* cord;                  // proteins ordered by block size (descending): the two blocks a warp inverts together
                                       // are of (nearly) equal size, so neither half-warp idles through the other's columns
+    int n_big, big_nst, binv_total;   // blocks of more than 16 patterns: cord[0 .. n_big), one warp each (comb_factor_big)
 };
 
 
@@ -354,7 +362,8 @@ struct GlobalCtx {
 // six stage solves read it coalesced.  Everything around the block (mRNA row, Schur coupling through the
 // transcription gains, unit responses w) is shared with the other kinetic models.
 // ------------------------------------------------------------------------------------------------
-constexpr int COMB_MAX_STATES = 16;   // ns <= 4
+constexpr int COMB_MAX_STATES = 16;   // register path: ns <= 4; larger blocks go through comb_factor_big
+constexpr int COMB_MAX_SITES = 8;     // 256 patterns per protein (512 KB of scratch per such block and resident system)
 
 __device__ __forceinline__ double comb_state_rhs(const GlobalCtx& cx, const double* src, int i, int m) {
     const int st = cx.offy[i], ss = cx.offs[i], ns = cx.ns[i];
@@ -370,12 +379,94 @@ __device__ __forceinline__ double comb_state_rhs(const GlobalCtx& cx, const doub
     return fma(-out, blk[m], in);
 }
 
+// Blocks of 32..256 patterns (5..8 sites): one warp per protein, lane = rows lane + 32 j.  The matrix is assembled and
+// inverted IN this CTA's L2-resident scratch (same layout as the register path leaves behind: element (r, q) at
+// q*nst + r, lanes contiguous); the pivot row of each column is snapshotted into a per-warp strip behind the inverses
+// because its owner lane overwrites it during the same column.  Unpivoted, as above (column diagonal dominance).
+__device__ __forceinline__ void comb_factor_big(const GlobalCtx& cx, double c) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* const snap = cx.binv + cx.binv_total + warp * cx.big_nst;
+    for (int ib = warp; ib < cx.n_big; ib += GLOBAL_WARPS) {
+        const int i = cx.cord[ib];
+        const int ns = cx.ns[i], st = cx.offy[i], ss = cx.offs[i], nst = 1 << ns;
+        double* const bi = cx.binv + cx.boff[i];
+        const double Di = cx.cD[i], Ei = cx.cE[i];
+        for (int r = lane; r < nst; r += 32) {
+            for (int q = 0; q < nst; ++q) bi[q * nst + r] = 0.0;
+            double out = (r == 0) ? Di : 0.0;
+            for (int j = 0; j < ns; ++j) {
+                const int bit = 1 << j;
+                const double s = cx.Sall[ss + j];
+                const bool set = (r & bit) != 0;
+                out += set ? Ei + cx.cDp[ss + j] + Di : s;
+                bi[(r ^ bit) * nst + r] = -c * (set ? s : Ei);
+            }
+            bi[r * nst + r] = fma(c, out, 1.0);
+        }
+        __syncwarp();
+        for (int k = 0; k < nst; ++k) {
+            for (int q = lane; q < nst; q += 32) snap[q] = bi[q * nst + k];
+            __syncwarp();
+            const double p = 1.0 / snap[k];
+            for (int r = lane; r < nst; r += 32) {
+                const bool me = r == k;
+                const double coef = me ? p : -bi[k * nst + r] * p;
+                for (int q = 0; q < nst; ++q) {
+                    const double v = me ? 0.0 : bi[q * nst + r];
+                    bi[q * nst + r] = fma(coef, snap[q], v);
+                }
+                bi[k * nst + r] = coef;
+            }
+            __syncwarp();
+        }
+        double wsum = 0.0;
+        const double f = cx.mult[st + 1] * cx.facA[st];
+        for (int r = lane; r < nst; r += 32) {
+            const double wr = bi[r] * f;                          // column 0 of the inverse: response to a unit mRNA source
+            cx.w[st + 1 + r] = wr;
+            wsum += wr;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        if (lane == 0) cx.m[i] = wsum;
+    }
+}
+
+__device__ __forceinline__ void comb_block_solve_big(const GlobalCtx& cx, double* x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* const snap = cx.binv + cx.binv_total + warp * cx.big_nst;
+    for (int ib = warp; ib < cx.n_big; ib += GLOBAL_WARPS) {
+        const int i = cx.cord[ib];
+        const int st = cx.offy[i], nst = 1 << cx.ns[i];
+        const double* const bi = cx.binv + cx.boff[i];
+        const double xr = x[st] * cx.facA[st];
+        for (int q = lane; q < nst; q += 32) snap[q] = (q == 0) ? fma(cx.mult[st + 1], xr, x[st + 1]) : x[st + 1 + q];
+        __syncwarp();
+        double zs = 0.0;
+        for (int r = lane; r < nst; r += 32) {
+            double acc = 0.0;
+            for (int q = 0; q < nst; ++q) acc = fma(bi[q * nst + r], snap[q], acc);
+            x[st + 1 + r] = acc;
+            zs += acc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+        if (lane == 0) {
+            x[st] = xr;
+            cx.pvec[i] = zs;
+            cx.z[i] = 0.0;
+        }
+        __syncwarp();
+    }
+}
+
 // Inverses of all pattern blocks for c = gamma*h, the unit responses w of the pattern states and m_i.
 // Needs facA[st] = 1/(1 + c B) and mult[st+1] = c C (written by eval_rhs_comb) behind a barrier.
 __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
     const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int N = cx.N;
-    for (int i0 = 0; i0 < N; i0 += 16) {
+    if (cx.n_big > 0) comb_factor_big(cx, c);
+    for (int i0 = cx.n_big; i0 < N; i0 += 16) {
         const bool act = i0 + grp < N;
         const int i = act ? cx.cord[i0 + grp] : 0;
         const int ns = act ? cx.ns[i] : 0, st = act ? cx.offy[i] : 0, ss = act ? cx.offs[i] : 0;
@@ -438,7 +529,8 @@ __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
 __device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x) {
     const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int N = cx.N;
-    for (int i0 = 0; i0 < N; i0 += 16) {
+    if (cx.n_big > 0) comb_block_solve_big(cx, x);
+    for (int i0 = cx.n_big; i0 < N; i0 += 16) {
         const bool act = i0 + grp < N;
         const int i = act ? cx.cord[i0 + grp] : 0;
         const int st = act ? cx.offy[i] : 0;
@@ -699,26 +791,49 @@ __device__ __forceinline__ void dispatch_uniform(int v, F&& f) {
     }
 }
 
+// Column hand-over of the Gauss-Jordan sweep: the 16 owner lanes of the NEXT pivot column (one half-warp) publish it to
+// shared memory AND choose its pivot among the rows not used yet - key = FP32 magnitude with the low 7 mantissa bits
+// replaced by (127 - row), so ONE integer max (redux.sync over the half-warp) returns the largest entry and, on ties,
+// the lowest row; the winning lane also publishes -1/pivot and records the permutation.  (Until round 2 every warp
+// repeated this search after the barrier: ~50 of the ~170 instructions of a column, in all 8 warps.)
+template <int TILE, int SLOT>
+__device__ __forceinline__ void gj_publish(const GlobalCtx& cx, const double (&A)[TILE][TILE], double* coln, double* info,
+                                           unsigned rowused, int tr, int knext) {
+    unsigned key = 0;
+    double best = 1.0;
+#pragma unroll
+    for (int a = 0; a < TILE; ++a) {
+        const double v = A[a][SLOT];
+        coln[tr + 16 * a] = v;
+        const unsigned kq = ((rowused >> a) & 1u) ? 0u : ((__float_as_uint(fabsf((float)v)) & ~127u) | (unsigned)(127 - (tr + 16 * a)));
+        if (kq > key) { key = kq; best = v; }
+    }
+    const unsigned top = __reduce_max_sync(0xffffu << (threadIdx.x & 16), key);
+    if (key == top) {
+        const int p = 127 - (int)(top & 127u);
+        info[0] = -fast_rcp(best);                       // -1/pivot
+        *(int*)(info + 1) = p;
+        cx.piv[knext] = p;
+        cx.pinv[p] = knext;
+    }
+}
+
 template <int TILE>
 __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE][TILE]) {
     constexpr int GP = 16 * TILE;            // padded order
-    constexpr int NW = (TILE + 1) / 2;       // pivot candidates per lane
     const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4, lane = threadIdx.x & 31;
     const int nQ = cx.nQ;
-    unsigned mymask = 0;                     // bit w: physical row lane + 32 w has already served as a pivot row
+    unsigned rowused = 0;                    // bit a: physical row tr + 16 a has already served as a pivot row
     GJ_TRACE_DECL
     // Thread (tr, tc) = (tid & 15, tid >> 4): the 16 owners of one matrix ROW segment sit in one half-warp, so
     // the pivot row reaches every thread by a warp shuffle; only the pivot COLUMN crosses warps, through shared
-    // memory, written by its 16 owner lanes at the end of the previous iteration (other parity buffer).
-    // => ONE block barrier per eliminated column.
-    // The loop body is kept SMALL (one copy, ~300 instructions): the column slots of the tile are rotated by one
+    // memory, written (with its pivot choice, gj_publish) by its 16 owner lanes at the end of the previous iteration
+    // (other parity buffer).  => ONE block barrier per eliminated column.
+    // The loop body is kept SMALL (one copy): the column slots of the tile are rotated by one
     // after every 16 columns so that the active column always sits in slot 0 (TILE rotations = identity), and the
     // row slot of the pivot is resolved by one uniform branch tree.  (An unrolled body of 12 copies measured
     // ~2x slower: the column sweep became instruction-fetch bound.)
-    if (nQ > 0 && tc == 0) {
-#pragma unroll
-        for (int a = 0; a < TILE; ++a) cx.colbuf[tr + 16 * a] = A[a][0];
-    }
+    if (nQ > 0 && tc == 0) gj_publish<TILE, 0>(cx, A, cx.colbuf, cx.rowbuf, 0u, tr, 0);
 #pragma unroll 1
     for (int kb = 0; kb < TILE; ++kb) {
 #pragma unroll 1
@@ -726,32 +841,19 @@ __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE]
             const int k = kb * 16 + kk;
             if (k >= nQ) break;
             const double* const colb = cx.colbuf + (kk & 1) * GP;
+            const double* const info = cx.rowbuf + (kk & 1) * 2;
             __syncthreads();
             GJ_TRACE(0)
             double cv[TILE];                 // this thread's rows of column k
 #pragma unroll
             for (int a = 0; a < TILE; ++a) cv[a] = colb[tr + 16 * a];
-            // Pivot search, redundantly in every warp.  Key = FP32 magnitude with the low 7 mantissa bits replaced
-            // by (127 - row): ONE integer max (redux.sync) returns the largest entry and, on ties, the lowest row.
-            // Used rows carry key 0; padded rows hold exact zeros and lose to any valid row.
-            unsigned key = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const int r = lane + 32 * w;
-                if (r < GP) {
-                    const unsigned kq = (__float_as_uint(fabsf((float)colb[r])) & ~127u) | (unsigned)(127 - r);
-                    key = max(key, ((mymask >> w) & 1u) ? 0u : kq);
-                }
-            }
-            key = __reduce_max_sync(0xffffffffu, key);
-            const int p = 127 - (int)(key & 127u);
+            const double nip = info[0];      // -1/pivot
+            const int p = *(const int*)(info + 1);
             GJ_TRACE(1)
-            if ((p & 31) == lane) mymask |= 1u << (p >> 5);
-            if (threadIdx.x == 0) { cx.piv[k] = p; cx.pinv[p] = k; }
-            const double nip = -fast_rcp(colb[p]);        // -1/pivot
             const int src = (lane & 16) | (p & 15);       // lane of this half-warp that owns row p
             const bool prow = tr == (p & 15);
             const bool pcol = tc == kk;
+            if (prow) rowused |= 1u << (p >> 4);
             double rv[TILE];
             GJ_TRACE(2)
             // Row p sits in register slot p >> 4 (uniform over the CTA).  Inside the dispatched block: fetch it,
@@ -774,27 +876,36 @@ __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE]
                 }
             });
             GJ_TRACE(3)
-#pragma unroll
-            for (int a = 0; a < TILE; ++a) {
-                const double g = cv[a] * nip;
-#pragma unroll
-                for (int b = 0; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
-            }
-            GJ_TRACE(4)
             // column k+1 for the next iteration (other parity: nobody reads that buffer any more); after column 15
-            // of a block it is the first column of the NEXT slot (the rotation below has not happened yet)
-            if (k + 1 < nQ) {
-                double* const coln = cx.colbuf + ((kk + 1) & 1) * GP;
-                if (kk < 15) {
-                    if (tc == kk + 1) {
+            // of a block it is the first column of the NEXT slot (the rotation below has not happened yet).  Its owner
+            // half-warp updates that column FIRST and publishes it (with the pivot choice) before the rest of its tile.
+            const bool more = k + 1 < nQ;
+            double* const coln = cx.colbuf + ((kk + 1) & 1) * GP;
+            double* const infon = cx.rowbuf + ((kk + 1) & 1) * 2;
+            if (kk < 15) {
 #pragma unroll
-                        for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][0];
-                    }
-                } else if (tc == 0) {
+                for (int a = 0; a < TILE; ++a) A[a][0] = fma(cv[a] * nip, rv[0], A[a][0]);
+                if (more && tc == kk + 1) gj_publish<TILE, 0>(cx, A, coln, infon, rowused, tr, k + 1);
 #pragma unroll
-                    for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][TILE > 1 ? 1 : 0];
+                for (int a = 0; a < TILE; ++a) {
+                    const double g = cv[a] * nip;
+#pragma unroll
+                    for (int b = 1; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
+                }
+            } else {
+                constexpr int S1 = TILE > 1 ? 1 : 0;
+#pragma unroll
+                for (int a = 0; a < TILE; ++a) A[a][S1] = fma(cv[a] * nip, rv[S1], A[a][S1]);
+                if (more && tc == 0) gj_publish<TILE, S1>(cx, A, coln, infon, rowused, tr, k + 1);
+#pragma unroll
+                for (int a = 0; a < TILE; ++a) {
+                    const double g = cv[a] * nip;
+#pragma unroll
+                    for (int b = 0; b < TILE; ++b)
+                        if (b != S1) A[a][b] = fma(g, rv[b], A[a][b]);
                 }
             }
+            GJ_TRACE(4)
             GJ_TRACE(5)
         }
         // rotate the column slots: slot b <- slot b+1 (executed TILE times in total = identity)
@@ -978,8 +1089,20 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
 }
 
 // COMB: the combinatorial kinetic model (its own instantiation, so that the other models compile exactly as without it)
-template <int TILE, bool COMB>
+template <bool OVF>
+__device__ __forceinline__ double* place_array(double* smem, double* gsc, int off) {
+    if constexpr (OVF) {
+        if (off >= OVF_BASE) return gsc + (off - OVF_BASE);
+    }
+    return smem + off;
+}
+
+// OVF (capacity fallback, generic Schur path only): the large per-system arrays - Schur matrix, stage vectors, block
+// factors, state - may live in a per-CTA slice of a global scratch buffer (L2 resident) when the network does not fit
+// into one CTA's shared memory; the host layout (pk_global.cu::layout_smem) decides array by array.
+template <int TILE, bool COMB, bool OVF = false>
 __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB) ? 2 : 1) global_net_kernel(const GlobalArgs a) {
+    static_assert(!OVF || TILE == 0, "the overflow layout exists for the generic Schur path only");
     extern __shared__ double smem[];
     const GlobalTopoDev& tp = a.tp;
     const GlobalSmem& L = a.sm;
@@ -987,16 +1110,21 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
     __shared__ long long s_sys;
     __shared__ StepState S_;
     int* const ismem = (int*)(smem + L.ints);
+    double* gsc = nullptr;
+    if constexpr (OVF) gsc = a.ovf + (size_t)blockIdx.x * (size_t)L.ovf_total;
+#define at(off) place_array<OVF>(smem, gsc, off)
     GlobalCtx cx{tp,
-                 smem + L.par, smem + L.Kt, smem + L.Sall, smem + L.y, smem + L.arg, smem + L.U, smem + L.w,
-                 smem + L.facA, smem + L.mult, smem + L.clo, smem + L.pvec, smem + L.g, smem + L.m, smem + L.z,
-                 smem + L.Sc, smem + L.idiag, smem + L.red, (int*)(smem + L.perm), L.ld, n, N, tp.nQ, tp.model,
+                 at(L.par), smem + L.Kt, smem + L.Sall, at(L.y), at(L.arg), at(L.U), at(L.w),
+                 at(L.facA), at(L.mult), at(L.clo), smem + L.pvec, smem + L.g, smem + L.m, smem + L.z,
+                 at(L.Sc), smem + L.idiag, smem + L.red, (int*)(smem + L.perm), L.ld, n, N, tp.nQ, tp.model,
                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.0,
                  ismem + L.i_offy, ismem + L.i_offs, ismem + L.i_ns, ismem + L.i_drv, ismem + L.i_tfptr, ismem + L.i_tfidx,
                  ismem + L.i_qlist, ismem + L.i_qpos, ismem + L.i_sprot, (const unsigned char*)(ismem + L.i_ent),
                  smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
-                 a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord};
+                 a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord,
+                 L.n_big, L.big_nst, L.binv_total};
+#undef at
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
     cx.cC = cx.cB + N;

@@ -270,7 +270,7 @@ int pk_destroy(pk_handle_t h) {
                       &h->nsteps, &h->nrej, &h->target, &h->sigma, &h->group, &h->scratch, &h->traj, &h->ag_stage, &h->isig, &h->tw, &h->bar, &h->lamg};
     for (DevBuf* b : bufs) b->release();
     DevBuf* gbufs[] = {&h->g_params, &h->g_y0, &h->g_t, &h->g_stops, &h->g_Y, &h->g_loss, &h->g_F, &h->g_metric,
-                       &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc};
+                       &h->g_status, &h->g_nsteps, &h->g_nrej, &h->g_traj, &h->g_binv, &h->g_fc, &h->g_ovf};
     for (DevBuf* b : gbufs) b->release();
     pkh::release_global_topologies(h);
     pk_sym_free(h);

@@ -70,29 +70,43 @@ int bucket_of(double t, const std::vector<double>& g) {       // jacspeedup.py:1
     return std::min(std::max(j, 0), (int)g.size() - 1);
 }
 
-void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
+// Shared-memory layout of one system.  `spill` = how many of the large arrays (in the order Sc, U, clo, mult, facA, w,
+// arg, y, par) live in the per-CTA global scratch instead (capacity fallback, generic Schur path only): their offsets
+// are OVF_BASE + offset into the scratch slice, L.ovf_total doubles per CTA.
+void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic, int spill) {
     const pk::GlobalTopoDev& d = th->dev;
     pk::GlobalSmem& L = th->sm;
+    const int n_big = L.n_big, big_nst = L.big_nst, binv_total = L.binv_total;
     memset(&L, 0, sizeof(L));
-    int o = 0;
+    L.n_big = n_big; L.big_nst = big_nst; L.binv_total = binv_total;
+    int o = 0, og = 0, rank = 0;
     auto take = [&](int count) {
         const int at = o;
         o += (count + 1) & ~1;
         return at;
     };
+    auto take_big = [&](int count, int order) {        // order = position in the spill list
+        (void)rank;
+        if (order < spill) {
+            const int at = pk::OVF_BASE + og;
+            og += (count + 1) & ~1;
+            return at;
+        }
+        return take(count);
+    };
     const int n = d.n, N = d.N, nQ = d.nQ;
     // register-resident Gauss-Jordan path for up to 128 regulators, shared-memory LU beyond
-    L.tile = (force_generic || nQ > 16 * pk::GJ_MAX_TILE) ? 0 : (nQ <= 32 ? 2 : nQ <= 64 ? 4 : nQ <= 96 ? 6 : 8);
-    L.par = take(th->P);
+    L.tile = (force_generic || spill > 0 || nQ > 16 * pk::GJ_MAX_TILE) ? 0 : (nQ <= 32 ? 2 : nQ <= 64 ? 4 : nQ <= 96 ? 6 : 8);
+    L.par = take_big(th->P, 8);
     L.Kt = take(d.K);
     L.Sall = take(d.S);
-    L.y = take(n);
-    L.arg = take(n);
-    L.U = take(6 * n);
-    L.w = take(n);
-    L.facA = take(n);
-    L.mult = take(n);
-    L.clo = take(n);
+    L.y = take_big(n, 7);
+    L.arg = take_big(n, 6);
+    L.U = take_big(6 * n, 1);
+    L.w = take_big(n, 5);
+    L.facA = take_big(n, 4);
+    L.mult = take_big(n, 3);
+    L.clo = take_big(n, 2);
     L.pvec = take(N);
     L.g = take(N);
     L.m = take(N);
@@ -101,7 +115,7 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     L.tfdeg = take(N);
     if (L.tile == 0) {
         L.ld = nQ | 1;                               // odd leading dimension: conflict-free column walks
-        L.Sc = take(nQ * L.ld);
+        L.Sc = take_big(nQ * L.ld, 0);
         L.idiag = take(nQ);
         L.red = take(2 * pk::GLOBAL_WARPS + nQ);
         L.perm = take((nQ + 1) / 2 + 1);
@@ -136,11 +150,14 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic) {
     L.i_cord = itake(N);
     o += (io + 1) / 2;
     L.total = o;
+    L.ovf_total = og;
     th->smem_bytes = (size_t)o * sizeof(double);
 }
+constexpr int N_SPILLABLE = 9;
 
 typedef void (*global_kernel_t)(const pk::GlobalArgs);
-global_kernel_t kernel_for_tile(int tile, bool comb) {
+global_kernel_t kernel_for_tile(int tile, bool comb, bool ovf) {
+    if (ovf) return comb ? pk::global_net_kernel<0, true, true> : pk::global_net_kernel<0, false, true>;
     if (comb) switch (tile) {
         case 2: return pk::global_net_kernel<2, true>;
         case 4: return pk::global_net_kernel<4, true>;
@@ -179,10 +196,16 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     std::vector<int> off_y(N), off_s(N);
     int n = 0, S = 0;
     size_t binv_elems = 0;            // model 2: doubles of block-inverse scratch per resident system
+    int n_big = 0, big_nst = 0;       // model 2: blocks of more than 16 patterns (inverted by one warp in the scratch)
     for (int i = 0; i < N; ++i) {
         if (tp->n_sites[i] < 0) return fail("pk_global_upload: negative n_sites");
-        if (comb && tp->n_sites[i] > 4)
-            return fail("pk_global_upload: the combinatorial model supports at most 4 sites per protein (16 pattern states)");
+        if (comb && tp->n_sites[i] > pk::COMB_MAX_SITES)
+            return fail("pk_global_upload: the combinatorial model supports at most " + std::to_string(pk::COMB_MAX_SITES) +
+                        " sites per protein (2^sites pattern states each)");
+        if (comb && tp->n_sites[i] > 4) {
+            ++n_big;
+            big_nst = std::max(big_nst, 1 << tp->n_sites[i]);
+        }
         off_y[i] = n;
         off_s[i] = S;
         // network.py:144-149: combinatorial block = mRNA + 2^ns pattern states, otherwise mRNA + P0 + ns sites
@@ -248,7 +271,14 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     pk::GlobalTopoDev& d = th->dev;
     d.model = tp->model; d.N = N; d.K = K; d.nb = nb; d.n = n; d.S = S; d.nQ = (int)qlist.size();
     th->P = K + 5 * N + S + 1;
-    th->binv_elems = binv_elems;
+    if (binv_elems + (size_t)pk::GLOBAL_WARPS * big_nst > (size_t)1 << 30) {
+        delete th;
+        return fail("pk_global_upload: combinatorial pattern blocks need more than 8 GiB of scratch per resident system");
+    }
+    th->sm.n_big = n_big;
+    th->sm.big_nst = big_nst;
+    th->sm.binv_total = (int)binv_elems;
+    th->binv_elems = binv_elems + (size_t)pk::GLOBAL_WARPS * big_nst;     // + one pivot-row snapshot strip per warp
     th->kin_grid.assign(tp->kin_grid, tp->kin_grid + nb);
     cudaError_t e = cudaSuccess;
 #define UP(field, src, count)                                                     \
@@ -273,14 +303,22 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
         delete th;
         return fail(std::string("pk_global_upload: ") + cudaGetErrorString(e));
     }
-    pkh::layout_smem(th, nnzC, tp->force_generic_schur);
+    // Capacity: when one system does not fit into a CTA's shared memory, the large arrays move one by one (Schur matrix
+    // first, then the stage vectors, the block factors, the state) into a per-CTA slice of a global scratch buffer, which
+    // the 126 MB L2 keeps resident; only the small per-protein arrays and the staged topology must stay on chip.
+    // force_generic_schur: 1 = shared-memory LU although the register path fits, 2 = additionally every spillable array
+    // in the scratch (tests compare that against the all-shared layout: same arithmetic, bit-identical results).
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
-    if (th->smem_bytes > (size_t)max_optin) {
+    const size_t cap = (size_t)max_optin - 256;       // static shared memory of the kernel (queue slot, step state)
+    int spill = tp->force_generic_schur >= 2 ? pkh::N_SPILLABLE : 0;
+    pkh::layout_smem(th, nnzC, tp->force_generic_schur, spill);
+    while (th->smem_bytes > cap && spill < pkh::N_SPILLABLE) pkh::layout_smem(th, nnzC, tp->force_generic_schur, ++spill);
+    if (th->smem_bytes > cap) {
         const size_t need = th->smem_bytes;
         delete th;
-        return fail("pk_global_upload: network needs " + std::to_string(need) + " B of shared memory per system, device offers " +
-                    std::to_string(max_optin));
+        return fail("pk_global_upload: the per-protein arrays and the staged topology alone need " + std::to_string(need) +
+                    " B of shared memory per system, device offers " + std::to_string(max_optin));
     }
     h->topos.push_back(th);
     *topo_id = (int32_t)h->topos.size() - 1;
@@ -484,7 +522,7 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     a.nfc = (long long)nfc;
     a.counter = h->counter;
 
-    const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile, d.model == 2);
+    const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile, d.model == 2, th->sm.ovf_total > 0);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th->smem_bytes));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pk::GLOBAL_BLOCK, th->smem_bytes));
@@ -525,6 +563,10 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
         CK(h->g_binv.ensure((size_t)grid * th->binv_elems * sizeof(double)));
         a.binv = (double*)h->g_binv.p;
         a.binv_stride = (long long)th->binv_elems;
+    }
+    if (th->sm.ovf_total) {                           // capacity fallback: per-CTA slices of the arrays outside shared memory
+        CK(h->g_ovf.ensure((size_t)grid * th->sm.ovf_total * sizeof(double)));
+        a.ovf = (double*)h->g_ovf.p;
     }
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned long long), st));
     CK(cudaEventRecord(h->ev0, st));

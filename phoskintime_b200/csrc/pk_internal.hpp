@@ -62,7 +62,7 @@ struct pk_handle_s {
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
     pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj, isig, tw, lamg;
-    pkh::DevBuf g_params, g_y0, g_t, g_stops, g_Y, g_loss, g_F, g_metric, g_status, g_nsteps, g_nrej, g_traj, g_binv, g_fc;
+    pkh::DevBuf g_params, g_y0, g_t, g_stops, g_Y, g_loss, g_F, g_metric, g_status, g_nsteps, g_nrej, g_traj, g_binv, g_fc, g_ovf;
     unsigned long long* counter = nullptr;
     int last_launches = 0;
     float last_ms = 0.f;

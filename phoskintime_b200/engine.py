@@ -361,7 +361,10 @@ class Engine:
     # --------------------------------------------------------------------- global network
     def global_upload(self, sys_, force_generic=False):
         """Upload the static topology of a `GlobalSystem` (the array part of the reference's
-        System.odeint_args(), global_model/network.py:508-526) once; returns the topology id."""
+        System.odeint_args(), global_model/network.py:508-526) once; returns the topology id.
+        `force_generic` (testing): 1/True = shared-memory LU of the Schur block although the register path fits,
+        2 = additionally every large per-system array in the per-CTA global scratch (the capacity fallback the
+        library chooses by itself when a network does not fit into one CTA's shared memory)."""
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         arrs = {"n_sites": i32(sys_.idx.n_sites), "W_indptr": i32(sys_.W_indptr), "W_indices": i32(sys_.W_indices),
@@ -372,7 +375,7 @@ class Engine:
         tp.model, tp.N, tp.K, tp.n_bins = int(sys_.model), int(sys_.idx.N), int(sys_.K), int(arrs["kin_grid"].size)
         for k, a in arrs.items():
             setattr(tp, k, a.ctypes.data)
-        tp.force_generic_schur = int(bool(force_generic))
+        tp.force_generic_schur = int(force_generic)
         tid = C.c_int32(-1)
         _lib.check(self.lib.pk_global_upload(self._h, C.byref(tp), C.byref(tid)))
         return tid.value

@@ -15,7 +15,7 @@ import numpy as np
 
 MODEL_IDS = {"distributive": 0, "sequential": 1, "combinatorial": 2, "saturating": 4, "saturation": 4,
              0: 0, 1: 1, 2: 2, 4: 4}
-MAX_COMB_SITES = 4          # combinatorial blocks are inverted by 16 lanes in registers (csrc/global_net.cuh)
+MAX_COMB_SITES = 8          # blocks of up to 16 patterns are inverted in registers, 32..256 patterns by one warp in the L2-resident scratch (csrc/global_net.cuh)
 PARAM_KEYS = ("c_k", "A_i", "B_i", "C_i", "D_i", "Dp_i", "E_i")
 
 

@@ -78,8 +78,11 @@ def test_combinatorial_layout_and_27_tuple():
     assert args[22].sum() == sum(ns * (1 << ns) // 2 for ns in idx.n_sites)
     ld = synthetic_loss_data(s, T15, seed=1)
     assert np.array_equal(ld["prot_map"][:, 1], idx.n_states)
+    # blocks of 32..256 patterns are supported (one warp per block on the device); 2^9 patterns per protein are refused
+    big = synthetic_system(seed=27, N=7, K=4, max_sites=6, model=2)
+    assert big.idx.n_sites.max() == 6 and big.idx.state_dim == 7 + int((1 << big.idx.n_sites).sum())
     with pytest.raises(ValueError):
-        synthetic_system(seed=4, N=9, K=4, max_sites=6, model=2)
+        synthetic_system(seed=4, N=9, K=4, max_sites=12, model=2)
 
 
 def test_raw_parameter_transform_roundtrip():

@@ -15,7 +15,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import global_models as og  # noqa: E402
 from phoskintime_b200.global_model import synthetic_system  # noqa: E402
 
-FILES = sorted(glob.glob(os.path.join(GOLDEN, "global_*.npz")))
+# the seven round-1 cases first (tests below address some of them by position), the capacity cases of round 2 last
+_LATE = ("global_m0_N300.npz", "global_m2_N7.npz")
+FILES = sorted(glob.glob(os.path.join(GOLDEN, "global_*.npz")), key=lambda f: (os.path.basename(f) in _LATE, f))
 IDS = [os.path.basename(f)[7:-4] for f in FILES]
 
 
@@ -30,7 +32,7 @@ def load_case(path):
 
 
 def test_goldens_present():
-    assert len(FILES) == 7
+    assert len(FILES) == 9
 
 
 @pytest.mark.parametrize("path", FILES, ids=IDS)
@@ -41,7 +43,7 @@ def test_stock_simulation_matches_reference(path):
     selection — i.e. bounded by the solve's own tolerance (rtol=atol=1e-8), hence the bound below."""
     g, s, _ = load_case(path)
     net = s.as_dict()
-    for b in (0, min(2, g["params"].shape[0] - 1)):
+    for b in ((0,) if int(g["N"]) > 120 else (0, min(2, g["params"].shape[0] - 1))):     # N = 300: ~50 s per vector
         Y = og.simulate_odeint(int(g["model"]), net, g["t"], 1e-8, 1e-8, 200000, params=og.unpack_params(g["params"][b], net))
         assert Y.shape == g["Y"][b].shape
         assert np.all(np.abs(Y - g["Y"][b]) <= 1e-6 * np.abs(g["Y"][b]) + 2e-8)
