@@ -550,8 +550,12 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     // later upload still fits under the previous chunk's kernel.  Measured at 1 M succ-5 systems (tools/e2e_pipe_scan.py):
     // 4 equal chunks 3.46 ms, 5 equal 3.36, 4 x1.4 3.30, 5 x1.2 3.30, 6 x1.2 3.30, 3 x1.3 3.47 (every chunk is a launch
     // with its own tail).
-    const int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 5 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
-    const double growth = nchunks == 5 ? 1.2 : 1.0;
+    int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 5 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
+    double growth = nchunks == 5 ? 1.2 : 1.0;
+    if (const char* ev = getenv("PHOSKIN_PIPE_SCAN")) {      // TEMPORARY tuning knob: "chunks,growth"
+        int n_ = 0; double g_ = 1.0;
+        if (sscanf(ev, "%d,%lf", &n_, &g_) == 2 && n_ >= 1 && n_ <= PIPE_MAX_CHUNKS) { nchunks = n_; growth = g_; }
+    }
     cudaStream_t sin = h->s_in, sout = h->s_out;
     // small shared inputs first, then the per-system inputs chunk by chunk on the copy-in stream
     CK(cudaMemcpyAsync((void*)a.t, j->t, (size_t)j->T * sizeof(double), cudaMemcpyHostToDevice, sin));

@@ -58,7 +58,7 @@ struct pk_handle_s {
     int clock_khz = 0;
     char name[128] = {0};
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-    static constexpr int MAX_CHUNKS = 8;
+    static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evr0 = nullptr, evr1 = nullptr;
     pkh::DevBuf params, y0, t, sol, flat, Y, ssr, score, status, nsteps, nrej, target, sigma, group, scratch, traj, isig, tw, lamg;
