@@ -76,6 +76,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int tfdata, tfdeg;                // staged topology (doubles)
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
     int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff, i_cord;
+    int cscr;                         // model 2: pivot-row strips of comb_factor (16 x 16 doubles, 16-byte aligned)
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
     int ovf_total;                    // capacity fallback: doubles of per-CTA global (L2-resident) scratch; an array whose offset is
                                       // >= OVF_BASE lives there (at offset - OVF_BASE) instead of in shared memory
@@ -347,6 +348,7 @@ struct GlobalCtx {
     const int* cord;                  // proteins ordered by block size (descending): the two blocks a warp inverts together
                                       // are of (nearly) equal size, so neither half-warp idles through the other's columns
     int n_big, big_nst, binv_total;   // blocks of more than 16 patterns: cord[0 .. n_big), one warp each (comb_factor_big)
+    double* cscr;                     // model 2: [16 half-warps][16] pivot-row strips of comb_factor
 };
 
 
@@ -466,6 +468,11 @@ __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
     const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
     const int N = cx.N;
     if (cx.n_big > 0) comb_factor_big(cx, c);
+    // The pivot row of every column reaches the 16 lanes of a block through a 16-double strip in shared memory (the owner
+    // lane stores it with 8 STS.128, everybody reads it back with 8 broadcast LDS.128) instead of 32 shuffles: the SM
+    // moves ONE warp shuffle per cycle, and 8 warps x 32 shuffles per column made the elimination shuffle-throughput
+    // bound (trace, N = 120: 63 k cycles per step; interleaving two blocks per half-warp changed nothing).
+    double2* const strip = (double2*)(cx.cscr + grp * COMB_MAX_STATES);
     for (int i0 = cx.n_big; i0 < N; i0 += 16) {
         const bool act = i0 + grp < N;
         const int i = act ? cx.cord[i0 + grp] : 0;
@@ -498,11 +505,21 @@ __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
 #pragma unroll
         for (int k = 0; k < COMB_MAX_STATES; ++k) {
             if (k < smax) {
+                const bool me = r == k;
+                if (me) {
+#pragma unroll
+                    for (int q = 0; q < COMB_MAX_STATES; q += 2) strip[q >> 1] = make_double2(a[q], a[q + 1]);
+                }
+                __syncwarp();
                 double prow[COMB_MAX_STATES];
 #pragma unroll
-                for (int q = 0; q < COMB_MAX_STATES; ++q) prow[q] = __shfl_sync(0xffffffffu, a[q], k, 16);
+                for (int q = 0; q < COMB_MAX_STATES; q += 2) {
+                    const double2 v = strip[q >> 1];
+                    prow[q] = v.x;
+                    prow[q + 1] = v.y;
+                }
+                __syncwarp();                                    // the strip is rewritten by the next column's owner
                 const double p = fast_rcp(prow[k]);
-                const bool me = r == k;
                 const double coef = me ? p : -a[k] * p;          // pivot row: row/pivot; other rows: -multiplier
 #pragma unroll
                 for (int q = 0; q < COMB_MAX_STATES; ++q)
@@ -543,15 +560,26 @@ __device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x)
             if (live) b = x[st + 1 + r];
             if (r == 0) b = fma(cx.mult[st + 1], xr, b);          // translation feeds pattern 0
         }
+        // row r of the block inverse first: 16 independent (clamped, unconditional) loads in flight at once - the inverses
+        // live in L2, and a load issued inside the shuffle loop below exposed one L2 round trip per term (trace, N = 120:
+        // 18 k cycles per solve, 28 % of the step)
         const double* bi = cx.binv + (act ? cx.boff[i] : 0);
-        double acc = 0.0;
+        double mrow[COMB_MAX_STATES];
 #pragma unroll
         for (int q = 0; q < COMB_MAX_STATES; ++q) {
-            if (q < smax) {
-                const double bq = __shfl_sync(0xffffffffu, b, q, 16);
-                if (live && q < nst) acc = fma(bi[q * nst + r], bq, acc);
-            }
+            const bool ok = live && q < nst;
+            const double v = bi[ok ? q * nst + r : 0];
+            mrow[q] = ok ? v : 0.0;
         }
+        // right-hand side entries straight from shared memory (one broadcast load per term instead of two shuffles: the
+        // SM moves one warp shuffle per cycle, and 8 warps x 32 of them per pass were the pass)
+        double acc = mrow[0] * __shfl_sync(0xffffffffu, b, 0, 16);           // b_0 carries the translation term
+        const double* xb = x + st + 1;
+#pragma unroll
+        for (int q = 1; q < COMB_MAX_STATES; ++q) {
+            if (q < smax) acc = fma(mrow[q], xb[q < nst ? q : 0], acc);       // mrow[q] = 0 beyond the block
+        }
+        __syncwarp();                                                        // every lane has read x before anyone overwrites it
         double zs = live ? acc : 0.0;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
@@ -1103,7 +1131,7 @@ __device__ __forceinline__ double* place_array(double* smem, double* gsc, int of
 template <int TILE, bool COMB, bool OVF = false>
 __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB) ? 2 : 1) global_net_kernel(const GlobalArgs a) {
     static_assert(!OVF || TILE == 0, "the overflow layout exists for the generic Schur path only");
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const GlobalTopoDev& tp = a.tp;
     const GlobalSmem& L = a.sm;
     const int n = tp.n, N = tp.N, K = tp.K, S = tp.S, T = a.T, P = a.P;
@@ -1123,7 +1151,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                  smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
                  a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord,
-                 L.n_big, L.big_nst, L.binv_total};
+                 L.n_big, L.big_nst, L.binv_total, smem + L.cscr};
 #undef at
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;

@@ -546,16 +546,14 @@ int pk_local_solve_batch(pk_handle_t h, const pk_local_job* j) {
     WS(nsteps, j->out_nsteps, B * sizeof(int32_t), a.out_nsteps);
     WS(nrej, j->out_nrej, B * sizeof(int32_t), a.out_nrej);
 #undef WS
-    // Large batches: 5 chunks, each 1.2x the previous one — the first upload (nothing to hide behind) is short and every
-    // later upload still fits under the previous chunk's kernel.  Measured at 1 M succ-5 systems (tools/e2e_pipe_scan.py):
-    // 4 equal chunks 3.46 ms, 5 equal 3.36, 4 x1.4 3.30, 5 x1.2 3.30, 6 x1.2 3.30, 3 x1.3 3.47 (every chunk is a launch
-    // with its own tail).
-    int nchunks = B >= 4 * PIPE_MIN_CHUNK ? 5 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1);
-    double growth = nchunks == 5 ? 1.2 : 1.0;
-    if (const char* ev = getenv("PHOSKIN_PIPE_SCAN")) {      // TEMPORARY tuning knob: "chunks,growth"
-        int n_ = 0; double g_ = 1.0;
-        if (sscanf(ev, "%d,%lf", &n_, &g_) == 2 && n_ >= 1 && n_ <= PIPE_MAX_CHUNKS) { nchunks = n_; growth = g_; }
-    }
+    // Large batches are uploaded in chunks.  Round 1 (kernel 2.65 ms per 1 M succ-5 systems > upload ~2.1 ms: compute bound, the
+    // FIRST upload is what nothing hides): 5 chunks, each 1.2x the previous one.  Since round 2 the kernel (1.66 ms) is faster
+    // than the upload, so the pipeline is PCIe bound and the exposed part is the LAST chunk's kernel + read-back: 8 equal
+    // chunks.  Measured at 1 M systems (tools/e2e_pipe_scan.py, ms per call): 5 x1.2 2.82, 6 equal 2.84, 7 equal 2.92,
+    // 7 x1.1 2.78, 8 equal 2.72, 8 x0.95 2.90, 8 x1.1 2.89, 9 equal 2.88, 10 equal 3.06, 12 equal 3.61 (every chunk is a launch
+    // with its own tail and ~10 API calls; shrinking chunks lose more to that than they gain at the end).
+    const int nchunks = B >= 8 * PIPE_MIN_CHUNK ? 8 : (B >= 4 * PIPE_MIN_CHUNK ? 5 : (B >= 2 * PIPE_MIN_CHUNK ? 2 : 1));
+    const double growth = nchunks == 5 ? 1.2 : 1.0;
     cudaStream_t sin = h->s_in, sout = h->s_out;
     // small shared inputs first, then the per-system inputs chunk by chunk on the copy-in stream
     CK(cudaMemcpyAsync((void*)a.t, j->t, (size_t)j->T * sizeof(double), cudaMemcpyHostToDevice, sin));

@@ -113,6 +113,7 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic, int spill) {
     L.z = take(N);
     L.tfdata = take(nnzT);
     L.tfdeg = take(N);
+    L.cscr = take(d.model == 2 ? 16 * pk::COMB_MAX_STATES : 0);        // even offsets: 16-byte aligned strips
     if (L.tile == 0) {
         L.ld = nQ | 1;                               // odd leading dimension: conflict-free column walks
         L.Sc = take_big(nQ * L.ld, 0);
