@@ -284,7 +284,7 @@ __device__ __forceinline__ int fresh_tid() {           // re-read where it is us
     return t;
 }
 
-template <int TR, int TC>
+template <int TR, int TC, int NW>
 __device__ __forceinline__ void reg_load(int n, int ld, const double* W, double (&Wt)[TR][TC], int) {
     const int tid = fresh_tid();
     const int lane = tid & 31, warp = tid >> 5;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void reg_load(int n, int ld, const double* W, double 
     for (int a = 0; a < TR; ++a)
 #pragma unroll
         for (int b = 0; b < TC; ++b) {
-            const int i = lane + 32 * a, j = warp + 4 * b;
+            const int i = lane + 32 * a, j = warp + NW * b;
             Wt[a][b] = (i < n && j < n) ? W[i * ld + j] : 0.0;
         }
 }
@@ -333,7 +333,7 @@ __device__ __forceinline__ void reg_rotate_cols(double (&Wt)[TR][TC]) {
     }
 }
 
-template <int TR, int TC>
+template <int TR, int TC, int NW>
 __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* colbuf, int) {
     constexpr int RS = 32 * TR;
     const int tid = fresh_tid();
@@ -352,16 +352,17 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
     int rot_r = 0;                                     // physical row slot a holds logical slot (a + rot_r) mod TR
 #pragma unroll 1
     for (int bq = 0; bq < TC; bq += U) {
-        static_assert(8 % U == 0, "row rotations happen at column slots 8, 16, ... (k = 32, 64, ...): U must divide 8");
-        // k = 4 bq passes a multiple of 32: the next row slot becomes the pivot-row slot (once per 8 column slots — kept
+        constexpr int SLOTS32 = 32 / NW;               // column slots per 32 columns (NW warps deal the columns round-robin)
+        static_assert(SLOTS32 % U == 0, "row rotations happen at column slots 32/NW, 2*32/NW, ... (k = 32, 64, ...): U must divide 32/NW");
+        // k = NW bq passes a multiple of 32: the next row slot becomes the pivot-row slot (once per 32/NW column slots — kept
         // out of the column loop, where the compiler turns it into ~100 predicated moves per column)
-        if (bq > 0 && (bq & 7) == 0 && 4 * bq < n) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
+        if (bq > 0 && (bq & (SLOTS32 - 1)) == 0 && NW * bq < n) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int bk = bq + u;                     // logical column slot, held in physical slot u
 #pragma unroll 1
-            for (int wk = 0; wk < 4; ++wk) {
-                const int k = wk + 4 * bk;
+            for (int wk = 0; wk < NW; ++wk) {
+                const int k = wk + NW * bk;
                 if (bk >= TC || k >= n) break;         // uniform over the block
                 const double* cb = colbuf + (k & 1) * RS;
                 const int lk = k & 31;
@@ -389,10 +390,10 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
                     for (int a = 0; a < TR; ++a) Wt[a][u] = (row[a] == k) ? ip : m[a];
                 }
                 const int k1 = k + 1;                  // publish column k + 1 (its values are final now) for the next step
-                if (k1 < n && warp == (k1 & 3)) {
+                if (k1 < n && warp == (k1 & (NW - 1))) {
                     double* nb = colbuf + (k1 & 1) * RS;
 #pragma unroll
-                    for (int a = 0; a < TR; ++a) nb[row[a]] = (wk < 3) ? Wt[a][u] : Wt[a][u + 1 < TC ? u + 1 : u];
+                    for (int a = 0; a < TR; ++a) nb[row[a]] = (wk < NW - 1) ? Wt[a][u] : Wt[a][u + 1 < TC ? u + 1 : u];
                 }
                 __syncthreads();
             }
@@ -404,8 +405,8 @@ __device__ __forceinline__ void reg_invert(int n, double (&Wt)[TR][TC], double* 
     while (rot_r != 0) { reg_rotate_rows<TR, TC>(Wt); rot_r = rot_r + 1 == TR ? 0 : rot_r + 1; }
 }
 
-// dst = Winv * src (both in shared memory); red = 4 * 32 * TR doubles
-template <int TR, int TC>
+// dst = Winv * src (both in shared memory); red = NW * 32 * TR doubles
+template <int TR, int TC, int NW>
 __device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], const double* src, double* dst, double* red, int) {
     constexpr int RS = 32 * TR;
     const int tid = fresh_tid();
@@ -415,7 +416,7 @@ __device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], con
     for (int a = 0; a < TR; ++a) acc[a] = 0.0;
 #pragma unroll
     for (int b = 0; b < TC; ++b) {
-        const double xj = src[warp + 4 * b];           // same address across the warp: a broadcast load; the padded tail
+        const double xj = src[warp + NW * b];          // same address across the warp: a broadcast load; the padded tail
                                                        // of the vector is zero and so are the padded columns of Wt
 #pragma unroll
         for (int a = 0; a < TR; ++a) acc[a] = fma(Wt[a][b], xj, acc[a]);
@@ -423,7 +424,12 @@ __device__ __forceinline__ void reg_apply(int n, const double (&Wt)[TR][TC], con
 #pragma unroll
     for (int a = 0; a < TR; ++a) red[warp * RS + lane + 32 * a] = acc[a];
     __syncthreads();
-    for (int i = tid; i < n; i += 128) dst[i] = (red[i] + red[RS + i]) + (red[2 * RS + i] + red[3 * RS + i]);
+    for (int i = tid; i < n; i += 32 * NW) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2 += 2) sum += red[w2 * RS + i] + red[(w2 + 1) * RS + i];
+        dst[i] = sum;
+    }
     __syncthreads();
 }
 
@@ -471,11 +477,12 @@ __device__ __forceinline__ double dense_max(double v, double* red) {
 #endif
 template <int MODEL, int NT, int TR = 0, int TC = 0>
 __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local_dense_kernel(const LocalArgs a, const DenseLayout lay) {
-    static_assert(TR == 0 || NT == 128, "the register tile is laid out over 128 threads");
+    static_assert(TR == 0 || NT == 128 || NT == 256, "the register tile is laid out over 4 or 8 warps");
+    constexpr int NW = NT / 32;
     constexpr bool REG = TR > 0;
     double Wt[REG ? TR : 1][REG ? TC : 1];        // REG: (I - h gamma M)^-1, register resident
     extern __shared__ double smem[];
-    __shared__ double red[4];
+    __shared__ double red[8];
     __shared__ double coef[64];           // scratch + results of rosl_coeffs<6|7>
     __shared__ double smu[8], seps[8];    // REG: coefficients of the step in flight
     __shared__ unsigned long long s_idx;
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
         // inverse) a shared-memory record behind the exchange buffers
         EpiAcc e_loc{0, 0, 0, 0, 0, 0};
         EpiAcc& e = [&]() -> EpiAcc& {
-            if constexpr (REG) return ((EpiAcc*)(xbuf + 6 * 32 * TR))[lane];
+            if constexpr (REG) return ((EpiAcc*)(xbuf + (2 + NW) * 32 * TR))[lane];
             else return e_loc;
         }();
         if constexpr (REG) e = EpiAcc{0, 0, 0, 0, 0, 0};
@@ -612,8 +619,8 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
                 const double hnew = (a.m.family == 1 && forced && hh <= 1.03 * ctl.h && hh * 16.0 >= ctl.h) ? ctl.h : hh;
                 dense_fillW<MODEL, NT>(ns, n, ld, p, hnew * a.m.gamma, W, lane);
                 if constexpr (REG) {
-                    reg_load<TR, TC>(n, ld, W, Wt, lane);
-                    reg_invert<TR, TC>(n, Wt, xbuf, lane);
+                    reg_load<TR, TC, NW>(n, ld, W, Wt, lane);
+                    reg_invert<TR, TC, NW>(n, Wt, xbuf, lane);
                 } else {
                     dense_invert<NT>(n, ld, W, v2, v, lane);
                 }
@@ -647,7 +654,7 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
             if constexpr (REG) __syncthreads();
 
             auto apply = [&](const double* src, double* dst) {
-                if constexpr (REG) reg_apply<TR, TC>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
+                if constexpr (REG) reg_apply<TR, TC, NW>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
                 else dense_apply<NT>(n, ld, W, src, dst, lane);
             };
             // v_0 = h f(y); v_k = W^-1 v_{k-1}; y_new = y + sum MU_k v_k; err = sum EPS_k v_k
@@ -664,7 +671,7 @@ __global__ void __launch_bounds__(NT, TR ? PK_DENSE_REG_BLOCKS : 640 / NT) local
                 double* dst = v;
 #pragma unroll 1
                 for (int ks = 0; ks < nsol; ++ks) {
-                    reg_apply<TR, TC>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
+                    reg_apply<TR, TC, NW>(n, Wt, src, dst, xbuf + 2 * 32 * TR, lane);
                     if (ks + 1 < nsol) {
                         const double muk = smu[ks], epk = seps[ks];           // eps_0 = 0: E starts at zero
                         for (int i = lane; i < n; i += NT) {

@@ -15,9 +15,10 @@ cudaError_t launch_dense_nt(pk_handle_s* h, const pk::LocalArgs& a) {
     lay.ld = (a.n & 1) ? a.n : a.n + 1;   // odd leading dimension: conflict-free column walks
     lay.P = a.P;
     lay.nobs = 2 + a.ns;
-    lay.xtra = TR ? 6 * 32 * TR + 6 * NT : 0;          // exchange buffers + one EpiAcc (6 doubles) per thread
-    lay.nv = TR ? 4 * TC : a.n;
-    if (TR && (a.n > 4 * TC || a.n > 32 * TR)) return cudaErrorInvalidValue;
+    constexpr int NW = NT / 32;
+    lay.xtra = TR ? (2 + NW) * 32 * TR + 6 * NT : 0;   // exchange buffers + one EpiAcc (6 doubles) per thread
+    lay.nv = TR ? NW * TC : a.n;
+    if (TR && (a.n > NW * TC || a.n > 32 * TR)) return cudaErrorInvalidValue;
     size_t smem = (size_t)lay.total() * sizeof(double);
     auto kern = pk::local_dense_kernel<MODEL, NT, TR, TC>;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
@@ -40,6 +41,8 @@ template <int MODEL>
 cudaError_t launch_dense(pk_handle_s* h, const pk::LocalArgs& a) {
     // 41..68 states (rand-6: 65): the inverse lives in registers (3 x 17 tile per thread), see local_dense.cuh
     if constexpr (MODEL == 2) {
+        // (8 warps per system with a 3 x 9 tile — the functions are generic in the warp count — measured SLOWER: 3.09e5
+        //  against 3.57e5 solves/s on rand-6; the per-column overhead is paid by twice as many warps for half the FMAs each)
         if (a.n > 40 && a.n <= 68 && !getenv("PK_DENSE_SMEM")) return launch_dense_nt<MODEL, 128, 3, 17>(h, a);
     }
     if (a.n >= 40) return launch_dense_nt<MODEL, 128>(h, a);
