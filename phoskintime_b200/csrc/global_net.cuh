@@ -819,49 +819,26 @@ __device__ __forceinline__ void dispatch_uniform(int v, F&& f) {
     }
 }
 
-// Column hand-over of the Gauss-Jordan sweep: the 16 owner lanes of the NEXT pivot column (one half-warp) publish it to
-// shared memory AND choose its pivot among the rows not used yet - key = FP32 magnitude with the low 7 mantissa bits
-// replaced by (127 - row), so ONE integer max (redux.sync over the half-warp) returns the largest entry and, on ties,
-// the lowest row; the winning lane also publishes -1/pivot and records the permutation.  (Until round 2 every warp
-// repeated this search after the barrier: ~50 of the ~170 instructions of a column, in all 8 warps.)
-template <int TILE, int SLOT>
-__device__ __forceinline__ void gj_publish(const GlobalCtx& cx, const double (&A)[TILE][TILE], double* coln, double* info,
-                                           unsigned rowused, int tr, int knext) {
-    unsigned key = 0;
-    double best = 1.0;
-#pragma unroll
-    for (int a = 0; a < TILE; ++a) {
-        const double v = A[a][SLOT];
-        coln[tr + 16 * a] = v;
-        const unsigned kq = ((rowused >> a) & 1u) ? 0u : ((__float_as_uint(fabsf((float)v)) & ~127u) | (unsigned)(127 - (tr + 16 * a)));
-        if (kq > key) { key = kq; best = v; }
-    }
-    const unsigned top = __reduce_max_sync(0xffffu << (threadIdx.x & 16), key);
-    if (key == top) {
-        const int p = 127 - (int)(top & 127u);
-        info[0] = -fast_rcp(best);                       // -1/pivot
-        *(int*)(info + 1) = p;
-        cx.piv[knext] = p;
-        cx.pinv[p] = knext;
-    }
-}
-
 template <int TILE>
 __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE][TILE]) {
     constexpr int GP = 16 * TILE;            // padded order
+    constexpr int NW = (TILE + 1) / 2;       // pivot candidates per lane
     const int tr = threadIdx.x & 15, tc = threadIdx.x >> 4, lane = threadIdx.x & 31;
     const int nQ = cx.nQ;
-    unsigned rowused = 0;                    // bit a: physical row tr + 16 a has already served as a pivot row
+    unsigned mymask = 0;                     // bit w: physical row lane + 32 w has already served as a pivot row
     GJ_TRACE_DECL
     // Thread (tr, tc) = (tid & 15, tid >> 4): the 16 owners of one matrix ROW segment sit in one half-warp, so
     // the pivot row reaches every thread by a warp shuffle; only the pivot COLUMN crosses warps, through shared
-    // memory, written (with its pivot choice, gj_publish) by its 16 owner lanes at the end of the previous iteration
-    // (other parity buffer).  => ONE block barrier per eliminated column.
-    // The loop body is kept SMALL (one copy): the column slots of the tile are rotated by one
+    // memory, written by its 16 owner lanes at the end of the previous iteration (other parity buffer).
+    // => ONE block barrier per eliminated column.
+    // The loop body is kept SMALL (one copy, ~300 instructions): the column slots of the tile are rotated by one
     // after every 16 columns so that the active column always sits in slot 0 (TILE rotations = identity), and the
     // row slot of the pivot is resolved by one uniform branch tree.  (An unrolled body of 12 copies measured
     // ~2x slower: the column sweep became instruction-fetch bound.)
-    if (nQ > 0 && tc == 0) gj_publish<TILE, 0>(cx, A, cx.colbuf, cx.rowbuf, 0u, tr, 0);
+    if (nQ > 0 && tc == 0) {
+#pragma unroll
+        for (int a = 0; a < TILE; ++a) cx.colbuf[tr + 16 * a] = A[a][0];
+    }
 #pragma unroll 1
     for (int kb = 0; kb < TILE; ++kb) {
 #pragma unroll 1
@@ -869,19 +846,32 @@ __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE]
             const int k = kb * 16 + kk;
             if (k >= nQ) break;
             const double* const colb = cx.colbuf + (kk & 1) * GP;
-            const double* const info = cx.rowbuf + (kk & 1) * 2;
             __syncthreads();
             GJ_TRACE(0)
             double cv[TILE];                 // this thread's rows of column k
 #pragma unroll
             for (int a = 0; a < TILE; ++a) cv[a] = colb[tr + 16 * a];
-            const double nip = info[0];      // -1/pivot
-            const int p = *(const int*)(info + 1);
+            // Pivot search, redundantly in every warp.  Key = FP32 magnitude with the low 7 mantissa bits replaced
+            // by (127 - row): ONE integer max (redux.sync) returns the largest entry and, on ties, the lowest row.
+            // Used rows carry key 0; padded rows hold exact zeros and lose to any valid row.
+            unsigned key = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int r = lane + 32 * w;
+                if (r < GP) {
+                    const unsigned kq = (__float_as_uint(fabsf((float)colb[r])) & ~127u) | (unsigned)(127 - r);
+                    key = max(key, ((mymask >> w) & 1u) ? 0u : kq);
+                }
+            }
+            key = __reduce_max_sync(0xffffffffu, key);
+            const int p = 127 - (int)(key & 127u);
             GJ_TRACE(1)
+            if ((p & 31) == lane) mymask |= 1u << (p >> 5);
+            if (threadIdx.x == 0) { cx.piv[k] = p; cx.pinv[p] = k; }
+            const double nip = -fast_rcp(colb[p]);        // -1/pivot
             const int src = (lane & 16) | (p & 15);       // lane of this half-warp that owns row p
             const bool prow = tr == (p & 15);
             const bool pcol = tc == kk;
-            if (prow) rowused |= 1u << (p >> 4);
             double rv[TILE];
             GJ_TRACE(2)
             // Row p sits in register slot p >> 4 (uniform over the CTA).  Inside the dispatched block: fetch it,
@@ -904,36 +894,27 @@ __device__ __forceinline__ void gj_invert(const GlobalCtx& cx, double (&A)[TILE]
                 }
             });
             GJ_TRACE(3)
-            // column k+1 for the next iteration (other parity: nobody reads that buffer any more); after column 15
-            // of a block it is the first column of the NEXT slot (the rotation below has not happened yet).  Its owner
-            // half-warp updates that column FIRST and publishes it (with the pivot choice) before the rest of its tile.
-            const bool more = k + 1 < nQ;
-            double* const coln = cx.colbuf + ((kk + 1) & 1) * GP;
-            double* const infon = cx.rowbuf + ((kk + 1) & 1) * 2;
-            if (kk < 15) {
 #pragma unroll
-                for (int a = 0; a < TILE; ++a) A[a][0] = fma(cv[a] * nip, rv[0], A[a][0]);
-                if (more && tc == kk + 1) gj_publish<TILE, 0>(cx, A, coln, infon, rowused, tr, k + 1);
+            for (int a = 0; a < TILE; ++a) {
+                const double g = cv[a] * nip;
 #pragma unroll
-                for (int a = 0; a < TILE; ++a) {
-                    const double g = cv[a] * nip;
-#pragma unroll
-                    for (int b = 1; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
-                }
-            } else {
-                constexpr int S1 = TILE > 1 ? 1 : 0;
-#pragma unroll
-                for (int a = 0; a < TILE; ++a) A[a][S1] = fma(cv[a] * nip, rv[S1], A[a][S1]);
-                if (more && tc == 0) gj_publish<TILE, S1>(cx, A, coln, infon, rowused, tr, k + 1);
-#pragma unroll
-                for (int a = 0; a < TILE; ++a) {
-                    const double g = cv[a] * nip;
-#pragma unroll
-                    for (int b = 0; b < TILE; ++b)
-                        if (b != S1) A[a][b] = fma(g, rv[b], A[a][b]);
-                }
+                for (int b = 0; b < TILE; ++b) A[a][b] = fma(g, rv[b], A[a][b]);
             }
             GJ_TRACE(4)
+            // column k+1 for the next iteration (other parity: nobody reads that buffer any more); after column 15
+            // of a block it is the first column of the NEXT slot (the rotation below has not happened yet)
+            if (k + 1 < nQ) {
+                double* const coln = cx.colbuf + ((kk + 1) & 1) * GP;
+                if (kk < 15) {
+                    if (tc == kk + 1) {
+#pragma unroll
+                        for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][0];
+                    }
+                } else if (tc == 0) {
+#pragma unroll
+                    for (int a = 0; a < TILE; ++a) coln[tr + 16 * a] = A[a][TILE > 1 ? 1 : 0];
+                }
+            }
             GJ_TRACE(5)
         }
         // rotate the column slots: slot b <- slot b+1 (executed TILE times in total = identity)
