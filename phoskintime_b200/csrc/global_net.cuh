@@ -6,7 +6,7 @@
 //
 // Structure of the problem (what the design exploits):
 //   * protein i owns the block [mRNA, P0, site_1..site_ns]; phosphorylation rates S = W.(Kmat[:,bucket]*c_k)
-//     are piecewise constant in time (13 buckets) and do not depend on the state;
+//     are piecewise constant in time (one value per kinase-grid bucket) and do not depend on the state;
 //   * the ONLY coupling between blocks is mRNA synthesis: dR_i/dt = synth_i(TF_in_i) - B_i R_i with
 //     TF_in_i a sparse combination of the total protein p_j = P0_j + sum(sites_j) of its regulators.
 //   So  J = J_blk + E_R G E_p  with J_blk block diagonal (arrow for models 0/4, tridiagonal chain for
@@ -14,7 +14,8 @@
 //   E_p the "total protein" selector.  (I - cJ) x = b is solved EXACTLY by
 //       x = A^-1 b + c (G z) . w,      w = A^-1 e_R,  A = I - c J_blk  (tree elimination per protein)
 //       (I - c diag(m) G) z = z0,      z0_i = 1^T [A^-1 b]_protein i,   m_i = 1^T w_i
-//   i.e. one dense LU of size |Q| x |Q| (Q = non-driven proteins that regulate someone, ~N) instead
+//   i.e. one dense inverse of size |Q| x |Q| (Q = non-driven proteins that regulate someone, ~N; register-resident
+//   Gauss-Jordan up to 128, LU in shared memory or - capacity fallback - in an L2-resident scratch beyond) instead
 //   of state_dim x state_dim (~4-5 N): ~70x fewer flops than the reference's dense Jacobian route.
 //
 // Integrator: staged RODAS4 (Hairer & Wanner, 6 stages, order 4(3), stiffly accurate, L-stable) with

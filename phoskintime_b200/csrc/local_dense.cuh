@@ -1,15 +1,17 @@
-// Warp-per-system kernel with a dense shared-memory inverse: the random (2^ns-state hypercube)
-// model (models/randmod.py) and distributive / successive systems too large for the
-// register-resident kernel.  One warp owns one system: W = I - h*gamma*M is assembled in shared
-// memory from the analytic Jacobian (the models are linear, M is the transition-rate matrix) and
-// INVERTED in place (Gauss-Jordan, lanes own columns, no pivoting: for non-negative rates W is
-// strictly column diagonally dominant once the decoupled mRNA row is removed; zero multipliers are
-// skipped, so the early sparse columns are cheap).  The six Krylov vectors of a step, v_k = W^-1
-// v_{k-1}, are then lane-parallel mat-vecs instead of sequential triangular solves, and — because
-// the models are linear with constant coefficients — W^-1 depends on the step size only: proposed
-// steps are rounded down to a geometric grid (ratio 2^(1/HQ)), so consecutive steps share one
-// inverse and a solve needs ~50 inversions for ~120 steps.  Warps pull systems from the global
-// queue as they finish.
+// Dense-inverse kernels for the random (2^ns-state hypercube) model (models/randmod.py) and for distributive /
+// successive systems too large for the thread-per-system kernel.  1, 2 or 4 warps own one system: W = I - h*gamma*M is
+// assembled in shared memory from the analytic Jacobian (the models are linear, M is the transition-rate matrix) and
+// INVERTED (Gauss-Jordan, no pivoting: for non-negative rates W is strictly column diagonally dominant once the decoupled
+// mRNA row is removed).  The six (ROS5L) or seven (ROS6L) Krylov vectors of a step, v_k = W^-1 v_{k-1}, are then
+// mat-vecs instead of sequential triangular solves, and - because the models are linear with constant coefficients -
+// W^-1 depends on the step size only: proposed steps are quantised (mantissa bits cleared), forced shorter steps reuse
+// the inverse through the run-time gamma' family of the method (rosl_coeffs), so a rand-6 solve needs ~19 inversions for
+// ~154 steps.  Two storage variants:
+//   * shared-memory inverse (dense_invert / dense_apply): random model up to 7 sites (129 states), distributive / successive
+//     beyond 8 sites;
+//   * register-resident inverse for 41..68 states (local_dense_kernel<MODEL, 128, 3, 17>: reg_load / reg_invert /
+//     reg_apply below), the default for rand-6.
+// Thread groups pull systems from the global queue as they finish.
 #pragma once
 #include "pk_common.cuh"
 

@@ -301,6 +301,33 @@ def test_fused_gather_single_rank(engine):
         assert torch.equal(b["gathered"], a[key])
 
 
+def test_peer_memory_gather_single_rank(engine):
+    """pk_local_solve_gather_p2p at world 1 (pk_sym_alloc / pk_sym_buffer, the kernel's finish stage stores every system's
+    scalar into the symmetric buffer): row 0 of the buffer equals the requested per-sample output bit for bit, every
+    other output equals the plain call's.  (Two and eight ranks: tools/multi_gpu_check.py, profiles/r2_bench_*gpu_p2p.json.)"""
+    import torch
+    B = 40_007
+    rng = np.random.default_rng(19)
+    p = torch.from_numpy(rng.uniform(0.05, 3.0, (B, 14))).cuda()
+    y0 = torch.from_numpy(rng.uniform(0.1, 1.0, (B, 7))).cuda()
+    t = torch.from_numpy(T14).cuda()
+    tg = torch.from_numpy(rng.random(93)).cuda()
+    a = engine.solve_local_batch("succmod", p, y0, 5, t, want=("ssr", "score", "Y"), target=tg)
+    view = engine.sym_setup(B + 5, lambda h: [h])
+    assert tuple(view.shape) == (1, B + 5)
+    try:
+        for key in ("score", "ssr", "Y"):
+            view.fill_(-1.0)
+            b = engine.solve_local_batch("succmod", p, y0, 5, t, want=("ssr", "score", "Y"), target=tg, gather_p2p=key)
+            assert torch.equal(b["gathered"][0, :B], a[key]), key
+            assert bool((b["gathered"][0, B:] == -1.0).all())
+            for k in ("ssr", "score", "Y", "status", "nsteps", "nrej"):
+                assert torch.equal(a[k], b[k]), k
+    finally:
+        engine.lib.pk_sym_free(engine._h)
+        engine._sym = None
+
+
 def test_large_batch_properties(engine):
     """Size-independent checks at bench scale (2^18 systems): steady states stay put, the flow is
     a semigroup (solve to t1 then on to t2 == solve to t2), and the map is affine in (A, y0)."""
