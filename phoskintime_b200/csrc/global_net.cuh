@@ -84,6 +84,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int n_big;                        // model 2: proteins with more than 4 sites (first n_big entries of the size order)
     int big_nst;                      // model 2: largest pattern block (states) among them, 0 if none
     int binv_total;                   // model 2: sum of 4^ns (doubles); the 8 pivot-row snapshots of the big path follow it
+    int cls16, cls8, cls4;            // model 2: ends (in the size order) of the 16-, 8- and 4-pattern classes; 2/1 patterns follow
 };
 constexpr int OVF_BASE = 1 << 28;
 
@@ -349,7 +350,8 @@ struct GlobalCtx {
     const int* cord;                  // proteins ordered by block size (descending): the two blocks a warp inverts together
                                       // are of (nearly) equal size, so neither half-warp idles through the other's columns
     int n_big, big_nst, binv_total;   // blocks of more than 16 patterns: cord[0 .. n_big), one warp each (comb_factor_big)
-    double* cscr;                     // model 2: [16 half-warps][16] pivot-row strips of comb_factor
+    double* cscr;                     // model 2: 256 doubles of pivot-row strips of comb_factor (W per group of W lanes)
+    int cls16, cls8, cls4;            // ends of the size classes in the order cord (after the n_big large blocks)
 };
 
 
@@ -465,25 +467,26 @@ __device__ __forceinline__ void comb_block_solve_big(const GlobalCtx& cx, double
 
 // Inverses of all pattern blocks for c = gamma*h, the unit responses w of the pattern states and m_i.
 // Needs facA[st] = 1/(1 + c B) and mult[st+1] = c C (written by eval_rhs_comb) behind a barrier.
-__device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
-    const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
-    const int N = cx.N;
-    if (cx.n_big > 0) comb_factor_big(cx, c);
-    // The pivot row of every column reaches the 16 lanes of a block through a 16-double strip in shared memory (the owner
-    // lane stores it with 8 STS.128, everybody reads it back with 8 broadcast LDS.128) instead of 32 shuffles: the SM
-    // moves ONE warp shuffle per cycle, and 8 warps x 32 shuffles per column made the elimination shuffle-throughput
-    // bound (trace, N = 120: 63 k cycles per step; interleaving two blocks per half-warp changed nothing).
-    double2* const strip = (double2*)(cx.cscr + grp * COMB_MAX_STATES);
-    for (int i0 = cx.n_big; i0 < N; i0 += 16) {
-        const bool act = i0 + grp < N;
+// One size class of pattern blocks: W = 2^ns lanes per block (lane = row), GLOBAL_BLOCK / W blocks per pass - a block of
+// 4 patterns no longer occupies the 16 lanes (and the 16 elimination columns) of a 16-pattern one (round 2: the passes
+// over N = 120 proteins with 1..4 sites drop from 8 to ~4).
+// The pivot row of every column reaches the W lanes of a block through a W-double strip in shared memory (the owner
+// lane stores it, everybody reads it back with broadcast loads) instead of 2 W shuffles: the SM moves ONE warp shuffle
+// per cycle.
+template <int W>
+__device__ __forceinline__ void comb_factor_w(const GlobalCtx& cx, double c, int first, int last) {
+    constexpr int G = GLOBAL_BLOCK / W;
+    const int r = threadIdx.x & (W - 1), grp = threadIdx.x / W;
+    double2* const strip = (double2*)(cx.cscr + grp * W);
+    for (int i0 = first; i0 < last; i0 += G) {
+        const bool act = i0 + grp < last;
         const int i = act ? cx.cord[i0 + grp] : 0;
         const int ns = act ? cx.ns[i] : 0, st = act ? cx.offy[i] : 0, ss = act ? cx.offs[i] : 0;
-        const int nst = act ? (1 << ns) : 0;
-        const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));     // the two halves of a warp step together
+        const int nst = act ? (1 << ns) : 0;                                  // == W (1 or 2 in the last class)
         const bool live = r < nst;
-        double a[COMB_MAX_STATES];                                            // row r of M (identity outside the block)
+        double a[W];                                                          // row r of M (identity outside the block)
 #pragma unroll
-        for (int q = 0; q < COMB_MAX_STATES; ++q) a[q] = (q == r) ? 1.0 : 0.0;
+        for (int q = 0; q < W; ++q) a[q] = (q == r) ? 1.0 : 0.0;
         if (live) {
             const double Di = cx.cD[i], Ei = cx.cE[i];
             double out = (r == 0) ? Di : 0.0;
@@ -495,95 +498,96 @@ __device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
                 const int col = r ^ bit;
                 const double v = -c * (set ? s : Ei);
 #pragma unroll
-                for (int q = 0; q < COMB_MAX_STATES; ++q)
+                for (int q = 0; q < W; ++q)
                     if (q == col) a[q] = v;
             }
             const double dg = fma(c, out, 1.0);
 #pragma unroll
-            for (int q = 0; q < COMB_MAX_STATES; ++q)
+            for (int q = 0; q < W; ++q)
                 if (q == r) a[q] = dg;
         }
 #pragma unroll
-        for (int k = 0; k < COMB_MAX_STATES; ++k) {
-            if (k < smax) {
-                const bool me = r == k;
-                if (me) {
+        for (int k = 0; k < W; ++k) {
+            const bool me = r == k;
+            if (me) {
 #pragma unroll
-                    for (int q = 0; q < COMB_MAX_STATES; q += 2) strip[q >> 1] = make_double2(a[q], a[q + 1]);
-                }
-                __syncwarp();
-                double prow[COMB_MAX_STATES];
-#pragma unroll
-                for (int q = 0; q < COMB_MAX_STATES; q += 2) {
-                    const double2 v = strip[q >> 1];
-                    prow[q] = v.x;
-                    prow[q + 1] = v.y;
-                }
-                __syncwarp();                                    // the strip is rewritten by the next column's owner
-                const double p = fast_rcp(prow[k]);
-                const double coef = me ? p : -a[k] * p;          // pivot row: row/pivot; other rows: -multiplier
-#pragma unroll
-                for (int q = 0; q < COMB_MAX_STATES; ++q)
-                    if (q != k) a[q] = fma(coef, prow[q], me ? 0.0 : a[q]);
-                a[k] = coef;
+                for (int q = 0; q < W; q += 2) strip[q >> 1] = make_double2(a[q], a[q + 1]);
             }
+            __syncwarp();
+            double prow[W];
+#pragma unroll
+            for (int q = 0; q < W; q += 2) {
+                const double2 v = strip[q >> 1];
+                prow[q] = v.x;
+                prow[q + 1] = v.y;
+            }
+            __syncwarp();                                        // the strip is rewritten by the next column's owner
+            const double p = fast_rcp(prow[k]);
+            const double coef = me ? p : -a[k] * p;              // pivot row: row/pivot; other rows: -multiplier
+#pragma unroll
+            for (int q = 0; q < W; ++q)
+                if (q != k) a[q] = fma(coef, prow[q], me ? 0.0 : a[q]);
+            a[k] = coef;
         }
         double wr = 0.0;
         if (live) {
             double* bi = cx.binv + cx.boff[i];
 #pragma unroll
-            for (int q = 0; q < COMB_MAX_STATES; ++q)
+            for (int q = 0; q < W; ++q)
                 if (q < nst) bi[q * nst + r] = a[q];              // element (r, q): lanes r contiguous
             wr = a[0] * cx.mult[st + 1] * cx.facA[st];            // response of pattern r to a unit mRNA source
             cx.w[st + 1 + r] = wr;
         }
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) wr += __shfl_xor_sync(0xffffffffu, wr, o);
+        for (int o = W / 2; o > 0; o >>= 1) wr += __shfl_xor_sync(0xffffffffu, wr, o);
         if (act && r == 0) cx.m[i] = wr;
     }
 }
 
+__device__ __forceinline__ void comb_factor(const GlobalCtx& cx, double c) {
+    if (cx.n_big > 0) comb_factor_big(cx, c);
+    comb_factor_w<16>(cx, c, cx.n_big, cx.cls16);
+    comb_factor_w<8>(cx, c, cx.cls16, cx.cls8);
+    comb_factor_w<4>(cx, c, cx.cls8, cx.cls4);
+    comb_factor_w<2>(cx, c, cx.cls4, cx.N);
+}
+
 // x0 = A^-1 b for the combinatorial blocks (in place), z0_i = total-protein part into pvec, z cleared
-__device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x) {
-    const int r = threadIdx.x & 15, grp = threadIdx.x >> 4;
-    const int N = cx.N;
-    if (cx.n_big > 0) comb_block_solve_big(cx, x);
-    for (int i0 = cx.n_big; i0 < N; i0 += 16) {
-        const bool act = i0 + grp < N;
+template <int W>
+__device__ __forceinline__ void comb_block_solve_w(const GlobalCtx& cx, double* x, int first, int last) {
+    constexpr int G = GLOBAL_BLOCK / W;
+    const int r = threadIdx.x & (W - 1), grp = threadIdx.x / W;
+    for (int i0 = first; i0 < last; i0 += G) {
+        const bool act = i0 + grp < last;
         const int i = act ? cx.cord[i0 + grp] : 0;
         const int st = act ? cx.offy[i] : 0;
         const int nst = act ? (1 << cx.ns[i]) : 0;
-        const int smax = max(nst, __shfl_xor_sync(0xffffffffu, nst, 16));
         const bool live = r < nst;
-        double xr = 0.0, b = 0.0;
-        if (act) {
-            xr = x[st] * cx.facA[st];
-            if (live) b = x[st + 1 + r];
-            if (r == 0) b = fma(cx.mult[st + 1], xr, b);          // translation feeds pattern 0
-        }
-        // row r of the block inverse first: 16 independent (clamped, unconditional) loads in flight at once - the inverses
-        // live in L2, and a load issued inside the shuffle loop below exposed one L2 round trip per term (trace, N = 120:
+        // row r of the block inverse first: W independent (clamped, unconditional) loads in flight at once - the inverses
+        // live in L2, and a load issued inside the accumulation loop exposed one L2 round trip per term (trace, N = 120:
         // 18 k cycles per solve, 28 % of the step)
         const double* bi = cx.binv + (act ? cx.boff[i] : 0);
-        double mrow[COMB_MAX_STATES];
+        double mrow[W];
 #pragma unroll
-        for (int q = 0; q < COMB_MAX_STATES; ++q) {
+        for (int q = 0; q < W; ++q) {
             const bool ok = live && q < nst;
             const double v = bi[ok ? q * nst + r : 0];
             mrow[q] = ok ? v : 0.0;
         }
-        // right-hand side entries straight from shared memory (one broadcast load per term instead of two shuffles: the
-        // SM moves one warp shuffle per cycle, and 8 warps x 32 of them per pass were the pass)
-        double acc = mrow[0] * __shfl_sync(0xffffffffu, b, 0, 16);           // b_0 carries the translation term
+        double xr = 0.0, b0 = 0.0;
+        if (act) {
+            xr = x[st] * cx.facA[st];
+            b0 = fma(cx.mult[st + 1], xr, x[st + 1]);              // translation feeds pattern 0
+        }
+        // right-hand side entries straight from shared memory (one broadcast load per term instead of two shuffles)
+        double acc = mrow[0] * b0;
         const double* xb = x + st + 1;
 #pragma unroll
-        for (int q = 1; q < COMB_MAX_STATES; ++q) {
-            if (q < smax) acc = fma(mrow[q], xb[q < nst ? q : 0], acc);       // mrow[q] = 0 beyond the block
-        }
+        for (int q = 1; q < W; ++q) acc = fma(mrow[q], xb[q < nst ? q : 0], acc);       // mrow[q] = 0 beyond the block
         __syncwarp();                                                        // every lane has read x before anyone overwrites it
         double zs = live ? acc : 0.0;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
+        for (int o = W / 2; o > 0; o >>= 1) zs += __shfl_xor_sync(0xffffffffu, zs, o);
         if (live) x[st + 1 + r] = acc;
         if (act && r == 0) {
             x[st] = xr;
@@ -591,6 +595,14 @@ __device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x)
             cx.z[i] = 0.0;
         }
     }
+}
+
+__device__ __forceinline__ void comb_block_solve(const GlobalCtx& cx, double* x) {
+    if (cx.n_big > 0) comb_block_solve_big(cx, x);
+    comb_block_solve_w<16>(cx, x, cx.n_big, cx.cls16);
+    comb_block_solve_w<8>(cx, x, cx.cls16, cx.cls8);
+    comb_block_solve_w<4>(cx, x, cx.cls8, cx.cls4);
+    comb_block_solve_w<2>(cx, x, cx.cls4, cx.N);
 }
 
 template <bool FACTOR>
@@ -1133,7 +1145,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                  smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
                  a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord,
-                 L.n_big, L.big_nst, L.binv_total, smem + L.cscr};
+                 L.n_big, L.big_nst, L.binv_total, smem + L.cscr, L.cls16, L.cls8, L.cls4};
 #undef at
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;

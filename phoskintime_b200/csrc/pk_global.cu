@@ -76,9 +76,9 @@ int bucket_of(double t, const std::vector<double>& g) {       // jacspeedup.py:1
 void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic, int spill) {
     const pk::GlobalTopoDev& d = th->dev;
     pk::GlobalSmem& L = th->sm;
-    const int n_big = L.n_big, big_nst = L.big_nst, binv_total = L.binv_total;
+    const int n_big = L.n_big, big_nst = L.big_nst, binv_total = L.binv_total, c16 = L.cls16, c8 = L.cls8, c4 = L.cls4;
     memset(&L, 0, sizeof(L));
-    L.n_big = n_big; L.big_nst = big_nst; L.binv_total = binv_total;
+    L.n_big = n_big; L.big_nst = big_nst; L.binv_total = binv_total; L.cls16 = c16; L.cls8 = c8; L.cls4 = c4;
     int o = 0, og = 0, rank = 0;
     auto take = [&](int count) {
         const int at = o;
@@ -278,6 +278,14 @@ int pk_global_upload(pk_handle_t h, const pk_global_topology* tp, int32_t* topo_
     }
     th->sm.n_big = n_big;
     th->sm.big_nst = big_nst;
+    {   // size classes of the register path in the kernel's order (larger blocks first): 16, 8, 4 patterns, then 2 / 1
+        int cnt[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < N; ++i)
+            if (comb && tp->n_sites[i] <= 4) ++cnt[tp->n_sites[i]];
+        th->sm.cls16 = n_big + cnt[4];
+        th->sm.cls8 = th->sm.cls16 + cnt[3];
+        th->sm.cls4 = th->sm.cls8 + cnt[2];
+    }
     th->sm.binv_total = (int)binv_elems;
     th->binv_elems = binv_elems + (size_t)pk::GLOBAL_WARPS * big_nst;     // + one pivot-row snapshot strip per warp
     th->kin_grid.assign(tp->kin_grid, tp->kin_grid + nb);
