@@ -312,6 +312,10 @@ int pk_global_dims(pk_handle_t h, int32_t topo_id, int32_t* state_dim, int32_t* 
 int pk_global_counts(pk_handle_t h, int32_t topo_id, int32_t* n_proteins, int32_t* n_kinases, int32_t* total_sites);
 void pk_global_job_init(pk_global_job* job);
 int pk_sizeof_global_job(void);
+/* The linear systems of a step are solved through the Schur complement on the regulator set: by fixed-point sweeps to an
+ * error bound of 1e-12 when the infinity norm of its iteration matrix is below 0.5 (most steps), by an exact dense
+ * inverse otherwise.  Environment PHOSKIN_SCHUR_ITER=<norm bound> overrides the 0.5 (0 = exact inverse in every step;
+ * the parity tests compare the two). */
 int pk_global_solve_batch(pk_handle_t h, const pk_global_job* job);
 /* LOSS_FN(Y, tables...) (global_model/lossfn.py:113-121, dispatch :386) on B trajectories that already
  * exist: Y [B,T,state_dim] -> out_loss [B,3] = (loss_p, loss_r, loss_ph) raw weighted sums. */

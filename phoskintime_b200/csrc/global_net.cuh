@@ -78,6 +78,7 @@ struct GlobalSmem {                   // offsets in doubles unless stated
     int ints;                         // start of the int region (offset in doubles); the i_* below are int offsets into it
     int i_offy, i_offs, i_ns, i_drv, i_tfptr, i_tfidx, i_qlist, i_qpos, i_piv, i_pinv, i_sprot, i_ent, i_boff, i_cord;
     int cscr;                         // model 2: pivot-row strips of comb_factor (16 x 16 doubles, 16-byte aligned)
+    int z2, fz, rabs;                 // iterative Schur solve: second iterate, row factors c m_i g_i, row sums of |TF| over Q
     int tile;                         // 0 (generic) or 2/4/6/8: the 16x16 thread grid owns TILE x TILE entries each
     int ovf_total;                    // capacity fallback: doubles of per-CTA global (L2-resident) scratch; an array whose offset is
                                       // >= OVF_BASE lives there (at offset - OVF_BASE) instead of in shared memory
@@ -112,6 +113,7 @@ struct GlobalArgs {
     double* binv;                     // [grid][binv_stride] model 2: inverses of the per-protein pattern blocks
     long long binv_stride;
     double* ovf;                      // [grid][sm.ovf_total] arrays that did not fit into shared memory (OVF instantiations)
+    double schur_iter_max;            // steps with ||K||_inf below this solve their Schur systems by fixed-point sweeps (0: never)
     unsigned long long* counter;
 };
 
@@ -328,6 +330,7 @@ struct StepState {                    // step controller of the system a CTA is 
     double hh;                        // size of the attempt in flight (h clamped to land on the next stop)
     float hacc, erracc;
     int naccpt, rejected_last, nst, nrej, status, land;
+    int itK;                          // > 0: the Schur systems of this step are solved by itK fixed-point sweeps (schur_neumann)
 };
 
 struct GlobalCtx {
@@ -352,6 +355,7 @@ struct GlobalCtx {
     int n_big, big_nst, binv_total;   // blocks of more than 16 patterns: cord[0 .. n_big), one warp each (comb_factor_big)
     double* cscr;                     // model 2: 256 doubles of pivot-row strips of comb_factor (W per group of W lanes)
     int cls16, cls8, cls4;            // ends of the size classes in the order cord (after the n_big large blocks)
+    double *z2, *fz, *rabs;           // iterative Schur solve (schur_neumann)
 };
 
 
@@ -1056,9 +1060,72 @@ __device__ __forceinline__ void lu_apply(const GlobalCtx& cx) {
     __syncthreads();
 }
 
+// Iterative Schur solve (round 2).  The Schur system is  z = z0 + K z  with  K = c diag(m g) G_QQ,  and G has ~4 entries
+// per row: when ||K||_inf = max_i |c m_i g_i| sum_j |G_ij| is below 0.6 (checked per step from a row-sum table, one block
+// reduction), the fixed point is reached by sweeps  z <- z0 + K z  - a sparse mat-vec by N threads and one barrier each -
+// and the error after k sweeps is bounded by ||K||^k / (1 - ||K||) ||z0||: the sweep count is chosen per step so that this
+// bound is 1e-12, far below the step's own tolerance.  A step whose six stage systems are solved this way needs NO
+// inversion (99 k of the 153 k cycles of a step at N = 120) and no dense apply.  Steps with ||K|| >= 0.6 (very large steps:
+// c m_i tends to C/(B D)) take the exact register Gauss-Jordan path as before.
+// z0 = cx.pvec (totals of the block solves); iterates alternate between cx.z and cx.z2 (entries outside Q stay 0);
+// itK is even, so the result lands in cx.z.
+__device__ __forceinline__ void schur_neumann(const GlobalCtx& cx, int itK) {
+    const int N = cx.N;
+    for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) cx.z[i] = cx.qpos[i] >= 0 ? cx.pvec[i] : 0.0;
+    __syncthreads();
+    // two lanes per row; with N <= 128 rows (one pass) the lane's share of its row - up to 4 {weight, column} pairs, the row
+    // factor and z0 - is loaded into registers ONCE per solve, so a sweep is 4 independent gathers, 4 FMAs, one shuffle, one
+    // store and the barrier (before: a chain of ~10 dependent shared-memory loads per sweep, ~900 cycles)
+    const int sub = threadIdx.x & 1, row0 = threadIdx.x >> 1;
+    if (N <= GLOBAL_BLOCK / 2) {
+        const bool in = row0 < N;
+        const int ii = in ? row0 : 0;
+        const bool live = in && cx.qpos[ii] >= 0;
+        const int qb = cx.tfptr[ii] + sub, qe = live ? cx.tfptr[ii + 1] : 0;
+        double cw[4];
+        int ci[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int q = qb + 2 * t;
+            const bool ok = q < qe;
+            cw[t] = ok ? cx.tfdata[ok ? q : 0] : 0.0;
+            ci[t] = ok ? cx.tfidx[ok ? q : 0] : 0;
+        }
+        const double fzi = live ? cx.fz[ii] : 0.0, z0i = live ? cx.pvec[ii] : 0.0;
+#pragma unroll 1
+        for (int it = 0; it < itK; ++it) {
+            const double* src = (it & 1) ? cx.z2 : cx.z;
+            double* dst = (it & 1) ? cx.z : cx.z2;
+            double acc = fma(cw[0], src[ci[0]], fma(cw[1], src[ci[1]], fma(cw[2], src[ci[2]], cw[3] * src[ci[3]])));
+            for (int q = qb + 8; q < qe; q += 2) acc = fma(cx.tfdata[q], src[cx.tfidx[q]], acc);      // rows beyond 8 entries
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (in && sub == 0) dst[ii] = fma(fzi, acc, z0i);
+            __syncthreads();
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int it = 0; it < itK; ++it) {
+        const double* src = (it & 1) ? cx.z2 : cx.z;
+        double* dst = (it & 1) ? cx.z : cx.z2;
+        for (int base = 0; base < N; base += GLOBAL_BLOCK / 2) {           // uniform trip count: the shuffle below is warp-wide
+            const int i = base + row0;
+            const bool in = i < N;
+            const int ii = in ? i : 0;
+            const bool live = in && cx.qpos[ii] >= 0;
+            double acc = 0.0;
+            if (live)
+                for (int q = cx.tfptr[ii] + sub; q < cx.tfptr[ii + 1]; q += 2) acc = fma(cx.tfdata[q], src[cx.tfidx[q]], acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (in && sub == 0) dst[ii] = live ? fma(cx.fz[ii], acc, cx.pvec[ii]) : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
 // x (vector in shared memory, holds the right-hand side b) <- (I - cJ)^-1 b
 template <int TILE, bool COMB>
-__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1]
+__device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, double c, const double (&A)[TILE ? TILE : 1][TILE ? TILE : 1], int itK
 #ifdef PK_GLOBAL_TRACE
                                             , long long& ph_last_
 #endif
@@ -1094,7 +1161,8 @@ __device__ __forceinline__ void schur_solve(const GlobalCtx& cx, double* x, doub
     __syncthreads();
     PH(10);
     if (cx.nQ > 0) {
-        if constexpr (TILE > 0) gj_apply<TILE>(cx, A);
+        if (itK > 0) schur_neumann(cx, itK);
+        else if constexpr (TILE > 0) gj_apply<TILE>(cx, A);
         else lu_apply(cx);
     }
     PH(11);
@@ -1145,7 +1213,8 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                  smem + L.tfdata, smem + L.tfdeg,
                  smem + L.colbuf, smem + L.rowbuf, smem + L.bp, smem + L.partial, ismem + L.i_piv, ismem + L.i_pinv,
                  a.binv ? a.binv + (size_t)blockIdx.x * a.binv_stride : nullptr, ismem + L.i_boff, ismem + L.i_cord,
-                 L.n_big, L.big_nst, L.binv_total, smem + L.cscr, L.cls16, L.cls8, L.cls4};
+                 L.n_big, L.big_nst, L.binv_total, smem + L.cscr, L.cls16, L.cls8, L.cls4,
+                 smem + L.z2, smem + L.fz, smem + L.rabs};
 #undef at
     cx.cA = cx.par + K;
     cx.cB = cx.cA + N;
@@ -1177,6 +1246,13 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
             smem[L.tfdata + q] = tp.TF_data[q];
         }
         for (int q = threadIdx.x; q < tp.nQ; q += GLOBAL_BLOCK) ismem[L.i_qlist + q] = tp.qlist[q];
+        for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {          // row sums of |TF| over the regulator set (schur_neumann)
+            double rs = 0.0;
+            if (tp.qpos[i] >= 0)
+                for (int q = tp.TF_indptr[i]; q < tp.TF_indptr[i + 1]; ++q)
+                    if (tp.qpos[tp.TF_indices[q]] >= 0) rs += fabs(tp.TF_data[q]);
+            smem[L.rabs + i] = rs;
+        }
         for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {          // state -> protein map
             const int st = tp.offset_y[i], ns = tp.n_sites[i];
             const int bl = tp.model == 2 ? 1 + (1 << ns) : 2 + ns;
@@ -1312,12 +1388,34 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                 eval_rhs<true, COMB>(cx, y, U, STEP_C);
                 PH(1);
                 if (cx.nQ > 0) {
-                    if constexpr (TILE > 0) {
-                        gj_assemble<TILE>(cx, STEP_C, A);
-                        PH(2);
-                        gj_invert<TILE>(cx, A);
-                    } else {
-                        schur_factor(cx, STEP_C);
+                    // ||K||_inf of this step's Schur system and the sweep count that brings the fixed-point error bound to 1e-12
+                    float kn = 0.f;
+                    {
+                        const double c = STEP_C;
+                        for (int i = threadIdx.x; i < N; i += GLOBAL_BLOCK) {
+                            const double f = c * cx.m[i] * cx.g[i];
+                            cx.fz[i] = f;
+                            kn = fmaxf(kn, (float)(fabs(f) * cx.rabs[i]) * 1.0001f);
+                        }
+                    }
+                    const float KN = (float)block_max_f(kn, cx.red);
+                    if (threadIdx.x == 0) {
+                        int K = 0;
+                        if (a.schur_iter_max > 0.0 && KN < (float)a.schur_iter_max) {      // false for NaN
+                            K = KN < 1e-30f ? 2 : (int)ceilf(__logf(1e-12f * (1.0f - KN)) / __logf(KN));
+                            K = max(2, (K + 1) & ~1);
+                        }
+                        S_.itK = K;
+                    }
+                    __syncthreads();
+                    if (S_.itK == 0) {
+                        if constexpr (TILE > 0) {
+                            gj_assemble<TILE>(cx, STEP_C, A);
+                            PH(2);
+                            gj_invert<TILE>(cx, A);
+                        } else {
+                            schur_factor(cx, STEP_C);
+                        }
                     }
                 }
                 PH(3);
@@ -1327,7 +1425,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                 }
                 __syncthreads();
                 PH(4);
-                schur_solve<TILE, COMB>(cx, U, STEP_C, A PH_ARG);
+                schur_solve<TILE, COMB>(cx, U, STEP_C, A, S_.itK PH_ARG);
                 // stages 2..6:  (I - cJ) U_s = c ( f(y + sum a_sj U_j) + sum c_sj/h U_j )
 #pragma unroll 1
                 for (int s = 1; s < 6; ++s) {
@@ -1360,7 +1458,7 @@ __global__ void __launch_bounds__(GLOBAL_BLOCK, (TILE >= 1 && TILE <= 6 && !COMB
                     });
                     __syncthreads();
                     PH(7);
-                    schur_solve<TILE, COMB>(cx, Us, STEP_C, A PH_ARG);
+                    schur_solve<TILE, COMB>(cx, Us, STEP_C, A, S_.itK PH_ARG);
                 }
                 // y_new = arg_6 + U_6, err = U_6
                 float err = 0.f;

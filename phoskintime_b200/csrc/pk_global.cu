@@ -114,6 +114,9 @@ void layout_smem(GlobalTopoHost* th, int nnzT, int force_generic, int spill) {
     L.tfdata = take(nnzT);
     L.tfdeg = take(N);
     L.cscr = take(d.model == 2 ? 16 * pk::COMB_MAX_STATES : 0);        // even offsets: 16-byte aligned strips
+    L.z2 = take(N);
+    L.fz = take(N);
+    L.rabs = take(N);
     if (L.tile == 0) {
         L.ld = nQ | 1;                               // odd leading dimension: conflict-free column walks
         L.Sc = take_big(nQ * L.ld, 0);
@@ -529,6 +532,11 @@ int pk_global_solve_batch(pk_handle_t h, const pk_global_job* j) {
     a.lam_prior = j->lambda_prior;
     a.y0_stride = j->y0_stride;
     a.nfc = (long long)nfc;
+    {   // fixed-point Schur solves below this ||K||_inf (global_net.cuh: schur_neumann); PHOSKIN_SCHUR_ITER=0 forces the
+        // exact inversion in every step (tests compare the two paths)
+        const char* ev = getenv("PHOSKIN_SCHUR_ITER");
+        a.schur_iter_max = ev ? atof(ev) : 0.5;
+    }
     a.counter = h->counter;
 
     const pkh::global_kernel_t kern = pkh::kernel_for_tile(th->sm.tile, d.model == 2, th->sm.ovf_total > 0);

@@ -204,6 +204,24 @@ def test_capacity_fallback_layout_is_bit_identical(engine, name):
     assert _ratio(out[2]["Y"], g["Y_tight"], 1e-6, 1e-9) <= 0.5
 
 
+@pytest.mark.parametrize("name", ["m0_N36", "m0_N120", "m1_N14", "m4_N14", "m2_N10", "m2_N24", "m0_N300"])
+def test_iterative_schur_solve_equals_exact_inversion(engine, name, monkeypatch):
+    """Steps whose Schur system has ||K||_inf < 0.5 solve it by fixed-point sweeps to a bound of 1e-12 instead of the
+    register Gauss-Jordan inverse (csrc/global_net.cuh: schur_neumann).  PHOSKIN_SCHUR_ITER=0 forces the exact inversion in
+    every step: same accepted / rejected step counts and trajectories equal to 1e-9 relative (+1e-12) - two decades below the
+    step's own tolerance, three below the parity bound."""
+    g, s, _ = load_case(os.path.join(GOLDEN, f"global_{name}.npz"))
+    P = g["params"][:2]
+    monkeypatch.setenv("PHOSKIN_SCHUR_ITER", "0")
+    exact = simulate_batch(s, P, g["t"], ("Y",), y0=g["y0"], engine=engine)
+    monkeypatch.delenv("PHOSKIN_SCHUR_ITER")
+    it = simulate_batch(s, P, g["t"], ("Y",), y0=g["y0"], engine=engine)
+    assert (exact["status"] == 0).all() and (it["status"] == 0).all()
+    assert np.array_equal(exact["nsteps"], it["nsteps"]) and np.array_equal(exact["nrej"], it["nrej"])
+    assert np.all(np.abs(it["Y"] - exact["Y"]) <= 1e-9 * np.abs(exact["Y"]) + 1e-12), _ratio(it["Y"], exact["Y"], 1e-9, 1e-12)
+    assert _ratio(it["Y"], g["Y_tight"][:2], 1e-6, 1e-9) <= 1.0
+
+
 def test_network_beyond_one_cta_runs(engine):
     """N = 300 proteins (1371 states, 2332 parameters, 254 regulators): the Schur block alone (254 x 255 doubles = 518 KB)
     exceeds a CTA's 227 KB, so the upload must choose the overflow layout by itself instead of refusing; the trajectories are
