@@ -139,3 +139,35 @@ def test_no_gpu_global_calls_fail_loudly():
     s = synthetic_system(seed=1, N=6, K=3, max_sites=2)
     with pytest.raises(pk.PhoskinError):
         simulate_odeint(s, T15, 1e-6, 1e-9, 1000)
+
+
+def test_fixed_point_schur_bound_and_sweep_count():
+    """The algorithm behind csrc/global_net.cuh::schur_neumann, restated in numpy: for K = diag(f) G_QQ with
+    ||K||_inf < 0.5 the sweeps z <- z0 + K z started from z0 reach the solution of (I - K) z = z0 to 1e-12 relative within the
+    sweep count the kernel derives from the norm bound ||K||^k / (1 - ||K||)."""
+    s = synthetic_system(seed=5, N=120, K=40, max_sites=4)
+    N = s.idx.N
+    G = np.zeros((N, N))
+    for i in range(N):
+        for q in range(s.TF_indptr[i], s.TF_indptr[i + 1]):
+            G[i, s.TF_indices[q]] += s.TF_data[q]
+    used = (np.abs(G).sum(axis=0) > 0) & (np.asarray(s.driver_map) < 0)        # regulator set Q: non-driven regulators
+    Q = np.flatnonzero(used)
+    Gq = G[np.ix_(Q, Q)]
+    rabs = np.abs(Gq).sum(axis=1)
+    rng = np.random.default_rng(3)
+    for target in (0.05, 0.2, 0.49):
+        f = rng.uniform(-1.0, 1.0, Q.size)
+        f *= target / np.max(np.abs(f) * rabs)                                   # scale the row factors to the wanted norm
+        Kmat = f[:, None] * Gq
+        kn = float(np.max(np.abs(f) * rabs)) * 1.0001
+        assert abs(np.abs(Kmat).sum(axis=1).max() * 1.0001 - kn) < 1e-12
+        k_it = int(np.ceil(np.log(1e-12 * (1.0 - kn)) / np.log(kn)))
+        k_it = max(2, (k_it + 1) & ~1)
+        z0 = rng.standard_normal(Q.size)
+        z = z0.copy()
+        for _ in range(k_it):
+            z = z0 + Kmat @ z
+        exact = np.linalg.solve(np.eye(Q.size) - Kmat, z0)
+        assert np.max(np.abs(z - exact)) <= 1e-12 * np.max(np.abs(z0)) * 1.01, (target, k_it)
+        assert k_it <= 42
